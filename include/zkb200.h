@@ -1,0 +1,193 @@
+/* zkb200.h - C ABI of libzkb200.so: the B200-native NTT / coset-LDE / Merkle / FRI engine
+ * that sits behind the function signatures of SpekalsG3/zk-stark-tutor's hot path.
+ *
+ * The reference is a Rust crate with NO FFI of its own; its "interface" for this path is a
+ * set of plain `pub fn`s.  Each entry point below names the reference function whose BODY
+ * it replaces (file:line inside the reference).  INTEGRATION.md shows the Rust-side
+ * `extern "C"` block and the shim bodies a maintainer would add.
+ *
+ * Conventions
+ *  - A field element is 16 bytes, little-endian u128, canonical (< p = 1 + 407*2^119):
+ *    the same bytes as Rust's in-memory `u128` on x86-64.  `FieldElement` itself is not
+ *    repr(C) ({&Field, u128}); the shim packs `.value`s into a contiguous [u128].
+ *  - A digest / Merkle node is 64 raw bytes (BLAKE2b-512).
+ *  - Every data pointer may be a HOST pointer or a DEVICE pointer of the context's GPU;
+ *    the library detects which (cudaPointerGetAttributes).  Host buffers are staged
+ *    through the context's stream inside the call; device buffers are used in place, so a
+ *    pipeline LDE -> commit -> FRI never leaves HBM.
+ *  - All functions return 0 on success or a negative ZKB_ERR_* code; zkb_last_error()
+ *    gives the message.  The reference PANICS on the same misuse; the Rust
+ *    shim turns a non-zero status into panic!(message).
+ *  - There is no CPU fallback: without a CUDA device zkb_ctx_create fails.
+ *  - A context is used by one thread at a time (the reference is single-threaded).
+ */
+#ifndef ZKB200_H
+#define ZKB200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ZKB_OK 0
+#define ZKB_ERR_CUDA (-1)        /* CUDA runtime error (message has the call)                 */
+#define ZKB_ERR_ARG (-2)         /* null / inconsistent argument                              */
+#define ZKB_ERR_EMPTY (-3)       /* ntt on empty input        (ntt.rs:11 index panic)         */
+#define ZKB_ERR_NOT_POW2 (-4)    /* Merkle length not 2^k     (merkle_root.rs:9,36)           */
+#define ZKB_ERR_TOO_LONG (-5)    /* coeffs.len() > root_order (ntt_arithmetics.rs:168)        */
+#define ZKB_ERR_ROOT_ORDER (-6)  /* root^order != 1 or not primitive (ntt_arithmetics.rs:11-24) */
+#define ZKB_ERR_DIV_ZERO (-7)    /* divide by zero (field_element.rs:85, ntt_arithmetics.rs:258) */
+#define ZKB_ERR_INDEX (-8)       /* opening index out of range (merkle_root.rs:37)            */
+#define ZKB_ERR_LENGTH (-9)      /* domain/codeword length mismatch (fri.rs:215-219)          */
+#define ZKB_ERR_ROUNDS (-10)     /* FRI needs >= 2 rounds (fri.rs:225 unwrap)                 */
+#define ZKB_ERR_DEGREE (-11)     /* divide by polynomial of larger degree (ntt_arithmetics.rs:268) */
+#define ZKB_ERR_CALLBACK (-12)   /* Fiat-Shamir callback returned non-zero                    */
+
+typedef struct zkb_ctx zkb_ctx;
+typedef struct zkb_tree zkb_tree;
+typedef struct zkb_fri_layers zkb_fri_layers;
+typedef struct zkb_ps zkb_ps;
+
+/* ---- context ------------------------------------------------------------------------ */
+/* One context per GPU.  `stream` = a cudaStream_t to run on (e.g. torch's current stream),
+ * or NULL to let the context create its own non-blocking stream. */
+int zkb_ctx_create(int device, void* stream, zkb_ctx** out);
+void zkb_ctx_destroy(zkb_ctx* ctx);
+const char* zkb_last_error(const zkb_ctx* ctx);
+int zkb_ctx_sync(zkb_ctx* ctx);                       /* cudaStreamSynchronize             */
+uint64_t zkb_ctx_launches(const zkb_ctx* ctx);        /* kernels launched so far           */
+const char* zkb_version(void);
+/* plain device-memory helpers for hosts that do not bring their own allocator */
+int zkb_dev_alloc(zkb_ctx* ctx, size_t bytes, void** dptr);
+int zkb_dev_free(zkb_ctx* ctx, void* dptr);
+int zkb_memcpy(zkb_ctx* ctx, void* dst, const void* src, size_t bytes);   /* any direction, sync */
+
+/* ---- field (scalar helpers, host) : src/field/field.rs:58-71,87-99,160-169 ------------ */
+int zkb_primitive_nth_root(uint64_t n, uint8_t out[16]);  /* Field::primitive_nth_root     */
+void zkb_field_generator(uint8_t out[16]);                /* Field::generator field.rs:41  */
+void zkb_field_mul(const uint8_t a[16], const uint8_t b[16], uint8_t out[16]);
+void zkb_field_inv(const uint8_t a[16], uint8_t out[16]);
+void zkb_field_pow(const uint8_t a[16], uint64_t e, uint8_t out[16]);
+void zkb_field_sample(const uint8_t* bytes, size_t len, uint8_t out[16]); /* Field::sample  */
+
+/* ---- NTT : src/fft/ntt.rs ------------------------------------------------------------ */
+/* ntt(root, inputs) ntt.rs:7-49.  n_in >= 1 values in; out receives next_pow2(n_in) values
+ * (zero padded before the transform, natural order out).  n_in == 1 copies.  `root` must be
+ * a primitive next_pow2(n_in)-th root (not checked, as in the reference). */
+int zkb_ntt(zkb_ctx* ctx, const uint8_t root[16], const void* in, size_t n_in, void* out);
+/* intt(root, input) ntt.rs:51-68: identity for n_in < 2, else ntt(root^-1) * n^-1. */
+int zkb_intt(zkb_ctx* ctx, const uint8_t root[16], const void* in, size_t n_in, void* out);
+/* `batch` independent transforms of the same length: column c starts at in + c*in_stride
+ * elements / out + c*out_stride elements (trace columns). */
+int zkb_ntt_batch(zkb_ctx* ctx, const uint8_t root[16], int inverse, const void* in, size_t n_in,
+                  size_t in_stride, void* out, size_t out_stride, size_t batch);
+
+/* ---- polynomial helpers : src/field/polynomial.rs, src/fft/ntt_arithmetics.rs --------- */
+/* Polynomial::scale polynomial.rs:109-121: out[i] = factor^i * coeffs[i] */
+int zkb_poly_scale(zkb_ctx* ctx, const uint8_t factor[16], const void* coeffs, size_t n, void* out);
+/* fast_coset_evaluate ntt_arithmetics.rs:161-170 (the LDE): evaluations of the polynomial
+ * on offset*<omega>, out[k] <-> offset*omega^k, `order` values out.  n_coeffs <= order. */
+int zkb_coset_lde(zkb_ctx* ctx, const uint8_t omega[16], uint64_t order, const uint8_t offset[16],
+                  const void* coeffs, size_t n_coeffs, void* out);
+int zkb_coset_lde_batch(zkb_ctx* ctx, const uint8_t omega[16], uint64_t order, const uint8_t offset[16],
+                        const void* coeffs, size_t n_coeffs, size_t in_stride, void* out,
+                        size_t out_stride, size_t batch);
+/* fast_multiply ntt_arithmetics.rs:5-64.  *n_out receives the coefficient count
+ * (deg l + deg r + 1, or 0 if an operand is the zero polynomial); `out` must hold
+ * n_lhs + n_rhs values.  HOST pointers only (small operands in the reference). */
+int zkb_poly_mul(zkb_ctx* ctx, const uint8_t root[16], uint64_t root_order, const void* lhs, size_t n_lhs,
+                 const void* rhs, size_t n_rhs, void* out, size_t* n_out);
+/* fast_coset_divide ntt_arithmetics.rs:239-310.  `out` must hold n_lhs values. HOST pointers. */
+int zkb_coset_div(zkb_ctx* ctx, const uint8_t root[16], uint64_t root_order, const uint8_t offset[16],
+                  const void* lhs, size_t n_lhs, const void* rhs, size_t n_rhs, void* out, size_t* n_out);
+
+/* ---- Merkle : src/merkle_root.rs ------------------------------------------------------ */
+/* MerkleRoot::commit merkle_root.rs:21-32 for T = FieldElement: leaf = BLAKE2b-512(decimal
+ * ASCII of the value), node = BLAKE2b-512(left || right); n must be a power of two. */
+int zkb_merkle_commit(zkb_ctx* ctx, const void* vals, size_t n, uint8_t root[64]);
+/* Same, but keeps the tree on the device so that openings do not rebuild it
+ * (the reference rebuilds the whole tree on every MerkleRoot::open, merkle_root.rs:55-66).
+ * The tree keeps a device copy of / reference to `vals`: if `vals` is a device pointer it
+ * must stay alive until zkb_merkle_free. */
+int zkb_merkle_build(zkb_ctx* ctx, const void* vals, size_t n, zkb_tree** tree);
+int zkb_merkle_root(const zkb_tree* tree, uint8_t root[64]);
+/* MerkleRoot::open merkle_root.rs:34-66 for k indices at once: paths_out (HOST) receives
+ * k * log2(n) * 64 bytes, each path leaf-sibling first.  n must be >= 2. */
+int zkb_merkle_open(zkb_tree* tree, const uint64_t* idx, size_t k, uint8_t* paths_out);
+void zkb_merkle_free(zkb_tree* tree);
+/* MerkleRoot::verify merkle_root.rs:69-95 (host; returns 1 = accept, 0 = reject) */
+int zkb_merkle_verify(const uint8_t root[64], uint64_t index, const uint8_t* path, size_t path_len,
+                      const uint8_t leaf[16]);
+/* BLAKE2b-512 of arbitrary bytes on the host (crypto/blake2b512.rs:4-14) */
+void zkb_blake2b512(const uint8_t* msg, size_t len, uint8_t out[64]);
+/* SHAKE256 XOF on the host (crypto/shake256.rs:7-19) */
+void zkb_shake256(const uint8_t* msg, size_t len, uint8_t* out, size_t out_len);
+
+/* ---- FRI : src/fri.rs ------------------------------------------------------------------ */
+typedef struct zkb_fri_params {
+    uint8_t offset[16];            /* FRI::new fri.rs:23-38 */
+    uint8_t omega[16];
+    uint64_t domain_length;
+    uint64_t expansion_factor;
+    uint64_t num_colinearity_tests;
+} zkb_fri_params;
+
+/* FRI::num_rounds fri.rs:40-50 */
+uint64_t zkb_fri_num_rounds(const zkb_fri_params* p);
+/* the split-and-fold step of FRI::commit fri.rs:150-159:
+ * out[i] = 2^-1((1 + alpha/x_i) cw[i] + (1 - alpha/x_i) cw[n/2+i]), x_i = offset*omega^i */
+int zkb_fri_fold(zkb_ctx* ctx, const void* cw, size_t n, const uint8_t alpha[16],
+                 const uint8_t offset[16], const uint8_t omega[16], void* out);
+/* Fiat-Shamir hook: called once per round with that round's Merkle root, in order.
+ * If want_alpha != 0 it must write the challenge alpha (field element, 16-byte LE) -
+ * i.e. push Root, then Field::sample(fiat_shamir_prover(32)) as fri.rs:136-146 does.
+ * On the last round want_alpha == 0 (root pushed, no challenge drawn, fri.rs:140). */
+typedef int (*zkb_fs_callback)(void* user, uint32_t round, const uint8_t root[64], int want_alpha,
+                               uint8_t alpha_out[16]);
+/* FRI::commit fri.rs:115-172 with every layer kept on the device: per round Merkle-commit
+ * the codeword, hand the root to `fs`, fold with the returned alpha (fold fused with the
+ * next layer's leaf hashing).  The caller pushes Codeword(last) itself (zkb_fri_last_codeword). */
+int zkb_fri_commit(zkb_ctx* ctx, const zkb_fri_params* p, const void* codeword, size_t n,
+                   zkb_fs_callback fs, void* user, zkb_fri_layers** layers);
+uint64_t zkb_fri_layer_count(const zkb_fri_layers* l);
+uint64_t zkb_fri_layer_len(const zkb_fri_layers* l, uint64_t round);
+int zkb_fri_layer_root(const zkb_fri_layers* l, uint64_t round, uint8_t root[64]);
+/* copy layer `round` (a codeword of zkb_fri_layer_len values) to `out` (host or device) */
+int zkb_fri_layer_codeword(zkb_fri_layers* l, uint64_t round, void* out);
+const void* zkb_fri_layer_device_ptr(const zkb_fri_layers* l, uint64_t round);
+/* FRI::query fri.rs:174-208 payloads for the layer pair (round, round+1) at the ncc
+ * indices idx_c: leafs_out (HOST) gets ncc * 3 * 16 bytes (cur[a], cur[b], next[c]);
+ * paths_out (HOST) gets, per s: path(a) || path(b) (log2(len) nodes each) || path(c in next)
+ * (log2(len)-1 nodes), 64 bytes per node. */
+int zkb_fri_query(zkb_fri_layers* l, uint64_t round, const uint64_t* idx_c, size_t ncc,
+                  uint8_t* leafs_out, uint8_t* paths_out);
+void zkb_fri_layers_free(zkb_fri_layers* l);
+/* FRI::sample_indices fri.rs:85-113 (host) */
+int zkb_fri_sample_indices(const uint8_t* seed, size_t seed_len, uint64_t size, uint64_t reduced_size,
+                           uint64_t number, uint64_t* out);
+
+/* ---- proof stream : src/proof_stream.rs, src/stark/proof_stream_enum.rs ------------------ */
+/* IndependentProofStream (prefix == NULL) or SignatureProofStream (prefix = the document;
+ * rescue_prime/proof_stream.rs:15-22 hashes it with BLAKE2b-512). */
+int zkb_ps_create(const uint8_t* document, size_t document_len, int is_signature, zkb_ps** out);
+void zkb_ps_free(zkb_ps* ps);
+int zkb_ps_push_root(zkb_ps* ps, const uint8_t root[64], size_t len);
+int zkb_ps_push_codeword(zkb_ps* ps, const void* vals_host, size_t n);
+int zkb_ps_push_path(zkb_ps* ps, const uint8_t* nodes, size_t count);       /* count x 64 bytes */
+int zkb_ps_push_leafs(zkb_ps* ps, const uint8_t a[16], const uint8_t b[16], const uint8_t c[16]);
+int zkb_ps_push_value(zkb_ps* ps, const uint8_t v[16]);
+/* ProofStream::digest (the wire bytes): returns the length; copies min(len, cap) bytes */
+size_t zkb_ps_digest(const zkb_ps* ps, uint8_t* out, size_t cap);
+/* fiat_shamir_prover(num_bytes) proof_stream.rs:36-40 */
+int zkb_ps_fiat_shamir(const zkb_ps* ps, size_t num_bytes, uint8_t* out);
+/* FRI::prove fri.rs:210-248 end to end against a proof stream: commit, push the last
+ * codeword, sample the top-level indices, push all Leafs/Path objects.  top_indices_out
+ * receives num_colinearity_tests indices (the function's return value in the reference). */
+int zkb_fri_prove(zkb_ctx* ctx, const zkb_fri_params* p, const void* codeword, size_t n, zkb_ps* ps,
+                  uint64_t* top_indices_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ZKB200_H */

@@ -1,0 +1,100 @@
+// ctx.hpp - library context: one per (process, GPU).  Owns the stream, a scratch
+// arena, the cache of power tables (twiddles) and the last error string.
+// Single-threaded callers per context, like the reference (no globals,
+// no interior mutability in the reference; the C ABI keeps state in explicit handles).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+#include <memory>
+#include "fe128.cuh"
+#include "../../include/zkb200.h"
+
+namespace zkb {
+
+// Two-level table of powers of `base` covering exponents [0, 2^log_n):
+//   lo[i] = base^i * R        i < 2^lo_bits
+//   hi[j] = base^(j<<lo_bits) * R
+// so base^e * R = montmul(hi[e >> lo_bits], lo[e & mask]).  128 KiB for log_n = 24.
+struct PowTable {
+    fe base;            // canonical
+    uint32_t log_n;
+    uint32_t lo_bits;
+    fe* lo = nullptr;   // device
+    fe* hi = nullptr;   // device
+    uint64_t stamp = 0;
+};
+
+struct DevPow {         // what kernels take by value
+    const fe* lo;
+    const fe* hi;
+    uint32_t lo_bits;
+};
+
+}  // namespace zkb
+
+struct zkb_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    int sm_count = 148;
+    std::string err;
+    // scratch arena (grown on demand, never shrunk)
+    void* scratch = nullptr;
+    size_t scratch_bytes = 0;
+    // pinned staging for small host<->device traffic (roots, challenges)
+    uint8_t* pinned = nullptr;
+    size_t pinned_bytes = 0;
+    std::vector<std::unique_ptr<zkb::PowTable>> pow_tables;
+    uint64_t clock = 0;
+    uint64_t launches = 0;   // kernels launched through this context (bench "gpu_launches")
+};
+
+namespace zkb {
+
+int set_err(zkb_ctx* c, int code, const char* fmt, ...);
+
+#define ZKB_CUDA(ctx, call)                                                              \
+    do {                                                                                 \
+        cudaError_t e__ = (call);                                                        \
+        if (e__ != cudaSuccess)                                                          \
+            return zkb::set_err((ctx), ZKB_ERR_CUDA, "%s failed: %s (%s:%d)", #call,     \
+                                cudaGetErrorString(e__), __FILE__, __LINE__);            \
+    } while (0)
+
+#define ZKB_TRY(expr)            \
+    do {                         \
+        int rc__ = (expr);       \
+        if (rc__ != 0) return rc__; \
+    } while (0)
+
+int scratch_reserve(zkb_ctx* c, size_t bytes, void** out);
+int get_pow_table(zkb_ctx* c, const fe& base, uint32_t log_n, DevPow* out);
+bool is_device_ptr(const void* p);
+
+// RAII device buffer used for transient staging of host inputs
+struct DevBuf {
+    void* p = nullptr;
+    ~DevBuf() { if (p) cudaFree(p); }
+    int alloc(zkb_ctx* c, size_t bytes);
+};
+
+// If `p` is a host pointer, stage it into `buf` (async on the ctx stream) and return the
+// device pointer; device pointers are passed through.
+int stage_in(zkb_ctx* c, const void* p, size_t bytes, DevBuf& buf, const void** dev);
+
+// ---- host-side field helpers (canonical values) built on the verified host path of
+// fe128.cuh
+inline fe h_mul(const fe& a, const fe& b) { return fe_mul(a, b); }
+inline fe h_pow(const fe& a, uint64_t e) { return fe_from_mont(fe_mont_pow(fe_to_mont(a), e)); }
+fe h_inv(const fe& a);                      // a^(p-2); inverse(0) = 0 like field.rs:160-169
+inline fe h_from_u64(uint64_t x) { fe r = fe_zero(); r.v[0] = (uint32_t)x; r.v[1] = (uint32_t)(x >> 32); return r; }
+inline fe h_load(const uint8_t* le16) { fe r; for (int i = 0; i < 4; i++) r.v[i] = (uint32_t)le16[4 * i] | ((uint32_t)le16[4 * i + 1] << 8) | ((uint32_t)le16[4 * i + 2] << 16) | ((uint32_t)le16[4 * i + 3] << 24); return r; }
+inline void h_store(uint8_t* le16, const fe& a) { for (int i = 0; i < 4; i++) { le16[4 * i] = (uint8_t)a.v[i]; le16[4 * i + 1] = (uint8_t)(a.v[i] >> 8); le16[4 * i + 2] = (uint8_t)(a.v[i] >> 16); le16[4 * i + 3] = (uint8_t)(a.v[i] >> 24); } }
+
+inline uint32_t ilog2_u64(uint64_t x) { uint32_t l = 0; while ((1ull << l) < x) l++; return l; }
+inline uint64_t next_pow2_u64(uint64_t x) { uint64_t p = 1; while (p < x) p <<= 1; return p; }
+
+}  // namespace zkb

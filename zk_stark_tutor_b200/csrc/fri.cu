@@ -1,0 +1,317 @@
+// fri.cu - FRI commit / query / prove on the device.
+//
+// Replaces the bodies of (reference file:line):
+//   FRI::num_rounds   src/fri.rs:40-50
+//   FRI::commit       src/fri.rs:115-172   (Merkle root -> Fiat-Shamir alpha -> split-and-fold)
+//   FRI::query        src/fri.rs:174-208
+//   FRI::prove        src/fri.rs:210-248
+//
+// The fold  c'[i] = 2^-1((1 + a/x_i) c[i] + (1 - a/x_i) c[i+n/2]),  x_i = offset*omega^i
+// is evaluated as  half(c[i] + c[i+n/2] + k_i (c[i] - c[i+n/2])),  k_i = (alpha/offset) omega^-i
+// - the same field element (exact arithmetic), 2.25 multiplications per output instead of the
+// reference's pow + xgcd inverse + 5 products.  omega^-i comes from one two-level power
+// table of omega_0^-1 shared by all rounds (round r uses exponent i*2^r).  For layers of
+// more than 1024 values the fold runs inside the leaf-hash kernel of the NEXT layer
+// (merkle.cu k_leaf_tile<true>): the folded value is written once to HBM and hashed while
+// still in registers.  Every layer (codeword + pruned tree) stays on the device for the
+// query phase; only the 64-byte root goes to the host each round, where the Fiat-Shamir
+// callback turns it into alpha (SHAKE256 over a transcript of < 1.5 KB).
+#include <string.h>
+#include <vector>
+#include "merkle.cuh"
+#include "hosthash.hpp"
+
+namespace zkb {
+
+__device__ __forceinline__ fe pow2lvl_f(const DevPow& t, uint64_t e) {
+    fe lo = fe_ldg(t.lo + (e & ((1ull << t.lo_bits) - 1)));
+    fe hi = fe_ldg(t.hi + (e >> t.lo_bits));
+    return fe_montmul(hi, lo);
+}
+
+// stand-alone fold (small layers, and the zkb_fri_fold entry point)
+__global__ void k_fold(FoldArgs f) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= f.half) return;
+    fe k_m = fe_montmul(f.kk_m, pow2lvl_f(f.winv, i * f.exp_mul));
+    fe a = fe_ldg(f.cw + i), b = fe_ldg(f.cw + f.half + i);
+    fe s = fe_add(a, b), d = fe_sub(a, b);
+    fe_store(f.next + i, fe_half(fe_add(s, fe_montmul(k_m, d))));
+}
+
+__global__ void k_gather3(const fe* cur, const fe* nxt, uint64_t half, const uint64_t* idx, uint32_t k, fe* out) {
+    uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= k) return;
+    uint64_t a = idx[s];
+    fe_store(out + 3 * s, fe_ldg(cur + a));
+    fe_store(out + 3 * s + 1, fe_ldg(cur + a + half));
+    fe_store(out + 3 * s + 2, fe_ldg(nxt + a));
+}
+
+static int launch_fold(zkb_ctx* c, const FoldArgs& f) {
+    k_fold<<<(unsigned)((f.half + 255) / 256), 256, 0, c->stream>>>(f);
+    c->launches++;
+    ZKB_CUDA(c, cudaGetLastError());
+    return 0;
+}
+
+}  // namespace zkb
+
+using namespace zkb;
+
+struct zkb_fri_layers {
+    zkb_ctx* ctx = nullptr;
+    uint64_t rounds = 0;
+    std::vector<uint64_t> len;           // codeword length per round
+    std::vector<const fe*> cw;           // device codeword per round (round 0 may alias the caller's buffer)
+    std::vector<TreeLayout> layout;
+    std::vector<uint8_t*> nodes;         // device, per round (slices of `arena`)
+    std::vector<std::vector<uint8_t>> roots;
+    void* arena = nullptr;               // one allocation: folded codewords + all trees
+    void* owned_cw0 = nullptr;           // staged copy of a host codeword
+};
+
+extern "C" {
+
+uint64_t zkb_fri_num_rounds(const zkb_fri_params* p) {
+    if (!p) return 0;
+    uint64_t n = p->domain_length, r = 0;           // fri.rs:40-50
+    while (n > p->expansion_factor && n > 4 * p->num_colinearity_tests) { n /= 2; r++; }
+    return r;
+}
+
+int zkb_fri_fold(zkb_ctx* c, const void* cw, size_t n, const uint8_t alpha[16], const uint8_t offset[16],
+                 const uint8_t omega[16], void* out) {
+    if (!c || !cw || !alpha || !offset || !omega || !out) return ZKB_ERR_ARG;
+    if (n < 2 || (n & (n - 1))) return set_err(c, ZKB_ERR_NOT_POW2, "fri_fold: codeword length %zu is not a power of two >= 2", n);
+    ZKB_CUDA(c, cudaSetDevice(c->device));
+    const bool out_dev = is_device_ptr(out);
+    DevBuf bin, bout;
+    const void* d_in = nullptr;
+    ZKB_TRY(stage_in(c, cw, n * sizeof(fe), bin, &d_in));
+    fe* d_out = (fe*)out;
+    if (!out_dev) { ZKB_TRY(bout.alloc(c, (n / 2) * sizeof(fe))); d_out = (fe*)bout.p; }
+    fe w = h_load(omega), off = h_load(offset);
+    if (fe_is_zero(off) || fe_is_zero(w)) return set_err(c, ZKB_ERR_DIV_ZERO, "divide by zero");
+    fe winv = h_inv(w);
+    FoldArgs f;
+    f.cw = (const fe*)d_in; f.next = d_out; f.half = n / 2;
+    ZKB_TRY(get_pow_table(c, winv, ilog2_u64(n), &f.winv));
+    f.exp_mul = 1;
+    f.kk_m = fe_to_mont(h_mul(h_load(alpha), h_inv(off)));
+    f.wr_inv_m = fe_to_mont(winv);
+    ZKB_TRY(launch_fold(c, f));
+    if (!out_dev) ZKB_CUDA(c, cudaMemcpyAsync(out, d_out, (n / 2) * sizeof(fe), cudaMemcpyDeviceToHost, c->stream));
+    if (!out_dev || bin.p) ZKB_CUDA(c, cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+void zkb_fri_layers_free(zkb_fri_layers* l) {
+    if (!l) return;
+    cudaSetDevice(l->ctx->device);
+    cudaStreamSynchronize(l->ctx->stream);
+    if (l->arena) cudaFree(l->arena);
+    if (l->owned_cw0) cudaFree(l->owned_cw0);
+    delete l;
+}
+
+int zkb_fri_commit(zkb_ctx* c, const zkb_fri_params* p, const void* codeword, size_t n,
+                   zkb_fs_callback fs, void* user, zkb_fri_layers** out) {
+    if (!c || !p || !codeword || !fs || !out) return ZKB_ERR_ARG;
+    *out = nullptr;
+    if (p->domain_length != n) return set_err(c, ZKB_ERR_LENGTH, "Length of the domain doesnt match the length of initial codeword");
+    if (n < 2 || (n & (n - 1))) return set_err(c, ZKB_ERR_NOT_POW2, "Leafs len must be power of two (got %zu)", n);
+    const uint64_t rounds = zkb_fri_num_rounds(p);
+    if (rounds < 1) return set_err(c, ZKB_ERR_ROUNDS, "FRI needs at least one round");
+    ZKB_CUDA(c, cudaSetDevice(c->device));
+    fe omega = h_load(p->omega), offset = h_load(p->offset);
+    // fri.rs:133: omega^(n-1) == omega^-1, i.e. omega^n == 1 (checked once; squaring preserves it)
+    if (!fe_eq(h_pow(omega, n), fe_from_u32(1)) || fe_is_zero(omega))
+        return set_err(c, ZKB_ERR_ROOT_ORDER, "error in commit: omega does not have the right order!");
+    if (fe_is_zero(offset)) return set_err(c, ZKB_ERR_DIV_ZERO, "divide by zero");
+
+    std::unique_ptr<zkb_fri_layers> L(new zkb_fri_layers());
+    L->ctx = c;
+    L->rounds = rounds;
+    size_t arena_bytes = 0;
+    std::vector<size_t> cw_off(rounds), node_off(rounds);
+    for (uint64_t r = 0; r < rounds; r++) {
+        uint64_t len = n >> r;
+        L->len.push_back(len);
+        TreeLayout tl;
+        tl.init(ilog2_u64(len));
+        L->layout.push_back(tl);
+        if (r > 0) { cw_off[r] = arena_bytes; arena_bytes += len * sizeof(fe); }
+        node_off[r] = arena_bytes;
+        arena_bytes += tl.total_nodes * 64;
+    }
+    ZKB_CUDA(c, cudaMalloc(&L->arena, arena_bytes));
+    auto fail = [&](int rc) { cudaStreamSynchronize(c->stream); cudaFree(L->arena); if (L->owned_cw0) cudaFree(L->owned_cw0); L->arena = nullptr; L->owned_cw0 = nullptr; return rc; };
+    if (is_device_ptr(codeword)) {
+        L->cw.push_back((const fe*)codeword);
+    } else {
+        cudaError_t e = cudaMalloc(&L->owned_cw0, n * sizeof(fe));
+        if (e == cudaSuccess) e = cudaMemcpyAsync(L->owned_cw0, codeword, n * sizeof(fe), cudaMemcpyHostToDevice, c->stream);
+        if (e != cudaSuccess) return fail(set_err(c, ZKB_ERR_CUDA, "staging the codeword failed: %s", cudaGetErrorString(e)));
+        L->cw.push_back((const fe*)L->owned_cw0);
+    }
+    for (uint64_t r = 0; r < rounds; r++) {
+        L->nodes.push_back((uint8_t*)L->arena + node_off[r]);
+        if (r > 0) L->cw.push_back((const fe*)((uint8_t*)L->arena + cw_off[r]));
+    }
+    DevPow winv_tab;
+    fe omega_inv0 = h_inv(omega);
+    int rc = get_pow_table(c, omega_inv0, ilog2_u64(n), &winv_tab);
+    if (rc) return fail(rc);
+
+    fe alpha = fe_zero();
+    fe offset_r = offset, omega_inv_r = omega_inv0;      // round-r offset and omega^-1
+    for (uint64_t r = 0; r < rounds; r++) {
+        const uint64_t len = L->len[r];
+        const TreeLayout& tl = L->layout[r];
+        if (r == 0) {
+            rc = merkle_build_levels(c, L->cw[0], nullptr, len, tl, L->nodes[0]);
+        } else {
+            FoldArgs f;
+            f.cw = L->cw[r - 1]; f.next = (fe*)L->cw[r]; f.half = len;
+            f.winv = winv_tab; f.exp_mul = 1ull << (r - 1);
+            f.kk_m = fe_to_mont(h_mul(alpha, h_inv(offset_r)));
+            f.wr_inv_m = fe_to_mont(omega_inv_r);
+            if (tl.cut > 0) {
+                rc = merkle_build_levels(c, nullptr, &f, len, tl, L->nodes[r]);     // fold fused with leaf hashing
+            } else {
+                rc = launch_fold(c, f);
+                if (!rc) rc = merkle_build_levels(c, L->cw[r], nullptr, len, tl, L->nodes[r]);
+            }
+            offset_r = h_mul(offset_r, offset_r);        // fri.rs:161-162
+            omega_inv_r = h_mul(omega_inv_r, omega_inv_r);
+        }
+        if (rc) return fail(rc);
+        cudaError_t e = cudaMemcpyAsync(c->pinned, L->nodes[r] + tl.level_off[tl.log_n] * 64, 64, cudaMemcpyDeviceToHost, c->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+        if (e != cudaSuccess) return fail(set_err(c, ZKB_ERR_CUDA, "FRI round %llu failed: %s", (unsigned long long)r, cudaGetErrorString(e)));
+        L->roots.emplace_back(c->pinned, c->pinned + 64);
+        const int want_alpha = r + 1 < rounds;
+        uint8_t alpha_le[16] = {0};
+        if (fs(user, (uint32_t)r, L->roots.back().data(), want_alpha, alpha_le) != 0)
+            return fail(set_err(c, ZKB_ERR_CALLBACK, "Fiat-Shamir callback failed in round %llu", (unsigned long long)r));
+        if (want_alpha) {
+            alpha = h_load(alpha_le);
+            if (fe_ge_p(alpha)) return fail(set_err(c, ZKB_ERR_ARG, "Fiat-Shamir callback returned a non-canonical alpha"));
+        }
+    }
+    *out = L.release();
+    return 0;
+}
+
+uint64_t zkb_fri_layer_count(const zkb_fri_layers* l) { return l ? l->rounds : 0; }
+uint64_t zkb_fri_layer_len(const zkb_fri_layers* l, uint64_t r) { return (l && r < l->rounds) ? l->len[r] : 0; }
+const void* zkb_fri_layer_device_ptr(const zkb_fri_layers* l, uint64_t r) { return (l && r < l->rounds) ? l->cw[r] : nullptr; }
+int zkb_fri_layer_root(const zkb_fri_layers* l, uint64_t r, uint8_t root[64]) {
+    if (!l || r >= l->rounds || !root) return ZKB_ERR_ARG;
+    memcpy(root, l->roots[r].data(), 64);
+    return 0;
+}
+int zkb_fri_layer_codeword(zkb_fri_layers* l, uint64_t r, void* out) {
+    if (!l || r >= l->rounds || !out) return ZKB_ERR_ARG;
+    zkb_ctx* c = l->ctx;
+    ZKB_CUDA(c, cudaMemcpyAsync(out, l->cw[r], l->len[r] * sizeof(fe), cudaMemcpyDefault, c->stream));
+    ZKB_CUDA(c, cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int zkb_fri_query(zkb_fri_layers* l, uint64_t r, const uint64_t* idx_c, size_t ncc, uint8_t* leafs_out, uint8_t* paths_out) {
+    if (!l || !idx_c || !leafs_out || !paths_out) return ZKB_ERR_ARG;
+    zkb_ctx* c = l->ctx;
+    if (r + 1 >= l->rounds) return set_err(c, ZKB_ERR_ARG, "fri_query: no layer after round %llu", (unsigned long long)r);
+    if (ncc == 0) return 0;
+    ZKB_CUDA(c, cudaSetDevice(c->device));
+    const uint64_t len = l->len[r], half = len / 2;
+    const uint32_t d_cur = l->layout[r].log_n, d_nxt = l->layout[r + 1].log_n;
+    for (size_t s = 0; s < ncc; s++)
+        if (idx_c[s] >= half) return set_err(c, ZKB_ERR_INDEX, "fri_query: index %llu out of range", (unsigned long long)idx_c[s]);
+    // index lists: a (cur), b (cur), c (next)
+    std::vector<uint64_t> ab(2 * ncc), cc(ncc);
+    for (size_t s = 0; s < ncc; s++) { ab[2 * s] = idx_c[s]; ab[2 * s + 1] = idx_c[s] + half; cc[s] = idx_c[s]; }
+    const size_t pb_cur = (size_t)d_cur * 64, pb_nxt = (size_t)d_nxt * 64;
+    DevBuf buf;
+    size_t bytes = 3 * ncc * 8 + 3 * ncc * 16 + 2 * ncc * pb_cur + ncc * pb_nxt + 64;
+    ZKB_TRY(buf.alloc(c, bytes));
+    uint64_t* d_ab = (uint64_t*)buf.p;
+    uint64_t* d_c = d_ab + 2 * ncc;
+    fe* d_leafs = (fe*)(d_c + ncc + (ncc & 1));
+    uint8_t* d_pab = (uint8_t*)(d_leafs + 3 * ncc);
+    uint8_t* d_pc = d_pab + 2 * ncc * pb_cur;
+    ZKB_CUDA(c, cudaMemcpyAsync(d_ab, ab.data(), 2 * ncc * 8, cudaMemcpyHostToDevice, c->stream));
+    ZKB_CUDA(c, cudaMemcpyAsync(d_c, cc.data(), ncc * 8, cudaMemcpyHostToDevice, c->stream));
+    k_gather3<<<(unsigned)((ncc + 127) / 128), 128, 0, c->stream>>>(l->cw[r], l->cw[r + 1], half, d_c, (uint32_t)ncc, d_leafs);
+    c->launches++;
+    ZKB_CUDA(c, cudaGetLastError());
+    ZKB_TRY(merkle_open_device(c, l->cw[r], l->layout[r], l->nodes[r], d_ab, 2 * ncc, d_pab));
+    if (d_nxt > 0) ZKB_TRY(merkle_open_device(c, l->cw[r + 1], l->layout[r + 1], l->nodes[r + 1], d_c, ncc, d_pc));
+    std::vector<uint8_t> hab(2 * ncc * pb_cur), hc(ncc * pb_nxt);
+    ZKB_CUDA(c, cudaMemcpyAsync(leafs_out, d_leafs, 3 * ncc * 16, cudaMemcpyDeviceToHost, c->stream));
+    ZKB_CUDA(c, cudaMemcpyAsync(hab.data(), d_pab, hab.size(), cudaMemcpyDeviceToHost, c->stream));
+    if (!hc.empty()) ZKB_CUDA(c, cudaMemcpyAsync(hc.data(), d_pc, hc.size(), cudaMemcpyDeviceToHost, c->stream));
+    ZKB_CUDA(c, cudaStreamSynchronize(c->stream));
+    // interleave per s: path(a) || path(b) || path(c)
+    uint8_t* o = paths_out;
+    for (size_t s = 0; s < ncc; s++) {
+        memcpy(o, hab.data() + (2 * s) * pb_cur, pb_cur); o += pb_cur;
+        memcpy(o, hab.data() + (2 * s + 1) * pb_cur, pb_cur); o += pb_cur;
+        memcpy(o, hc.data() + s * pb_nxt, pb_nxt); o += pb_nxt;
+    }
+    return 0;
+}
+
+// ---- FRI::prove against the built-in proof stream -------------------------------------------
+static int ps_callback(void* user, uint32_t, const uint8_t root[64], int want_alpha, uint8_t alpha_out[16]) {
+    zkb_ps* ps = (zkb_ps*)user;
+    zkb_ps_push_root(ps, root, 64);                         // fri.rs:136-137
+    if (want_alpha) {
+        uint8_t ch[32];
+        zkb_ps_fiat_shamir(ps, 32, ch);                     // fri.rs:145
+        zkb_field_sample(ch, 32, alpha_out);                // fri.rs:146
+    }
+    return 0;
+}
+
+int zkb_fri_prove(zkb_ctx* c, const zkb_fri_params* p, const void* codeword, size_t n, zkb_ps* ps,
+                  uint64_t* top_indices_out) {
+    if (!c || !p || !ps || !top_indices_out) return ZKB_ERR_ARG;
+    const uint64_t ncc = p->num_colinearity_tests;
+    if (zkb_fri_num_rounds(p) < 2) return set_err(c, ZKB_ERR_ROUNDS, "FRI::prove needs at least two rounds (fri.rs:225)");
+    zkb_fri_layers* L = nullptr;
+    ZKB_TRY(zkb_fri_commit(c, p, codeword, n, ps_callback, ps, &L));
+    struct Guard { zkb_fri_layers* l; ~Guard() { zkb_fri_layers_free(l); } } guard{L};
+    const uint64_t R = L->rounds;
+    // send last codeword (fri.rs:166)
+    std::vector<uint8_t> last(L->len[R - 1] * 16);
+    ZKB_TRY(zkb_fri_layer_codeword(L, R - 1, last.data()));
+    zkb_ps_push_codeword(ps, last.data(), L->len[R - 1]);
+    // top-level indices (fri.rs:223-228)
+    uint8_t seed[32];
+    zkb_ps_fiat_shamir(ps, 32, seed);
+    if (ncc > L->len[R - 1]) return set_err(c, ZKB_ERR_ARG, "Cannot sample more indices than available in the last codeword");
+    if (zkb_fri_sample_indices(seed, 32, L->len[1], L->len[R - 1], ncc, top_indices_out) != 0)
+        return set_err(c, ZKB_ERR_ARG, "sample_indices failed");
+    std::vector<uint64_t> idx(top_indices_out, top_indices_out + ncc);
+    for (uint64_t r = 0; r + 1 < R; r++) {
+        const uint64_t half = L->len[r] / 2;
+        for (auto& i : idx) i %= half;                       // fri.rs:234-237
+        const size_t d_cur = L->layout[r].log_n, d_nxt = L->layout[r + 1].log_n;
+        std::vector<uint8_t> leafs(ncc * 48), paths(ncc * (2 * d_cur + d_nxt) * 64);
+        ZKB_TRY(zkb_fri_query(L, r, idx.data(), ncc, leafs.data(), paths.data()));
+        for (uint64_t s = 0; s < ncc; s++)                   // fri.rs:189-195
+            zkb_ps_push_leafs(ps, leafs.data() + 48 * s, leafs.data() + 48 * s + 16, leafs.data() + 48 * s + 32);
+        const uint8_t* q = paths.data();
+        for (uint64_t s = 0; s < ncc; s++) {                 // fri.rs:198-202
+            zkb_ps_push_path(ps, q, d_cur); q += d_cur * 64;
+            zkb_ps_push_path(ps, q, d_cur); q += d_cur * 64;
+            zkb_ps_push_path(ps, q, d_nxt); q += d_nxt * 64;
+        }
+    }
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,521 @@
+// ntt.cu - forward / inverse NTT, coset LDE and NTT-based polynomial arithmetic.
+//
+// Replaces the bodies of (reference file:line):
+//   ntt                  src/fft/ntt.rs:7-49      (+ bit_reverse_copy, src/utils/bit_reverse_copy.rs)
+//   intt                 src/fft/ntt.rs:51-68
+//   Polynomial::scale    src/field/polynomial.rs:109-121
+//   fast_coset_evaluate  src/fft/ntt_arithmetics.rs:161-170   (the LDE)
+//   fast_multiply        src/fft/ntt_arithmetics.rs:5-64
+//   fast_coset_divide    src/fft/ntt_arithmetics.rs:239-310
+//
+// Algorithm (results identical - exact arithmetic - but not the reference's single
+// radix-2 loop): N = N1*N2*N3 is transformed in up to three HBM passes (Bailey 4-step
+// applied twice).  Every pass is the same kernel: a CTA stages a tile of S x B values
+// (S = transform length of the pass, B = independent transforms that are CONTIGUOUS in
+// HBM so that every global access is a B*16-byte segment) in shared memory, runs all
+// log2(S) radix-2 stages there, multiplies by the inter-pass twiddle w_N^(k*col) taken
+// from a two-level power table, and writes the tile back.  Passes 1/2 are DIT with the
+// bit reversal folded into the global load address (free); the final pass is DIF with
+// the bit reversal folded into the shared-memory read of the (transposing) store.
+//   x[n1*M + m] --pass1: N1-point over n1, *w_N^(k1*m)--> A[k1*M + m]      (M = N2*N3)
+//   A[k1*M + n2*N3 + n3] --pass2: N2-point over n2, *w_M^(k2*n3)--> in place
+//   A[k1*M + k2*N3 + n3] --pass3: N3-point over n3--> X[k1 + N1*k2 + N1*N2*k3]
+// Zero padding (ntt.rs pads to the next power of two; the LDE pads N/ef coefficients
+// to N) is never materialised: loads beyond n_in read as zero, and the leading DIT
+// stages whose odd inputs are all zero are replaced by a broadcast (2 of 24 stages for
+// ef = 4).  The coset scaling c_i*offset^i of the LDE is fused into the pass-1 load.
+#include <string.h>
+#include "ctx.hpp"
+
+namespace zkb {
+
+struct PassParams {
+    const fe* in;
+    fe* out;
+    uint32_t log_s, log_b;
+    uint32_t transposed;         // 0: passes 1/2 (b fastest everywhere, DIT), 1: final pass (DIF)
+    uint32_t inner_count;
+    uint64_t ld_s, ld_b, ld_outer, ld_inner;
+    uint64_t st_k, st_b, st_outer, st_inner;
+    uint64_t in_batch, out_batch;
+    uint64_t n_valid;            // loads at logical index >= n_valid read as zero
+    uint32_t has_valid;
+    uint32_t skip_log;           // leading DIT stages replaced by a broadcast
+    uint64_t tw_mul;             // inter-pass twiddle exponent = k * col * tw_mul
+    DevPow tw;
+    uint32_t has_tw;
+    uint32_t has_scale;          // multiply loaded value by base^(logical index) (LDE)
+    DevPow sc;
+    uint32_t has_post;           // multiply stored value by `post` (n^-1 for the iNTT)
+    fe post;
+    const fe* tw_s;              // w_S^j * R, j < S/2
+};
+
+__device__ __forceinline__ fe pow2lvl(const DevPow& t, uint64_t e) {
+    fe lo = fe_ldg(t.lo + (e & ((1ull << t.lo_bits) - 1)));
+    fe hi = fe_ldg(t.hi + (e >> t.lo_bits));
+    return fe_montmul(hi, lo);
+}
+
+__device__ __forceinline__ uint32_t bitrev(uint32_t x, uint32_t bits) { return __brev(x) >> (32u - bits); }
+
+#define ZKB_NTT_THREADS 256
+
+__global__ void __launch_bounds__(ZKB_NTT_THREADS) k_ntt_pass(const PassParams p) {
+    extern __shared__ uint4 smem_raw[];
+    fe* sm = reinterpret_cast<fe*>(smem_raw);
+    const uint32_t S = 1u << p.log_s, B = 1u << p.log_b;
+    const uint32_t tid = threadIdx.x;
+    const uint32_t outer = blockIdx.x / p.inner_count, inner = blockIdx.x % p.inner_count;
+    const uint64_t in_base = (uint64_t)outer * p.ld_outer + (uint64_t)inner * p.ld_inner;
+    const fe* in = p.in + (uint64_t)blockIdx.y * p.in_batch;
+    fe* out = p.out + (uint64_t)blockIdx.y * p.out_batch + (uint64_t)outer * p.st_outer + (uint64_t)inner * p.st_inner;
+    fe* tws = sm + (p.transposed ? (size_t)B * (S + 1) : (size_t)S * B);
+    for (uint32_t j = tid; j < (S >> 1); j += ZKB_NTT_THREADS) tws[j] = fe_ldg(p.tw_s + j);
+
+    if (!p.transposed) {
+        // ---- load: smem row q <- x[rev(q)], only rows q = qq << z have a source ---------
+        const uint32_t z = p.skip_log, rows = S >> z;
+        for (uint32_t idx = tid; idx < rows * B; idx += ZKB_NTT_THREADS) {
+            uint32_t b = idx & (B - 1), qq = idx >> p.log_b;
+            uint32_t s = (p.log_s == z) ? 0u : bitrev(qq, p.log_s - z);
+            uint64_t lin = in_base + (uint64_t)s * p.ld_s + (uint64_t)b * p.ld_b;
+            fe x = fe_zero();
+            if (!p.has_valid || lin < p.n_valid) {
+                x = fe_ldg(in + lin);
+                if (p.has_scale) x = fe_montmul(x, pow2lvl(p.sc, lin));
+            }
+            uint32_t q0 = qq << z;
+            for (uint32_t r = 0; r < (1u << z); r++) sm[(size_t)(q0 + r) * B + b] = x;
+        }
+        // ---- DIT stages -------------------------------------------------------------------
+        for (uint32_t lh = z; lh < p.log_s; lh++) {
+            __syncthreads();
+            const uint32_t h = 1u << lh;
+            for (uint32_t idx = tid; idx < (S >> 1) * B; idx += ZKB_NTT_THREADS) {
+                uint32_t b = idx & (B - 1), pi = idx >> p.log_b;
+                uint32_t j = pi & (h - 1);
+                uint32_t s0 = ((pi >> lh) << (lh + 1)) | j;
+                fe w = tws[j << (p.log_s - 1 - lh)];
+                fe e = sm[(size_t)s0 * B + b];
+                fe o = fe_montmul(sm[(size_t)(s0 + h) * B + b], w);
+                sm[(size_t)s0 * B + b] = fe_add(e, o);
+                sm[(size_t)(s0 + h) * B + b] = fe_sub(e, o);
+            }
+        }
+        __syncthreads();
+        // ---- store (natural order) with the inter-pass twiddle ----------------------------
+        for (uint32_t idx = tid; idx < S * B; idx += ZKB_NTT_THREADS) {
+            uint32_t b = idx & (B - 1), k = idx >> p.log_b;
+            fe x = sm[(size_t)k * B + b];
+            if (p.has_tw) {
+                uint64_t col = (uint64_t)inner * B + b;
+                x = fe_montmul(x, pow2lvl(p.tw, (uint64_t)k * col * p.tw_mul));
+            }
+            if (p.has_post) x = fe_montmul(x, p.post);
+            fe_store(out + (uint64_t)k * p.st_k + (uint64_t)b * p.st_b, x);
+        }
+    } else {
+        const uint32_t pitch = S + 1;      // odd pitch: conflict-free column reads in the store
+        for (uint32_t idx = tid; idx < S * B; idx += ZKB_NTT_THREADS) {
+            uint32_t s = idx & (S - 1), b = idx >> p.log_s;
+            uint64_t lin = in_base + (uint64_t)s * p.ld_s + (uint64_t)b * p.ld_b;
+            fe x = fe_zero();
+            if (!p.has_valid || lin < p.n_valid) {
+                x = fe_ldg(in + lin);
+                if (p.has_scale) x = fe_montmul(x, pow2lvl(p.sc, lin));
+            }
+            sm[(size_t)b * pitch + s] = x;
+        }
+        // ---- DIF stages: natural in, bit-reversed out ------------------------------------
+        for (int lh = (int)p.log_s - 1; lh >= 0; lh--) {
+            __syncthreads();
+            const uint32_t h = 1u << lh;
+            for (uint32_t idx = tid; idx < (S >> 1) * B; idx += ZKB_NTT_THREADS) {
+                uint32_t pi = idx & ((S >> 1) - 1), b = idx >> (p.log_s - 1);
+                uint32_t j = pi & (h - 1);
+                uint32_t s0 = ((pi >> lh) << (lh + 1)) | j;
+                fe* row = sm + (size_t)b * pitch;
+                fe u = row[s0], v = row[s0 + h];
+                row[s0] = fe_add(u, v);
+                row[s0 + h] = fe_montmul(fe_sub(u, v), tws[j << (p.log_s - 1 - lh)]);
+            }
+        }
+        __syncthreads();
+        for (uint32_t idx = tid; idx < S * B; idx += ZKB_NTT_THREADS) {
+            uint32_t b = idx & (B - 1), k = idx >> p.log_b;
+            fe x = sm[(size_t)b * pitch + bitrev(k, p.log_s)];
+            if (p.has_tw) {
+                uint64_t col = (uint64_t)inner * B + b;
+                x = fe_montmul(x, pow2lvl(p.tw, (uint64_t)k * col * p.tw_mul));
+            }
+            if (p.has_post) x = fe_montmul(x, p.post);
+            fe_store(out + (uint64_t)k * p.st_k + (uint64_t)b * p.st_b, x);
+        }
+    }
+}
+
+static size_t pass_smem_bytes(const PassParams& p) {
+    size_t S = (size_t)1 << p.log_s, B = (size_t)1 << p.log_b;
+    return ((p.transposed ? B * (S + 1) : S * B) + S / 2) * sizeof(fe);
+}
+
+static int launch_pass(zkb_ctx* c, const PassParams& p, uint32_t tiles, uint32_t batch) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        ZKB_CUDA(c, cudaFuncSetAttribute(k_ntt_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+        attr_set = true;
+    }
+    dim3 grid(tiles, batch);
+    k_ntt_pass<<<grid, ZKB_NTT_THREADS, pass_smem_bytes(p), c->stream>>>(p);
+    c->launches++;
+    ZKB_CUDA(c, cudaGetLastError());
+    return 0;
+}
+
+struct NttOpts {
+    bool has_scale = false;   // x_i *= scale_base^i on load (coset LDE)
+    fe scale_base;
+    bool inverse = false;     // use root^-1 and multiply by n^-1
+};
+
+static const uint32_t TILE_LOG = 12;     // 4096 elements = 64 KiB per tile
+
+static int tw_s_table(zkb_ctx* c, const fe& root, uint32_t log_n, uint32_t log_s, const fe** out) {
+    // w_S = root^(N/S); table of w_S^j * R for j < S/2
+    fe ws = root;
+    for (uint32_t i = 0; i < log_n - log_s; i++) ws = h_mul(ws, ws);
+    DevPow t;
+    ZKB_TRY(get_pow_table(c, ws, log_s - 1, &t));
+    *out = t.lo;
+    return 0;
+}
+
+// d_in / d_out are device pointers; n = 2^log_n is the transform length; n_in <= n values
+// are read per column (the rest are zero).
+int ntt_exec(zkb_ctx* c, fe root, const fe* d_in, size_t n_in, size_t in_stride, fe* d_out,
+             size_t out_stride, size_t batch, uint32_t log_n, const NttOpts& o) {
+    if (batch == 0) return 0;
+    const uint64_t N = 1ull << log_n;
+    if (log_n == 0) {
+        // length-1 transform: identity (the LDE scaling offset^0 = 1 as well)
+        for (size_t bi = 0; bi < batch; bi++)
+            ZKB_CUDA(c, cudaMemcpyAsync(d_out + bi * out_stride, d_in + bi * in_stride, sizeof(fe),
+                                        cudaMemcpyDeviceToDevice, c->stream));
+        return 0;
+    }
+    if (log_n > 30) return set_err(c, ZKB_ERR_ARG, "ntt: length 2^%u not supported on one GPU", log_n);
+    if (o.inverse) root = h_inv(root);
+    PassParams base;
+    memset(&base, 0, sizeof(base));
+    if (o.inverse) {
+        base.has_post = 1;
+        base.post = fe_to_mont(h_inv(h_from_u64(N)));
+    }
+    DevPow sc{};
+    if (o.has_scale) ZKB_TRY(get_pow_table(c, o.scale_base, log_n, &sc));
+
+    uint32_t a, b2 = 0, c3;
+    int passes;
+    if (log_n <= TILE_LOG) { passes = 1; a = 0; c3 = log_n; }
+    else if (log_n <= 20) { passes = 2; a = (log_n + 1) / 2; c3 = log_n - a; }
+    else { passes = 3; a = (log_n + 2) / 3; b2 = (log_n - a + 1) / 2; c3 = log_n - a - b2; }
+    const uint64_t N1 = 1ull << a, N2 = 1ull << b2, N3 = 1ull << c3, M = N2 * N3;
+
+    if (passes == 1) {
+        PassParams p = base;
+        p.in = d_in; p.out = d_out;
+        p.log_s = log_n; p.log_b = 0; p.transposed = 1; p.inner_count = 1;
+        p.ld_s = 1; p.st_k = 1;
+        p.in_batch = in_stride; p.out_batch = out_stride;
+        p.has_valid = n_in < N; p.n_valid = n_in;
+        p.has_scale = o.has_scale; p.sc = sc;
+        ZKB_TRY(tw_s_table(c, root, log_n, log_n, &p.tw_s));
+        return launch_pass(c, p, 1, (uint32_t)batch);
+    }
+    DevPow tw;
+    ZKB_TRY(get_pow_table(c, root, log_n, &tw));
+    fe* A = nullptr;
+    ZKB_TRY(scratch_reserve(c, sizeof(fe) * N * batch, (void**)&A));
+    {   // pass 1: N1-point transforms down the columns (stride M), B adjacent columns per tile
+        PassParams p = base;
+        p.has_post = 0;
+        p.in = d_in; p.out = A;
+        p.log_s = a;
+        uint32_t lb = TILE_LOG - a;
+        if ((1ull << lb) > M) lb = ilog2_u64(M);
+        p.log_b = lb; p.transposed = 0;
+        p.inner_count = (uint32_t)(M >> lb);
+        p.ld_s = M; p.ld_b = 1; p.ld_outer = 0; p.ld_inner = 1ull << lb;
+        p.st_k = M; p.st_b = 1; p.st_outer = 0; p.st_inner = 1ull << lb;
+        p.in_batch = in_stride; p.out_batch = N;
+        p.has_valid = n_in < N; p.n_valid = n_in;
+        uint64_t rows = (n_in + M - 1) / M;            // rows n1 that hold any data
+        if (rows == 0) rows = 1;
+        uint32_t rl = ilog2_u64(rows);                 // ceil log2
+        p.skip_log = a - rl;
+        p.has_tw = 1; p.tw = tw; p.tw_mul = 1;
+        p.has_scale = o.has_scale; p.sc = sc;
+        ZKB_TRY(tw_s_table(c, root, log_n, a, &p.tw_s));
+        ZKB_TRY(launch_pass(c, p, p.inner_count, (uint32_t)batch));
+    }
+    if (passes == 3) {   // pass 2: N2-point transforms inside each row k1 (stride N3), in place
+        PassParams p = base;
+        p.has_post = 0;
+        p.in = A; p.out = A;
+        p.log_s = b2;
+        uint32_t lb = TILE_LOG - b2;
+        if ((1ull << lb) > N3) lb = c3;
+        p.log_b = lb; p.transposed = 0;
+        p.inner_count = (uint32_t)(N3 >> lb);
+        p.ld_s = N3; p.ld_b = 1; p.ld_outer = M; p.ld_inner = 1ull << lb;
+        p.st_k = N3; p.st_b = 1; p.st_outer = M; p.st_inner = 1ull << lb;
+        p.in_batch = N; p.out_batch = N;
+        p.has_tw = 1; p.tw = tw; p.tw_mul = N1;
+        ZKB_TRY(tw_s_table(c, root, log_n, b2, &p.tw_s));
+        ZKB_TRY(launch_pass(c, p, (uint32_t)(N1 * p.inner_count), (uint32_t)batch));
+    }
+    {   // final pass: N3-point transforms along contiguous runs, transposing store
+        PassParams p = base;
+        p.in = A; p.out = d_out;
+        p.log_s = c3;
+        uint32_t lb = TILE_LOG - c3;
+        if ((1ull << lb) > N1) lb = a;
+        p.log_b = lb; p.transposed = 1;
+        p.inner_count = (uint32_t)(N1 >> lb);
+        p.ld_s = 1; p.ld_b = M; p.ld_outer = N3; p.ld_inner = (1ull << lb) * M;
+        p.st_k = N1 * N2; p.st_b = 1; p.st_outer = N1; p.st_inner = 1ull << lb;
+        p.in_batch = N; p.out_batch = out_stride;
+        ZKB_TRY(tw_s_table(c, root, log_n, c3, &p.tw_s));
+        ZKB_TRY(launch_pass(c, p, (uint32_t)(N2 * p.inner_count), (uint32_t)batch));
+    }
+    return 0;
+}
+
+// ---- small elementwise kernels ------------------------------------------------------------
+__global__ void k_scale(const fe* in, fe* out, uint64_t n, DevPow sc) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    fe_store(out + i, fe_montmul(fe_ldg(in + i), pow2lvl(sc, i)));
+}
+__global__ void k_pointwise_mul(const fe* a, const fe* b, fe* out, uint64_t n) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    fe_store(out + i, fe_montmul(fe_to_mont(fe_ldg(a + i)), fe_ldg(b + i)));
+}
+// out = a / b pointwise; flags[0] set if any b[i] == 0 (field_element.rs:85 panics there)
+__global__ void k_pointwise_div(const fe* a, const fe* b, fe* out, uint64_t n, uint32_t* flag) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    fe d = fe_ldg(b + i);
+    if (fe_is_zero(d)) { atomicOr(flag, 1u); fe_store(out + i, fe_zero()); return; }
+    // d^(p-2) in Montgomery form, p-2 = 0xCB7FFFFF FFFFFFFF FFFFFFFF FFFFFFFF
+    fe base = fe_to_mont(d), acc = fe_mont_one();
+    for (int bit = 127; bit >= 0; bit--) {
+        acc = fe_montmul(acc, acc);
+        uint32_t word = (bit >= 96) ? 0xCB7FFFFFu : 0xFFFFFFFFu;
+        if ((word >> (bit & 31)) & 1u) acc = fe_montmul(acc, base);
+    }
+    fe_store(out + i, fe_montmul(acc, fe_ldg(a + i)));     // (1/d)*R * a / R
+}
+
+static int poly_degree(const fe* p, size_t n) {   // polynomial.rs:46-63; -1 for the zero polynomial
+    int d = -1;
+    for (size_t i = 0; i < n; i++) if (!fe_is_zero(p[i])) d = (int)i;
+    return d;
+}
+
+static int check_root(zkb_ctx* c, const fe& root, uint64_t order) {
+    // ntt_arithmetics.rs:11-24
+    if (order == 0 || (order & (order - 1))) return set_err(c, ZKB_ERR_ROOT_ORDER, "root_order %llu is not a power of two", (unsigned long long)order);
+    fe one = fe_from_u32(1);
+    if (!fe_eq(h_pow(root, order), one))
+        return set_err(c, ZKB_ERR_ROOT_ORDER, "supplied root does not have supplied root_order %llu", (unsigned long long)order);
+    if (order > 1 && fe_eq(h_pow(root, order / 2), one))
+        return set_err(c, ZKB_ERR_ROOT_ORDER, "supplied root is not a primitive of root_order %llu", (unsigned long long)order);
+    return 0;
+}
+
+}  // namespace zkb
+
+using namespace zkb;
+
+extern "C" {
+
+int zkb_ntt_batch(zkb_ctx* c, const uint8_t root[16], int inverse, const void* in, size_t n_in,
+                  size_t in_stride, void* out, size_t out_stride, size_t batch) {
+    if (!c || !root || !in || !out) return ZKB_ERR_ARG;
+    if (n_in == 0) return set_err(c, ZKB_ERR_EMPTY, "ntt: empty input");
+    if (batch == 0) return 0;
+    ZKB_CUDA(c, cudaSetDevice(c->device));
+    const uint64_t n = next_pow2_u64(n_in);
+    const uint32_t log_n = ilog2_u64(n);
+    if (batch > 1 && (in_stride < n_in || out_stride < n)) return set_err(c, ZKB_ERR_ARG, "ntt_batch: strides shorter than the columns");
+    const bool out_dev = is_device_ptr(out);
+    DevBuf bin, bout;
+    const void* d_in = nullptr;
+    size_t in_elems = batch > 1 ? in_stride * (batch - 1) + n_in : n_in;
+    size_t out_elems = batch > 1 ? out_stride * (batch - 1) + n : n;
+    ZKB_TRY(stage_in(c, in, in_elems * sizeof(fe), bin, &d_in));
+    fe* d_out = (fe*)out;
+    if (!out_dev) { ZKB_TRY(bout.alloc(c, out_elems * sizeof(fe))); d_out = (fe*)bout.p; }
+    if (n_in < 2) {
+        // ntt.rs: bit_reverse_copy returns a 1-element input unchanged; intt returns it as is
+        for (size_t bi = 0; bi < batch; bi++)
+            ZKB_CUDA(c, cudaMemcpyAsync(d_out + bi * out_stride, (const fe*)d_in + bi * in_stride, sizeof(fe), cudaMemcpyDeviceToDevice, c->stream));
+    } else {
+        NttOpts o;
+        o.inverse = inverse != 0;
+        ZKB_TRY(ntt_exec(c, h_load(root), (const fe*)d_in, n_in, in_stride, d_out, out_stride, batch, log_n, o));
+    }
+    if (!out_dev) ZKB_CUDA(c, cudaMemcpyAsync(out, d_out, out_elems * sizeof(fe), cudaMemcpyDeviceToHost, c->stream));
+    if (!out_dev || bin.p) ZKB_CUDA(c, cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int zkb_ntt(zkb_ctx* c, const uint8_t root[16], const void* in, size_t n_in, void* out) {
+    return zkb_ntt_batch(c, root, 0, in, n_in, 0, out, 0, 1);
+}
+int zkb_intt(zkb_ctx* c, const uint8_t root[16], const void* in, size_t n_in, void* out) {
+    return zkb_ntt_batch(c, root, 1, in, n_in, 0, out, 0, 1);
+}
+
+int zkb_poly_scale(zkb_ctx* c, const uint8_t factor[16], const void* coeffs, size_t n, void* out) {
+    if (!c || !factor || (n && (!coeffs || !out))) return ZKB_ERR_ARG;
+    if (n == 0) return 0;
+    ZKB_CUDA(c, cudaSetDevice(c->device));
+    const bool out_dev = is_device_ptr(out);
+    DevBuf bin, bout;
+    const void* d_in = nullptr;
+    ZKB_TRY(stage_in(c, coeffs, n * sizeof(fe), bin, &d_in));
+    fe* d_out = (fe*)out;
+    if (!out_dev) { ZKB_TRY(bout.alloc(c, n * sizeof(fe))); d_out = (fe*)bout.p; }
+    DevPow sc;
+    ZKB_TRY(get_pow_table(c, h_load(factor), ilog2_u64(next_pow2_u64(n)), &sc));
+    k_scale<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>((const fe*)d_in, d_out, n, sc);
+    c->launches++;
+    ZKB_CUDA(c, cudaGetLastError());
+    if (!out_dev) ZKB_CUDA(c, cudaMemcpyAsync(out, d_out, n * sizeof(fe), cudaMemcpyDeviceToHost, c->stream));
+    if (!out_dev || bin.p) ZKB_CUDA(c, cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int zkb_coset_lde_batch(zkb_ctx* c, const uint8_t omega[16], uint64_t order, const uint8_t offset[16],
+                        const void* coeffs, size_t n_coeffs, size_t in_stride, void* out,
+                        size_t out_stride, size_t batch) {
+    if (!c || !omega || !offset || !out) return ZKB_ERR_ARG;
+    if (order == 0 || (order & (order - 1))) return set_err(c, ZKB_ERR_ARG, "coset_lde: order %llu is not a power of two", (unsigned long long)order);
+    if (n_coeffs > order) return set_err(c, ZKB_ERR_TOO_LONG, "coset_lde: %zu coefficients exceed root_order %llu", n_coeffs, (unsigned long long)order);
+    if (batch == 0) return 0;
+    if (batch > 1 && (in_stride < n_coeffs || out_stride < order)) return set_err(c, ZKB_ERR_ARG, "coset_lde_batch: strides shorter than the columns");
+    ZKB_CUDA(c, cudaSetDevice(c->device));
+    const bool out_dev = is_device_ptr(out);
+    size_t out_elems = batch > 1 ? out_stride * (batch - 1) + order : order;
+    DevBuf bin, bout;
+    fe* d_out = (fe*)out;
+    if (!out_dev) { ZKB_TRY(bout.alloc(c, out_elems * sizeof(fe))); d_out = (fe*)bout.p; }
+    if (n_coeffs == 0) {
+        for (size_t bi = 0; bi < batch; bi++)
+            ZKB_CUDA(c, cudaMemsetAsync(d_out + bi * out_stride, 0, order * sizeof(fe), c->stream));
+    } else {
+        if (!coeffs) return ZKB_ERR_ARG;
+        const void* d_in = nullptr;
+        size_t in_elems = batch > 1 ? in_stride * (batch - 1) + n_coeffs : n_coeffs;
+        ZKB_TRY(stage_in(c, coeffs, in_elems * sizeof(fe), bin, &d_in));
+        NttOpts o;
+        o.has_scale = true;
+        o.scale_base = h_load(offset);
+        ZKB_TRY(ntt_exec(c, h_load(omega), (const fe*)d_in, n_coeffs, in_stride, d_out, out_stride, batch, ilog2_u64(order), o));
+    }
+    if (!out_dev) ZKB_CUDA(c, cudaMemcpyAsync(out, d_out, out_elems * sizeof(fe), cudaMemcpyDeviceToHost, c->stream));
+    if (!out_dev || bin.p) ZKB_CUDA(c, cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int zkb_coset_lde(zkb_ctx* c, const uint8_t omega[16], uint64_t order, const uint8_t offset[16],
+                  const void* coeffs, size_t n_coeffs, void* out) {
+    return zkb_coset_lde_batch(c, omega, order, offset, coeffs, n_coeffs, 0, out, 0, 1);
+}
+
+// fast_multiply / fast_coset_divide: operands are small host polynomials in the reference
+// (<= the omicron domain); degrees are taken on the host, the transforms run on the device.
+static int poly_binop(zkb_ctx* c, bool divide, const uint8_t root_b[16], uint64_t root_order,
+                      const uint8_t* offset_b, const void* lhs, size_t n_lhs, const void* rhs,
+                      size_t n_rhs, void* out, size_t* n_out) {
+    if (!c || !root_b || !n_out || !out) return ZKB_ERR_ARG;
+    if (is_device_ptr(lhs) || is_device_ptr(rhs) || is_device_ptr(out))
+        return set_err(c, ZKB_ERR_ARG, "poly_mul/coset_div take host pointers");
+    ZKB_CUDA(c, cudaSetDevice(c->device));
+    fe root = h_load(root_b);
+    ZKB_TRY(check_root(c, root, root_order));
+    const fe* L = (const fe*)lhs; const fe* R = (const fe*)rhs;
+    int dl = poly_degree(L, n_lhs), dr = poly_degree(R, n_rhs);
+    uint64_t degree; size_t result_len;
+    if (!divide) {
+        if (dl < 0 || dr < 0) { *n_out = 0; return 0; }               // :26-28
+        degree = (uint64_t)dl + (uint64_t)dr; result_len = degree + 1;
+    } else {
+        if (dr < 0) return set_err(c, ZKB_ERR_DIV_ZERO, "cannot divide by zero polynomial");      // :258
+        if (dl < 0) { *n_out = 0; return 0; }                         // :260-262
+        if (dl < dr) return set_err(c, ZKB_ERR_DEGREE, "cannot divide by polynomial of larger degree");
+        degree = (uint64_t)dl; result_len = (size_t)(dl - dr + 1);
+    }
+    uint64_t order = root_order;
+    while (degree < order / 2) { root = h_mul(root, root); order /= 2; }   // :38-41 / :278-281
+    if (n_lhs > order || n_rhs > order)
+        return set_err(c, ZKB_ERR_TOO_LONG, "operand longer than the transform order %llu", (unsigned long long)order);
+    const uint32_t log_n = ilog2_u64(order);
+    DevBuf buf;
+    ZKB_TRY(buf.alloc(c, sizeof(fe) * order * 4 + 16));
+    fe* dL = (fe*)buf.p; fe* dR = dL + order; fe* eL = dR + order; fe* eR = eL + order;
+    uint32_t* flag = (uint32_t*)(eR + order);
+    ZKB_CUDA(c, cudaMemsetAsync(buf.p, 0, sizeof(fe) * order * 4 + 16, c->stream));
+    ZKB_CUDA(c, cudaMemcpyAsync(dL, L, sizeof(fe) * n_lhs, cudaMemcpyHostToDevice, c->stream));
+    ZKB_CUDA(c, cudaMemcpyAsync(dR, R, sizeof(fe) * n_rhs, cudaMemcpyHostToDevice, c->stream));
+    NttOpts fwd;
+    if (divide) { fwd.has_scale = true; fwd.scale_base = h_load(offset_b); }
+    if (order == 1) {
+        ZKB_CUDA(c, cudaMemcpyAsync(eL, dL, sizeof(fe), cudaMemcpyDeviceToDevice, c->stream));
+        ZKB_CUDA(c, cudaMemcpyAsync(eR, dR, sizeof(fe), cudaMemcpyDeviceToDevice, c->stream));
+    } else {
+        ZKB_TRY(ntt_exec(c, root, dL, order, 0, eL, 0, 1, log_n, fwd));
+        ZKB_TRY(ntt_exec(c, root, dR, order, 0, eR, 0, 1, log_n, fwd));
+    }
+    unsigned blocks = (unsigned)((order + 127) / 128);
+    if (divide) k_pointwise_div<<<blocks, 128, 0, c->stream>>>(eL, eR, dL, order, flag);
+    else k_pointwise_mul<<<blocks, 128, 0, c->stream>>>(eL, eR, dL, order);
+    c->launches++;
+    ZKB_CUDA(c, cudaGetLastError());
+    if (order > 1) {
+        NttOpts inv; inv.inverse = true;
+        ZKB_TRY(ntt_exec(c, root, dL, order, 0, dR, 0, 1, log_n, inv));
+    } else {
+        ZKB_CUDA(c, cudaMemcpyAsync(dR, dL, sizeof(fe), cudaMemcpyDeviceToDevice, c->stream));
+    }
+    size_t keep = result_len < order ? result_len : (size_t)order;    // coeffs.drain(result_degree..)
+    if (divide) {
+        DevPow sc;
+        ZKB_TRY(get_pow_table(c, h_inv(h_load(offset_b)), log_n, &sc));
+        k_scale<<<(unsigned)((keep + 255) / 256), 256, 0, c->stream>>>(dR, dR, keep, sc);
+        c->launches++;
+    }
+    uint32_t hflag = 0;
+    ZKB_CUDA(c, cudaMemcpyAsync(out, dR, sizeof(fe) * keep, cudaMemcpyDeviceToHost, c->stream));
+    ZKB_CUDA(c, cudaMemcpyAsync(&hflag, flag, 4, cudaMemcpyDeviceToHost, c->stream));
+    ZKB_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (divide && hflag) return set_err(c, ZKB_ERR_DIV_ZERO, "divide by zero");
+    *n_out = keep;
+    return 0;
+}
+
+int zkb_poly_mul(zkb_ctx* c, const uint8_t root[16], uint64_t root_order, const void* lhs, size_t n_lhs,
+                 const void* rhs, size_t n_rhs, void* out, size_t* n_out) {
+    return poly_binop(c, false, root, root_order, nullptr, lhs, n_lhs, rhs, n_rhs, out, n_out);
+}
+int zkb_coset_div(zkb_ctx* c, const uint8_t root[16], uint64_t root_order, const uint8_t offset[16],
+                  const void* lhs, size_t n_lhs, const void* rhs, size_t n_rhs, void* out, size_t* n_out) {
+    if (!offset) return ZKB_ERR_ARG;
+    return poly_binop(c, true, root, root_order, offset, lhs, n_lhs, rhs, n_rhs, out, n_out);
+}
+
+}  // extern "C"
