@@ -58,6 +58,12 @@ const char* zkb_last_error(const zkb_ctx* ctx);
 int zkb_ctx_sync(zkb_ctx* ctx);                       /* cudaStreamSynchronize             */
 uint64_t zkb_ctx_launches(const zkb_ctx* ctx);        /* kernels launched so far           */
 const char* zkb_version(void);
+/* Per-kernel-class device timing (CUDA events on the context's stream around every launch;
+ * this is what bench.py's roofline.achieved is computed from).  enable: 0 = off, 1 = on,
+ * 2 = on + reset the accumulators.  zkb_kernel_name(id) is NULL past the last class. */
+int zkb_ctx_profile(zkb_ctx* ctx, int enable);
+int zkb_ctx_profile_read(zkb_ctx* ctx, int kernel_id, double* total_ms, uint64_t* count);
+const char* zkb_kernel_name(int kernel_id);
 /* plain device-memory helpers for hosts that do not bring their own allocator */
 int zkb_dev_alloc(zkb_ctx* ctx, size_t bytes, void** dptr);
 int zkb_dev_free(zkb_ctx* ctx, void* dptr);
@@ -150,6 +156,12 @@ typedef int (*zkb_fs_callback)(void* user, uint32_t round, const uint8_t root[64
  * next layer's leaf hashing).  The caller pushes Codeword(last) itself (zkb_fri_last_codeword). */
 int zkb_fri_commit(zkb_ctx* ctx, const zkb_fri_params* p, const void* codeword, size_t n,
                    zkb_fs_callback fs, void* user, zkb_fri_layers** layers);
+/* The Stark prover's last two steps in one call (stark.rs:500-522): coset-LDE the
+ * coefficient vector to p->domain_length evaluations on p->offset * <p->omega>
+ * (fast_coset_evaluate ntt_arithmetics.rs:161-170), then FRI::commit on that codeword
+ * without it ever leaving HBM.  Layer 0 of `layers` is the codeword. */
+int zkb_lde_fri_commit(zkb_ctx* ctx, const zkb_fri_params* p, const void* coeffs, size_t n_coeffs,
+                       zkb_fs_callback fs, void* user, zkb_fri_layers** layers);
 uint64_t zkb_fri_layer_count(const zkb_fri_layers* l);
 uint64_t zkb_fri_layer_len(const zkb_fri_layers* l, uint64_t round);
 int zkb_fri_layer_root(const zkb_fri_layers* l, uint64_t round, uint8_t root[64]);
@@ -181,6 +193,12 @@ int zkb_ps_push_value(zkb_ps* ps, const uint8_t v[16]);
 size_t zkb_ps_digest(const zkb_ps* ps, uint8_t* out, size_t cap);
 /* fiat_shamir_prover(num_bytes) proof_stream.rs:36-40 */
 int zkb_ps_fiat_shamir(const zkb_ps* ps, size_t num_bytes, uint8_t* out);
+/* FRI::commit (fri.rs:115-172, including the final push of Codeword(last)) against the
+ * library's own proof stream; the layers stay on the device for zkb_fri_query. */
+int zkb_fri_commit_ps(zkb_ctx* ctx, const zkb_fri_params* p, const void* codeword, size_t n, zkb_ps* ps,
+                      zkb_fri_layers** layers);
+int zkb_lde_fri_commit_ps(zkb_ctx* ctx, const zkb_fri_params* p, const void* coeffs, size_t n_coeffs, zkb_ps* ps,
+                          zkb_fri_layers** layers);
 /* FRI::prove fri.rs:210-248 end to end against a proof stream: commit, push the last
  * codeword, sample the top-level indices, push all Leafs/Path objects.  top_indices_out
  * receives num_colinearity_tests indices (the function's return value in the reference). */

@@ -1,0 +1,437 @@
+"""GPU parity: the CUDA path (through the C ABI of libzkb200.so and its Python mirror of the
+reference's API) against the oracle, bit-exact.  Run on the B200 box: pytest -m gpu.
+
+Layout follows the reference's own tests: known-answer vectors first
+(src/fft/ntt.rs:78-130, src/merkle_root.rs:107-244), then randomised fast-vs-schoolbook
+properties (src/fft/ntt_arithmetics.rs:356-517), then FRI round trips
+(src/fri.rs:451-531), plus full-size cases from BASELINE.json's configs."""
+import hashlib
+import json
+import os
+import random
+
+import numpy as np
+import pytest
+
+import zk_stark_tutor_b200 as zk
+from zk_stark_tutor_b200 import proof_stream as ZPS
+from oracle import cbind as C, field as F, merkle as M, ntt as N, proof_stream as PS, fastfri
+from oracle.fri import FRI as OFRI
+
+pytestmark = pytest.mark.gpu
+P = F.P
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+KATS = json.load(open(os.path.join(GOLD, "reference_kats.json")))
+VEC = json.load(open(os.path.join(GOLD, "oracle_vectors.json")))
+rnd = random.Random(99)
+
+
+def rvals(n):
+    return [rnd.randrange(P) for _ in range(n)]
+
+
+def sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = zk.Context(0)            # raises if the CUDA library / device is missing: no fallback
+    yield c
+    c.close()
+
+
+def cuda(arr):
+    import torch
+    return torch.from_numpy(np.ascontiguousarray(arr).view(np.int64)).cuda()
+
+
+def host(t):
+    return t.cpu().numpy().view(np.uint64)
+
+
+# ---------------------------------------------------------------- NTT ----------------------
+def test_ntt_reference_kats(ctx):
+    w = F.primitive_nth_root(16)
+    k = KATS["ntt16"]
+    assert zk.ntt(w, [int(v) for v in k["in"]], ctx) == [int(v) for v in k["out"]]
+    k = KATS["intt16"]
+    assert zk.ntt(w, [int(v) for v in k["values"]], ctx) == [int(v) for v in k["coeffs"]]
+    assert zk.intt(w, [int(v) for v in k["coeffs"]], ctx) == [int(v) for v in k["values"]]
+
+
+@pytest.mark.parametrize("log_n", list(range(1, 15)) + [16, 17, 20, 21, 22])
+def test_ntt_vs_oracle(ctx, log_n):
+    n = 1 << log_n
+    x = C.synth(0x5EED0002, n)
+    w = F.primitive_nth_root(n)
+    want = C.ntt(w, x)
+    got = zk.ntt(w, x, ctx)
+    assert np.array_equal(got, want)
+    back = zk.intt(w, got, ctx)
+    assert np.array_equal(back, x)
+    assert np.array_equal(zk.intt(w, x, ctx), C.ntt(w, x, inverse=True))
+    for g in VEC["ntt"]:
+        if g["log_n"] == log_n:
+            assert sha(got) == g["sha256_out"]
+
+
+def test_ntt_edge_values(ctx):
+    n = 64
+    w = F.primitive_nth_root(n)
+    for xs in ([0] * n, [P - 1] * n, [1] + [0] * (n - 1), [P - 1, 1] * (n // 2), [(1 << 96) - 1] * n, [1 << 127] * n):
+        assert zk.ntt(w, xs, ctx) == N.ntt(w, xs)
+
+
+@pytest.mark.parametrize("n_in", [1, 2, 3, 5, 7, 100, 1000, 4097, 70000, (1 << 20) + 1])
+def test_ntt_ragged_lengths_are_zero_padded(ctx, n_in):
+    x = C.synth(11, n_in)
+    n = C.next_pow2(n_in)
+    w = F.primitive_nth_root(max(n, 2))
+    got = zk.ntt(w, x, ctx)
+    assert got.shape[0] == n
+    assert np.array_equal(got, C.ntt(w, x))
+    gi = zk.intt(w, x, ctx)
+    assert np.array_equal(gi, C.ntt(w, x, inverse=True))       # n_in == 1: identity (ntt.rs:55-57)
+
+
+def test_ntt_empty_input_is_an_error(ctx):
+    with pytest.raises(zk.ZkbError) as e:                       # ntt.rs:11 index panic
+        zk.ntt(F.primitive_nth_root(2), np.empty((0, 2), dtype=np.uint64), ctx)
+    assert e.value.code == -3
+
+
+def test_ntt_device_resident_and_batched(ctx):
+    n, b = 1 << 13, 5
+    w = F.primitive_nth_root(n)
+    cols = np.stack([C.synth(100 + i, n) for i in range(b)])
+    want = np.stack([C.ntt(w, cols[i]) for i in range(b)])
+    got = zk.ntt_batch(w, cuda(cols.reshape(-1, 2)).reshape(b, n, 2), ctx=ctx)
+    ctx.sync()
+    assert np.array_equal(host(got).reshape(b, n, 2), want)
+    back = zk.ntt_batch(w, got, inverse=True, ctx=ctx)
+    ctx.sync()
+    assert np.array_equal(host(back).reshape(b, n, 2), cols)
+    assert np.array_equal(zk.ntt_batch(w, cols, ctx=ctx), want)     # host buffers, ragged tail
+    rag = cols[:, :5000, :].copy()
+    want_r = np.stack([C.ntt(w, rag[i]) for i in range(b)])
+    assert np.array_equal(zk.ntt_batch(w, rag, ctx=ctx), want_r)
+
+
+@pytest.mark.parametrize("log_n", [24])
+def test_ntt_full_size_roundtrip_and_spot(ctx, log_n):
+    """BASELINE configs[1] top size: oracle on the whole vector (C oracle, seconds)."""
+    n = 1 << log_n
+    x = C.synth(0x5EED0002, n)
+    w = F.primitive_nth_root(n)
+    d = cuda(x)
+    y = zk.ntt(w, d, ctx)
+    back = zk.intt(w, y, ctx)
+    ctx.sync()
+    assert np.array_equal(host(back), x)
+    assert np.array_equal(host(y), C.ntt(w, x))
+
+
+# ---------------------------------------------------------------- LDE / polynomials --------
+def test_scale_kat_and_random(ctx):
+    k = KATS["scale"]
+    assert zk.scale(k["coeffs"], k["factor"], ctx) == k["out"]
+    xs = rvals(5000)
+    f = rvals(1)[0]
+    assert zk.scale(xs, f, ctx) == N.scale(xs, f)
+
+
+@pytest.mark.parametrize("log_n,n_coeffs", [(1, 1), (2, 1), (3, 2), (6, 16), (6, 13), (10, 256), (12, 1000), (12, 4096), (13, 2048),
+                                            (14, 4096), (16, 1 << 14), (17, 40000), (20, 1 << 18), (21, 1 << 19), (22, 1 << 20), (22, 3)])
+def test_coset_lde_vs_oracle(ctx, log_n, n_coeffs):
+    n = 1 << log_n
+    x = C.synth(0x5EED0003, n_coeffs)
+    w = F.primitive_nth_root(n)
+    want = C.coset_lde(w, n, F.GENERATOR, x)
+    got = zk.fast_coset_evaluate(w, n, F.GENERATOR, x, ctx)
+    assert np.array_equal(got, want)
+    for g in VEC["lde"]:
+        if g["log_n"] == log_n and g["n_coeffs"] == n_coeffs:
+            assert sha(got) == g["sha256_out"]
+            assert zk.MerkleRoot.commit(got, ctx).hex() == g["merkle_root"]
+
+
+def test_coset_lde_like_reference_property_test(ctx):
+    # ntt_arithmetics.rs:470-489: fast_coset_evaluate == evaluation on offset * w^k
+    n = 64
+    w = F.primitive_nth_root(n)
+    for _ in range(5):
+        a = rvals(rnd.randrange(1, 31))
+        ev = zk.fast_coset_evaluate(w, n, F.GENERATOR, a, ctx)
+        assert ev == N.fast_coset_evaluate(w, n, F.GENERATOR, a)
+        for k in (0, 1, 17, 63):
+            x = F.GENERATOR * F.fpow(w, k) % P
+            assert ev[k] == sum(c * F.fpow(x, i) for i, c in enumerate(a)) % P
+
+
+def test_coset_lde_edges(ctx):
+    w = F.primitive_nth_root(8)
+    assert zk.fast_coset_evaluate(w, 8, F.GENERATOR, [], ctx) == [0] * 8          # zero polynomial
+    with pytest.raises(zk.ZkbError) as e:                                          # ntt_arithmetics.rs:168 underflow
+        zk.fast_coset_evaluate(w, 8, F.GENERATOR, list(range(9)), ctx)
+    assert e.value.code == -5
+    assert zk.fast_coset_evaluate(1, 1, F.GENERATOR, [5], ctx) == [5]
+
+
+def test_coset_lde_batch_device(ctx):
+    n, nc, b = 1 << 14, 1 << 12, 6
+    w = F.primitive_nth_root(n)
+    cols = np.stack([C.synth(200 + i, nc) for i in range(b)])
+    want = np.stack([C.coset_lde(w, n, F.GENERATOR, cols[i]) for i in range(b)])
+    got = zk.coset_lde_batch(w, n, F.GENERATOR, cuda(cols.reshape(-1, 2)).reshape(b, nc, 2), ctx)
+    ctx.sync()
+    assert np.array_equal(host(got).reshape(b, n, 2), want)
+
+
+def test_fast_multiply_and_divide_vs_schoolbook(ctx):
+    # ntt_arithmetics.rs:356-380 and :491-517
+    n = 64
+    w = F.primitive_nth_root(n)
+    for _ in range(10):
+        a, b = rvals(rnd.randrange(1, 31)), rvals(rnd.randrange(1, 31))
+        school = [0] * (len(a) + len(b) - 1)
+        for i, x in enumerate(a):
+            for j, y in enumerate(b):
+                school[i + j] = (school[i + j] + x * y) % P
+        assert zk.fast_multiply(w, n, a, b, ctx) == school == N.fast_multiply(w, n, a, b)
+        assert zk.fast_coset_divide(w, n, F.GENERATOR, school, b, ctx) == a
+    # trailing zero coefficients / order shrink / zero operands
+    assert zk.fast_multiply(w, n, [1, 2, 0, 0], [3, 0], ctx) == N.fast_multiply(w, n, [1, 2, 0, 0], [3, 0])
+    assert zk.fast_multiply(w, n, [0, 0], [3, 1], ctx) == []
+    assert zk.fast_multiply(w, n, [7], [9], ctx) == [63]
+    big_w = F.primitive_nth_root(1 << 14)
+    a, b = rvals(5000), rvals(3000)
+    assert zk.fast_multiply(big_w, 1 << 14, a, b, ctx) == N.fast_multiply(big_w, 1 << 14, a, b)
+    with pytest.raises(zk.ZkbError) as e:
+        zk.fast_multiply(w, 32, [1], [1], ctx)                   # root does not have that order
+    assert e.value.code == -6
+    with pytest.raises(zk.ZkbError) as e:
+        zk.fast_coset_divide(w, n, F.GENERATOR, [1, 2], [0], ctx)
+    assert e.value.code == -7
+    with pytest.raises(zk.ZkbError) as e:
+        zk.fast_coset_divide(w, n, F.GENERATOR, [1, 2], [1, 2, 3], ctx)
+    assert e.value.code == -11
+    assert zk.fast_coset_divide(w, n, F.GENERATOR, [0], [1, 2, 3], ctx) == []
+
+
+# ---------------------------------------------------------------- Merkle -------------------
+def test_merkle_reference_kats(ctx):
+    for k in KATS["merkle"]["commit"]:
+        assert zk.MerkleRoot.commit(k["leafs"], ctx).hex() == k["root"]
+    o = KATS["merkle"]["open"]
+    path = zk.MerkleRoot.open(o["index"], o["leafs"], ctx)
+    assert [h.hex() for h in path] == o["path"]
+    root = bytes.fromhex(KATS["merkle"]["commit"][-1]["root"])
+    assert zk.MerkleRoot.verify(root, 1, path, 456)
+    assert not zk.MerkleRoot.verify(root, 1, path, 5462)
+    assert not zk.MerkleRoot.verify(root, 0, path, 456)
+
+
+@pytest.mark.parametrize("log_n", list(range(0, 17)) + [20, 21])
+def test_merkle_commit_vs_oracle(ctx, log_n):
+    n = 1 << log_n
+    vals = C.synth(0x5EED0004, n)
+    want = C.merkle(vals)
+    assert zk.MerkleRoot.commit(vals, ctx) == want
+    assert zk.MerkleRoot.commit(cuda(vals), ctx) == want
+    for g in VEC["merkle"]:
+        if g["log_n"] == log_n:
+            assert want.hex() == g["root"]
+
+
+def test_merkle_leaf_encoding_edges(ctx):
+    """decimal-ASCII leaf preimages of every length 1..39 (field_element.rs:46-50)"""
+    vals = [0, 1, 9] + [10 ** k for k in range(1, 39)] + [10 ** k - 1 for k in range(1, 39)] + [P - 1, P - 2, 1 << 64, (1 << 64) - 1,
+            (1 << 96) - 1, 1 << 96, 1 << 127, 5462, 11]
+    vals = (vals + [3] * 128)[:128]
+    assert zk.MerkleRoot.commit(vals, ctx) == M.commit(vals)
+    big = (vals * 16)[:2048]                    # through the 1024-leaf tile kernel as well
+    assert zk.MerkleRoot.commit(big, ctx) == C.merkle(C.to_arr(big))
+
+
+def test_merkle_not_power_of_two(ctx):
+    for n in (0, 3, 6, 1000):
+        with pytest.raises(zk.ZkbError) as e:                    # merkle_root.rs:9
+            zk.MerkleRoot.commit(C.synth(1, n) if n else np.empty((0, 2), dtype=np.uint64), ctx)
+        assert e.value.code == -4
+
+
+@pytest.mark.parametrize("log_n", [1, 2, 5, 6, 10, 11, 12, 16, 20])
+def test_merkle_open_vs_oracle(ctx, log_n):
+    n = 1 << log_n
+    vals = C.synth(0x5EED0005, n)
+    t = fastfri.Tree(vals)
+    tree = zk.MerkleTree(cuda(vals), ctx)
+    assert tree.root() == t.root
+    idx = list(range(n)) if n <= 64 else [0, 1, 31, 32, 33, n // 2 - 1, n // 2, n - 2, n - 1] + [rnd.randrange(n) for _ in range(40)]
+    paths = tree.open_many(idx)
+    vl = C.from_arr(vals[idx])
+    for i, p, v in zip(idx, paths, vl):
+        assert p == t.open(i)
+        assert zk.MerkleRoot.verify(t.root, i, p, v)
+        assert M.verify(t.root, i, p, v)
+    with pytest.raises(zk.ZkbError) as e:
+        tree.open(n)
+    assert e.value.code == -8
+    tree.close()
+
+
+# ---------------------------------------------------------------- FRI ----------------------
+@pytest.mark.parametrize("log_n", [1, 2, 5, 10, 11, 12, 15, 20])
+def test_fri_fold_vs_oracle(ctx, log_n):
+    n = 1 << log_n
+    w = F.primitive_nth_root(n)
+    cw = C.synth(0x5EED0006, n)
+    alpha = rvals(1)[0]
+    fri = zk.FRI(F.GENERATOR, w, n, 4, 1, ctx)
+    got = fri.fold(cw, alpha)
+    assert np.array_equal(got, C.fri_fold(cw, alpha, F.GENERATOR, w))
+    if n <= 1 << 10:
+        assert C.from_arr(got) == OFRI.fold(C.from_arr(cw), alpha, F.GENERATOR, w)      # literal fri.rs:150-159
+    off2 = F.mul(F.GENERATOR, F.GENERATOR)
+    assert np.array_equal(fri.fold(cw, 0, off2, w), C.fri_fold(cw, 0, off2, w))
+
+
+def _codeword(log_n, seed=0x5EED0003):
+    n = 1 << log_n
+    w = F.primitive_nth_root(n)
+    return n, w, C.coset_lde(w, n, F.GENERATOR, C.synth(seed, n // 4))
+
+
+def test_fri_prove_like_reference_test(ctx):
+    # src/fri.rs:451-531: degree 63, N = 256, ef 4, 17 colinearity tests
+    degree, ef, ncc = 63, 4, 17
+    n = (degree + 1) * ef
+    w = F.primitive_nth_root(n)
+    poly = list(range(degree + 1))
+    codeword = zk.ntt(w, poly + [0] * (n - len(poly)), ctx)
+    assert codeword == N.ntt(w, poly + [0] * (n - len(poly)))
+    fri = zk.FRI(F.GENERATOR, w, n, ef, ncc, ctx)
+    ofri = OFRI(F.GENERATOR, w, n, ef, ncc)
+    ps = zk.IndependentProofStream()
+    top = fri.prove(codeword, ps)
+    ops = PS.IndependentProofStream()
+    assert top == ofri.prove(codeword, ops)
+    assert ps.digest() == ops.digest()                      # final proof-stream bytes, bit-exact
+    points = []
+    assert ofri.verify(PS.IndependentProofStream(PS.parse(ps.digest())), points) is None
+    for x, y in points:
+        assert sum(c * F.fpow(w, x * i) for i, c in enumerate(poly)) % P == y
+    # disturbed codeword must be rejected by the (restated) reference verifier (fri.rs:514-528)
+    bad = [0] * (degree // 3) + codeword[degree // 3:]
+    ps = zk.IndependentProofStream()
+    fri.prove(bad, ps)
+    assert ofri.verify(PS.IndependentProofStream(PS.parse(ps.digest())), []) is not None
+
+
+@pytest.mark.parametrize("case", VEC["fri"], ids=lambda c: "2^%d%s" % (c["log_n"], "-sig" if c["document"] else ""))
+def test_fri_prove_vs_oracle_and_golden(ctx, case):
+    log_n, ncc, doc = case["log_n"], case["ncc"], case["document"]
+    n, w, cw = _codeword(log_n, case["seed"])
+    fri = zk.FRI(F.GENERATOR, w, n, 4, ncc, ctx)
+    ofri = OFRI(F.GENERATOR, w, n, 4, ncc)
+    # (1) one-call C path (zkb_fri_prove) with the library's own proof stream
+    ps = zk.SignatureProofStream(doc.encode()) if doc else zk.IndependentProofStream()
+    top = fri.prove(cuda(cw), ps)
+    d = ps.digest()
+    assert top == case["top_indices"]
+    assert len(d) == case["proof_bytes"]
+    assert hashlib.sha256(d).hexdigest() == case["sha256_proof"]
+    # (2) commit/query through the Fiat-Shamir callback with a foreign (oracle) proof stream
+    ops = PS.SignatureProofStream(doc.encode()) if doc else PS.IndependentProofStream()
+    layers = fri.commit(cw, ops)
+    assert [layers.root(r).hex() for r in range(len(layers))] == case["roots"]
+    layers.close()
+    if log_n <= 16:
+        # (3) against the oracle run live, layer by layer
+        ops2 = PS.SignatureProofStream(doc.encode()) if doc else PS.IndependentProofStream()
+        top2, codewords, trees = fastfri.prove(ofri, cw, ops2)
+        assert top2 == top and ops2.digest() == d
+        ops3 = PS.SignatureProofStream(doc.encode()) if doc else PS.IndependentProofStream()
+        layers = fri.commit(cuda(cw), ops3)
+        for r in range(len(layers)):
+            assert np.array_equal(layers.codeword(r), codewords[r])
+        layers.close()
+        vps = PS.SignatureProofStream(doc.encode(), PS.parse(d)) if doc else PS.IndependentProofStream(PS.parse(d))
+        assert ofri.verify(vps, []) is None
+
+
+def test_fri_python_stream_path_equals_c_path(ctx):
+    n, w, cw = _codeword(13)
+    fri = zk.FRI(F.GENERATOR, w, n, 4, 64, ctx)
+    a = zk.IndependentProofStream()
+    b = zk.IndependentProofStream()
+    b.force_python = True
+    assert fri.prove(cw, a) == fri.prove(cw, b)
+    assert a.digest() == b.digest()
+
+
+def test_fri_errors(ctx):
+    n, w, cw = _codeword(10)
+    with pytest.raises(AssertionError):                          # fri.rs:215-219
+        zk.FRI(F.GENERATOR, w, n * 2, 4, 64, ctx).prove(cw, zk.IndependentProofStream())
+    with pytest.raises(zk.ZkbError) as e:                        # fri.rs:133
+        zk.FRI(F.GENERATOR, F.mul(w, 3), n, 4, 64, ctx).prove(cw, zk.IndependentProofStream())
+    assert e.value.code == -6
+    with pytest.raises(zk.ZkbError) as e:                        # fri.rs:225: < 2 rounds
+        zk.FRI(F.GENERATOR, F.primitive_nth_root(256), 256, 4, 64, ctx).prove(cw[:256], zk.IndependentProofStream())
+    assert e.value.code == -10
+
+
+def test_lde_fri_commit_full_size_2_24(ctx):
+    """BASELINE configs[2]: coset LDE + Merkle + full FRI commit on one 2^24 codeword.
+    Checked (a) against the C oracle for the codeword, every root and every layer, and
+    (b) by the restated reference verifier accepting the proof bytes."""
+    log_n = 24
+    n = 1 << log_n
+    w = F.primitive_nth_root(n)
+    coeffs = C.synth(0x5EED0003, n // 4)
+    cw = zk.fast_coset_evaluate(w, n, F.GENERATOR, cuda(coeffs), ctx)
+    ctx.sync()
+    want_cw = C.coset_lde(w, n, F.GENERATOR, coeffs)
+    assert np.array_equal(host(cw), want_cw)
+    fri = zk.FRI(F.GENERATOR, w, n, 4, 64, ctx)
+    ofri = OFRI(F.GENERATOR, w, n, 4, 64)
+    assert fri.num_rounds() == 16
+    ps = zk.IndependentProofStream()
+    top = fri.prove(cw, ps)
+    d = ps.digest()
+    ops = PS.IndependentProofStream()
+    top2, codewords, trees = fastfri.prove(ofri, want_cw, ops)
+    assert top == top2
+    assert d == ops.digest()
+    assert ofri.verify(PS.IndependentProofStream(PS.parse(d)), []) is None
+
+
+@pytest.mark.parametrize("log_n,n_coeffs", [(10, 256), (12, 1000), (16, 1 << 14), (16, 0)])
+def test_lde_fri_commit_pipeline(ctx, log_n, n_coeffs):
+    """zkb_lde_fri_commit: LDE -> FRI commit without leaving HBM == the two calls separately."""
+    n = 1 << log_n
+    w = F.primitive_nth_root(n)
+    coeffs = C.synth(0x5EED0003, n_coeffs) if n_coeffs else np.empty((0, 2), dtype=np.uint64)
+    cw = C.coset_lde(w, n, F.GENERATOR, coeffs) if n_coeffs else np.zeros((n, 2), dtype=np.uint64)
+    ofri = OFRI(F.GENERATOR, w, n, 4, 64)
+    ops = PS.IndependentProofStream()
+    codewords, trees, _ = fastfri.commit(ofri, cw, ops)
+    fri = zk.FRI(F.GENERATOR, w, n, 4, 64, ctx)
+    for stream in (zk.IndependentProofStream(), PS.IndependentProofStream()):      # C callback / Python callback
+        layers = fri.lde_commit(cuda(coeffs) if n_coeffs else coeffs, stream)
+        assert stream.digest() == ops.digest()
+        assert [layers.root(r) for r in range(len(layers))] == [t.root for t in trees]
+        for r in range(len(layers)):
+            assert np.array_equal(layers.codeword(r), codewords[r])
+        layers.close()
+
+
+def test_profile_counters(ctx):
+    ctx.profile(True, reset=True)
+    n = 1 << 12
+    zk.MerkleRoot.commit(C.synth(1, n), ctx)
+    prof = ctx.profile_read()
+    ctx.profile(False)
+    assert prof["k_leaf_tile<false>"][1] == 1 and prof["k_leaf_tile<false>"][0] > 0

@@ -83,3 +83,20 @@ def test_big_fold_chunking():
         ax = F.div(alpha, F.mul(F.GENERATOR, F.fpow(w, i)))
         want = F.mul(F.inv(2), F.add(F.mul(F.add(1, ax), vals[i]), F.mul(F.sub(1, ax), vals[half + i])))
         assert got[i] == want
+
+
+def test_fastfri_matches_literal_restatement():
+    """oracle.fastfri (C kernels, trees built once) == oracle.fri.FRI.prove (literal fri.rs)."""
+    from oracle import fastfri, proof_stream as PS
+    for n, ncc, doc in ((256, 17, None), (2048, 64, None), (1024, 20, b"doc")):
+        w = F.primitive_nth_root(n)
+        coeffs = rvals(n // 4)
+        cw = N.fast_coset_evaluate(w, n, F.GENERATOR, coeffs)
+        fri = FRI(F.GENERATOR, w, n, 4, ncc)
+        mk = (lambda: PS.SignatureProofStream(doc)) if doc else PS.IndependentProofStream
+        ps1, ps2 = mk(), mk()
+        top1 = fri.prove(cw, ps1)
+        top2, _, _ = fastfri.prove(fri, C.to_arr(cw), ps2)
+        assert top1 == top2
+        assert ps1.digest() == ps2.digest()
+        assert fri.verify(ps2, []) is None

@@ -31,6 +31,9 @@ PROTOTYPES = {
     "zkb_ctx_sync": (ctypes.c_int, [vp]),
     "zkb_ctx_launches": (u64, [vp]),
     "zkb_version": (ctypes.c_char_p, []),
+    "zkb_ctx_profile": (ctypes.c_int, [vp, ctypes.c_int]),
+    "zkb_ctx_profile_read": (ctypes.c_int, [vp, ctypes.c_int, ctypes.POINTER(ctypes.c_double), c_u64p]),
+    "zkb_kernel_name": (ctypes.c_char_p, [ctypes.c_int]),
     "zkb_dev_alloc": (ctypes.c_int, [vp, sz, ctypes.POINTER(vp)]),
     "zkb_dev_free": (ctypes.c_int, [vp, vp]),
     "zkb_memcpy": (ctypes.c_int, [vp, vp, vp, sz]),
@@ -59,6 +62,9 @@ PROTOTYPES = {
     "zkb_fri_num_rounds": (u64, [ctypes.POINTER(FriParams)]),
     "zkb_fri_fold": (ctypes.c_int, [vp, vp, sz, c_u8p, c_u8p, c_u8p, vp]),
     "zkb_fri_commit": (ctypes.c_int, [vp, ctypes.POINTER(FriParams), vp, sz, FS_CALLBACK, vp, ctypes.POINTER(vp)]),
+    "zkb_lde_fri_commit": (ctypes.c_int, [vp, ctypes.POINTER(FriParams), vp, sz, FS_CALLBACK, vp, ctypes.POINTER(vp)]),
+    "zkb_fri_commit_ps": (ctypes.c_int, [vp, ctypes.POINTER(FriParams), vp, sz, vp, ctypes.POINTER(vp)]),
+    "zkb_lde_fri_commit_ps": (ctypes.c_int, [vp, ctypes.POINTER(FriParams), vp, sz, vp, ctypes.POINTER(vp)]),
     "zkb_fri_layer_count": (u64, [vp]),
     "zkb_fri_layer_len": (u64, [vp, u64]),
     "zkb_fri_layer_root": (ctypes.c_int, [vp, u64, c_u8p]),

@@ -15,6 +15,32 @@ int set_err(zkb_ctx* c, int code, const char* fmt, ...) {
     return code;
 }
 
+static cudaEvent_t prof_event(zkb_ctx* c) {
+    if (!c->prof_pool.empty()) { cudaEvent_t e = c->prof_pool.back(); c->prof_pool.pop_back(); return e; }
+    cudaEvent_t e = nullptr;
+    cudaEventCreate(&e);
+    return e;
+}
+LaunchScope::LaunchScope(zkb_ctx* c_, int id_) : c(c_), id(id_) {
+    c->launches++;
+    if (c->profiling) { a = prof_event(c); b = prof_event(c); cudaEventRecord(a, c->stream); }
+}
+LaunchScope::~LaunchScope() {
+    if (a) { cudaEventRecord(b, c->stream); c->prof_recs.push_back({id, a, b}); }
+}
+int prof_collect(zkb_ctx* c) {
+    if (c->prof_recs.empty()) return 0;
+    ZKB_CUDA(c, cudaStreamSynchronize(c->stream));
+    for (auto& r : c->prof_recs) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) { c->prof_ms[r.id] += ms; c->prof_count[r.id]++; }
+        c->prof_pool.push_back(r.a);
+        c->prof_pool.push_back(r.b);
+    }
+    c->prof_recs.clear();
+    return 0;
+}
+
 int DevBuf::alloc(zkb_ctx* c, size_t bytes) {
     ZKB_CUDA(c, cudaMalloc(&p, bytes ? bytes : 16));
     return 0;
@@ -96,9 +122,8 @@ int get_pow_table(zkb_ctx* c, const fe& base, uint32_t log_n, DevPow* out) {
     fe base_m = fe_to_mont(base);
     fe hi_base_m = base_m;
     for (uint32_t i = 0; i < t->lo_bits; i++) hi_base_m = fe_montmul(hi_base_m, hi_base_m);
-    k_pow_table<<<(n_lo + 255) / 256, 256, 0, c->stream>>>(base_m, t->lo, n_lo);
-    k_pow_table<<<(n_hi + 255) / 256, 256, 0, c->stream>>>(hi_base_m, t->hi, n_hi);
-    c->launches += 2;
+    { LaunchScope ls(c, K_POW_TABLE); k_pow_table<<<(n_lo + 255) / 256, 256, 0, c->stream>>>(base_m, t->lo, n_lo); }
+    { LaunchScope ls(c, K_POW_TABLE); k_pow_table<<<(n_hi + 255) / 256, 256, 0, c->stream>>>(hi_base_m, t->hi, n_hi); }
     ZKB_CUDA(c, cudaGetLastError());
     t->stamp = c->clock;
     *out = DevPow{t->lo, t->hi, t->lo_bits};
@@ -144,6 +169,8 @@ void zkb_ctx_destroy(zkb_ctx* c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     for (auto& t : c->pow_tables) cudaFree(t->lo);
+    for (auto& r : c->prof_recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+    for (auto e : c->prof_pool) cudaEventDestroy(e);
     if (c->scratch) cudaFree(c->scratch);
     if (c->pinned) cudaFreeHost(c->pinned);
     if (c->own_stream) cudaStreamDestroy(c->stream);
@@ -159,6 +186,26 @@ int zkb_ctx_sync(zkb_ctx* c) {
 }
 
 uint64_t zkb_ctx_launches(const zkb_ctx* c) { return c ? c->launches : 0; }
+
+int zkb_ctx_profile(zkb_ctx* c, int enable) {
+    if (!c) return ZKB_ERR_ARG;
+    ZKB_TRY(prof_collect(c));
+    c->profiling = enable != 0;
+    if (enable == 2) for (int i = 0; i < 16; i++) { c->prof_ms[i] = 0; c->prof_count[i] = 0; }
+    return 0;
+}
+int zkb_ctx_profile_read(zkb_ctx* c, int kernel_id, double* total_ms, uint64_t* count) {
+    if (!c || kernel_id < 0 || kernel_id >= K_COUNT) return ZKB_ERR_ARG;
+    ZKB_TRY(prof_collect(c));
+    if (total_ms) *total_ms = c->prof_ms[kernel_id];
+    if (count) *count = c->prof_count[kernel_id];
+    return 0;
+}
+const char* zkb_kernel_name(int kernel_id) {
+    static const char* names[K_COUNT] = {"k_pow_table", "k_ntt_pass", "k_elementwise", "k_leaf_tile<false>", "k_leaf_tile<true>",
+                                         "k_node_tile", "k_small", "k_open", "k_fold", "k_gather3"};
+    return (kernel_id >= 0 && kernel_id < K_COUNT) ? names[kernel_id] : nullptr;
+}
 
 int zkb_dev_alloc(zkb_ctx* c, size_t bytes, void** dptr) {
     if (!c || !dptr) return ZKB_ERR_ARG;

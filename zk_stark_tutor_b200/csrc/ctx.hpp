@@ -50,6 +50,13 @@ struct zkb_ctx {
     std::vector<std::unique_ptr<zkb::PowTable>> pow_tables;
     uint64_t clock = 0;
     uint64_t launches = 0;   // kernels launched through this context (bench "gpu_launches")
+    // optional per-kernel-class device timing (CUDA events on the launching stream)
+    bool profiling = false;
+    struct ProfRec { int id; cudaEvent_t a, b; };
+    std::vector<ProfRec> prof_recs;
+    std::vector<cudaEvent_t> prof_pool;
+    double prof_ms[16] = {0};
+    uint64_t prof_count[16] = {0};
 };
 
 namespace zkb {
@@ -69,6 +76,18 @@ int set_err(zkb_ctx* c, int code, const char* fmt, ...);
         int rc__ = (expr);       \
         if (rc__ != 0) return rc__; \
     } while (0)
+
+// kernel classes for zkb_ctx_profile_* (keep in sync with zkb_kernel_name)
+enum KernelId { K_POW_TABLE = 0, K_NTT_PASS = 1, K_ELEMENTWISE = 2, K_LEAF_TILE = 3, K_FOLD_LEAF_TILE = 4,
+                K_NODE_TILE = 5, K_MERKLE_SMALL = 6, K_OPEN = 7, K_FOLD = 8, K_GATHER = 9, K_COUNT = 10 };
+
+// Brackets one launch with events when profiling is on; always counts the launch.
+struct LaunchScope {
+    zkb_ctx* c; int id; cudaEvent_t a = nullptr, b = nullptr;
+    LaunchScope(zkb_ctx* c_, int id_);
+    ~LaunchScope();
+};
+int prof_collect(zkb_ctx* c);
 
 int scratch_reserve(zkb_ctx* c, size_t bytes, void** out);
 int get_pow_table(zkb_ctx* c, const fe& base, uint32_t log_n, DevPow* out);

@@ -19,6 +19,7 @@
 #include <string.h>
 #include <vector>
 #include "merkle.cuh"
+#include "ntt.cuh"
 #include "hosthash.hpp"
 
 namespace zkb {
@@ -49,8 +50,7 @@ __global__ void k_gather3(const fe* cur, const fe* nxt, uint64_t half, const uin
 }
 
 static int launch_fold(zkb_ctx* c, const FoldArgs& f) {
-    k_fold<<<(unsigned)((f.half + 255) / 256), 256, 0, c->stream>>>(f);
-    c->launches++;
+    { LaunchScope ls(c, K_FOLD); k_fold<<<(unsigned)((f.half + 255) / 256), 256, 0, c->stream>>>(f); }
     ZKB_CUDA(c, cudaGetLastError());
     return 0;
 }
@@ -115,9 +115,11 @@ void zkb_fri_layers_free(zkb_fri_layers* l) {
     delete l;
 }
 
-int zkb_fri_commit(zkb_ctx* c, const zkb_fri_params* p, const void* codeword, size_t n,
-                   zkb_fs_callback fs, void* user, zkb_fri_layers** out) {
-    if (!c || !p || !codeword || !fs || !out) return ZKB_ERR_ARG;
+// Shared body of zkb_fri_commit / zkb_lde_fri_commit.  Exactly one of `codeword` (n values)
+// and `coeffs` (n_coeffs <= n coefficients, extended to the coset codeword on the device
+// first: fast_coset_evaluate ntt_arithmetics.rs:161-170 with omega/offset of `p`) is set.
+static int fri_commit_impl(zkb_ctx* c, const zkb_fri_params* p, const void* codeword, const void* coeffs,
+                           size_t n_coeffs, size_t n, zkb_fs_callback fs, void* user, zkb_fri_layers** out) {
     *out = nullptr;
     if (p->domain_length != n) return set_err(c, ZKB_ERR_LENGTH, "Length of the domain doesnt match the length of initial codeword");
     if (n < 2 || (n & (n - 1))) return set_err(c, ZKB_ERR_NOT_POW2, "Leafs len must be power of two (got %zu)", n);
@@ -147,12 +149,28 @@ int zkb_fri_commit(zkb_ctx* c, const zkb_fri_params* p, const void* codeword, si
     }
     ZKB_CUDA(c, cudaMalloc(&L->arena, arena_bytes));
     auto fail = [&](int rc) { cudaStreamSynchronize(c->stream); cudaFree(L->arena); if (L->owned_cw0) cudaFree(L->owned_cw0); L->arena = nullptr; L->owned_cw0 = nullptr; return rc; };
-    if (is_device_ptr(codeword)) {
+    DevBuf staged_coeffs;
+    if (codeword && is_device_ptr(codeword)) {
         L->cw.push_back((const fe*)codeword);
     } else {
         cudaError_t e = cudaMalloc(&L->owned_cw0, n * sizeof(fe));
-        if (e == cudaSuccess) e = cudaMemcpyAsync(L->owned_cw0, codeword, n * sizeof(fe), cudaMemcpyHostToDevice, c->stream);
-        if (e != cudaSuccess) return fail(set_err(c, ZKB_ERR_CUDA, "staging the codeword failed: %s", cudaGetErrorString(e)));
+        if (e != cudaSuccess) return fail(set_err(c, ZKB_ERR_CUDA, "allocating the codeword failed: %s", cudaGetErrorString(e)));
+        if (codeword) {
+            e = cudaMemcpyAsync(L->owned_cw0, codeword, n * sizeof(fe), cudaMemcpyHostToDevice, c->stream);
+            if (e != cudaSuccess) return fail(set_err(c, ZKB_ERR_CUDA, "staging the codeword failed: %s", cudaGetErrorString(e)));
+        } else if (n_coeffs == 0) {
+            e = cudaMemsetAsync(L->owned_cw0, 0, n * sizeof(fe), c->stream);
+            if (e != cudaSuccess) return fail(set_err(c, ZKB_ERR_CUDA, "memset failed: %s", cudaGetErrorString(e)));
+        } else {
+            const void* d_coeffs = nullptr;
+            int rc = stage_in(c, coeffs, n_coeffs * sizeof(fe), staged_coeffs, &d_coeffs);
+            if (rc) return fail(rc);
+            NttOpts o;
+            o.has_scale = true;
+            o.scale_base = offset;
+            rc = ntt_exec(c, omega, (const fe*)d_coeffs, n_coeffs, 0, (fe*)L->owned_cw0, 0, 1, ilog2_u64(n), o);
+            if (rc) return fail(rc);
+        }
         L->cw.push_back((const fe*)L->owned_cw0);
     }
     for (uint64_t r = 0; r < rounds; r++) {
@@ -204,6 +222,20 @@ int zkb_fri_commit(zkb_ctx* c, const zkb_fri_params* p, const void* codeword, si
     return 0;
 }
 
+int zkb_fri_commit(zkb_ctx* c, const zkb_fri_params* p, const void* codeword, size_t n,
+                   zkb_fs_callback fs, void* user, zkb_fri_layers** out) {
+    if (!c || !p || !codeword || !fs || !out) return ZKB_ERR_ARG;
+    return fri_commit_impl(c, p, codeword, nullptr, 0, n, fs, user, out);
+}
+
+int zkb_lde_fri_commit(zkb_ctx* c, const zkb_fri_params* p, const void* coeffs, size_t n_coeffs,
+                       zkb_fs_callback fs, void* user, zkb_fri_layers** out) {
+    if (!c || !p || !fs || !out || (n_coeffs && !coeffs)) return ZKB_ERR_ARG;
+    if (n_coeffs > p->domain_length)
+        return set_err(c, ZKB_ERR_TOO_LONG, "coset_lde: %zu coefficients exceed root_order %llu", n_coeffs, (unsigned long long)p->domain_length);
+    return fri_commit_impl(c, p, nullptr, coeffs, n_coeffs, (size_t)p->domain_length, fs, user, out);
+}
+
 uint64_t zkb_fri_layer_count(const zkb_fri_layers* l) { return l ? l->rounds : 0; }
 uint64_t zkb_fri_layer_len(const zkb_fri_layers* l, uint64_t r) { return (l && r < l->rounds) ? l->len[r] : 0; }
 const void* zkb_fri_layer_device_ptr(const zkb_fri_layers* l, uint64_t r) { return (l && r < l->rounds) ? l->cw[r] : nullptr; }
@@ -244,8 +276,7 @@ int zkb_fri_query(zkb_fri_layers* l, uint64_t r, const uint64_t* idx_c, size_t n
     uint8_t* d_pc = d_pab + 2 * ncc * pb_cur;
     ZKB_CUDA(c, cudaMemcpyAsync(d_ab, ab.data(), 2 * ncc * 8, cudaMemcpyHostToDevice, c->stream));
     ZKB_CUDA(c, cudaMemcpyAsync(d_c, cc.data(), ncc * 8, cudaMemcpyHostToDevice, c->stream));
-    k_gather3<<<(unsigned)((ncc + 127) / 128), 128, 0, c->stream>>>(l->cw[r], l->cw[r + 1], half, d_c, (uint32_t)ncc, d_leafs);
-    c->launches++;
+    { LaunchScope ls(c, K_GATHER); k_gather3<<<(unsigned)((ncc + 127) / 128), 128, 0, c->stream>>>(l->cw[r], l->cw[r + 1], half, d_c, (uint32_t)ncc, d_leafs); }
     ZKB_CUDA(c, cudaGetLastError());
     ZKB_TRY(merkle_open_device(c, l->cw[r], l->layout[r], l->nodes[r], d_ab, 2 * ncc, d_pab));
     if (d_nxt > 0) ZKB_TRY(merkle_open_device(c, l->cw[r + 1], l->layout[r + 1], l->nodes[r + 1], d_c, ncc, d_pc));
@@ -276,6 +307,32 @@ static int ps_callback(void* user, uint32_t, const uint8_t root[64], int want_al
     return 0;
 }
 
+static int push_last_codeword(zkb_fri_layers* L, zkb_ps* ps) {
+    const uint64_t R = L->rounds;                           // fri.rs:166
+    std::vector<uint8_t> last(L->len[R - 1] * 16);
+    ZKB_TRY(zkb_fri_layer_codeword(L, R - 1, last.data()));
+    zkb_ps_push_codeword(ps, last.data(), L->len[R - 1]);
+    return 0;
+}
+
+int zkb_fri_commit_ps(zkb_ctx* c, const zkb_fri_params* p, const void* codeword, size_t n, zkb_ps* ps,
+                      zkb_fri_layers** out) {
+    if (!c || !p || !codeword || !ps || !out) return ZKB_ERR_ARG;
+    ZKB_TRY(fri_commit_impl(c, p, codeword, nullptr, 0, n, ps_callback, ps, out));
+    int rc = push_last_codeword(*out, ps);
+    if (rc) { zkb_fri_layers_free(*out); *out = nullptr; }
+    return rc;
+}
+
+int zkb_lde_fri_commit_ps(zkb_ctx* c, const zkb_fri_params* p, const void* coeffs, size_t n_coeffs, zkb_ps* ps,
+                          zkb_fri_layers** out) {
+    if (!c || !p || !ps || !out) return ZKB_ERR_ARG;
+    ZKB_TRY(zkb_lde_fri_commit(c, p, coeffs, n_coeffs, ps_callback, ps, out));
+    int rc = push_last_codeword(*out, ps);
+    if (rc) { zkb_fri_layers_free(*out); *out = nullptr; }
+    return rc;
+}
+
 int zkb_fri_prove(zkb_ctx* c, const zkb_fri_params* p, const void* codeword, size_t n, zkb_ps* ps,
                   uint64_t* top_indices_out) {
     if (!c || !p || !ps || !top_indices_out) return ZKB_ERR_ARG;
@@ -285,10 +342,7 @@ int zkb_fri_prove(zkb_ctx* c, const zkb_fri_params* p, const void* codeword, siz
     ZKB_TRY(zkb_fri_commit(c, p, codeword, n, ps_callback, ps, &L));
     struct Guard { zkb_fri_layers* l; ~Guard() { zkb_fri_layers_free(l); } } guard{L};
     const uint64_t R = L->rounds;
-    // send last codeword (fri.rs:166)
-    std::vector<uint8_t> last(L->len[R - 1] * 16);
-    ZKB_TRY(zkb_fri_layer_codeword(L, R - 1, last.data()));
-    zkb_ps_push_codeword(ps, last.data(), L->len[R - 1]);
+    ZKB_TRY(push_last_codeword(L, ps));
     // top-level indices (fri.rs:223-228)
     uint8_t seed[32];
     zkb_ps_fiat_shamir(ps, 32, seed);

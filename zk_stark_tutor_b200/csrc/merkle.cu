@@ -278,8 +278,7 @@ static int launch_small(zkb_ctx* c, const SmallArgs& a) {
         ZKB_CUDA(c, cudaFuncSetAttribute(k_small, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
         attr_set = true;
     }
-    k_small<<<1, 256, 96 * 1024, c->stream>>>(a);
-    c->launches++;
+    { LaunchScope ls(c, K_MERKLE_SMALL); k_small<<<1, 256, 96 * 1024, c->stream>>>(a); }
     ZKB_CUDA(c, cudaGetLastError());
     return 0;
 }
@@ -297,23 +296,27 @@ int merkle_build_levels(zkb_ctx* c, const fe* vals, const FoldArgs* fold, uint64
         return launch_small(c, a);
     }
     uint8_t* lvl5 = nodes + L.level_off[5] * 64;
-    if (fold) k_leaf_tile<true><<<(unsigned)(n >> 10), 256, 0, c->stream>>>(nullptr, *fold, lvl5);
-    else {
+    if (fold) {
+        LaunchScope ls(c, K_FOLD_LEAF_TILE);
+        k_leaf_tile<true><<<(unsigned)(n >> 10), 256, 0, c->stream>>>(nullptr, *fold, lvl5);
+    } else {
         FoldArgs dummy;
         memset(&dummy, 0, sizeof(dummy));
+        LaunchScope ls(c, K_LEAF_TILE);
         k_leaf_tile<false><<<(unsigned)(n >> 10), 256, 0, c->stream>>>(vals, dummy, lvl5);
     }
-    c->launches++;
     ZKB_CUDA(c, cudaGetLastError());
     uint32_t level = 5;
     uint64_t m = n >> 5;
     while (m > 1024) {
         const uint8_t* in = nodes + L.level_off[level] * 64;
-        k_node_tile<<<(unsigned)(m >> 10), 256, 0, c->stream>>>(in,
-            nodes + L.level_off[level + 1] * 64, nodes + L.level_off[level + 2] * 64,
-            nodes + L.level_off[level + 3] * 64, nodes + L.level_off[level + 4] * 64,
-            nodes + L.level_off[level + 5] * 64);
-        c->launches++;
+        {
+            LaunchScope ls(c, K_NODE_TILE);
+            k_node_tile<<<(unsigned)(m >> 10), 256, 0, c->stream>>>(in,
+                nodes + L.level_off[level + 1] * 64, nodes + L.level_off[level + 2] * 64,
+                nodes + L.level_off[level + 3] * 64, nodes + L.level_off[level + 4] * 64,
+                nodes + L.level_off[level + 5] * 64);
+        }
         ZKB_CUDA(c, cudaGetLastError());
         level += 5;
         m >>= 5;
@@ -332,8 +335,7 @@ int merkle_open_device(zkb_ctx* c, const fe* vals, const TreeLayout& layout, con
     if (k == 0) return 0;
     OpenArgs a;
     a.vals = vals; a.nodes = nodes; a.layout = layout; a.idx = d_idx; a.k = (uint32_t)k; a.out = d_out;
-    k_open<<<(unsigned)((k + 3) / 4), 128, 0, c->stream>>>(a);
-    c->launches++;
+    { LaunchScope ls(c, K_OPEN); k_open<<<(unsigned)((k + 3) / 4), 128, 0, c->stream>>>(a); }
     ZKB_CUDA(c, cudaGetLastError());
     return 0;
 }

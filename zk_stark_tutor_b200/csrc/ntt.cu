@@ -26,6 +26,7 @@
 // ef = 4).  The coset scaling c_i*offset^i of the LDE is fused into the pass-1 load.
 #include <string.h>
 #include "ctx.hpp"
+#include "ntt.cuh"
 
 namespace zkb {
 
@@ -167,17 +168,10 @@ static int launch_pass(zkb_ctx* c, const PassParams& p, uint32_t tiles, uint32_t
         attr_set = true;
     }
     dim3 grid(tiles, batch);
-    k_ntt_pass<<<grid, ZKB_NTT_THREADS, pass_smem_bytes(p), c->stream>>>(p);
-    c->launches++;
+    { LaunchScope ls(c, K_NTT_PASS); k_ntt_pass<<<grid, ZKB_NTT_THREADS, pass_smem_bytes(p), c->stream>>>(p); }
     ZKB_CUDA(c, cudaGetLastError());
     return 0;
 }
-
-struct NttOpts {
-    bool has_scale = false;   // x_i *= scale_base^i on load (coset LDE)
-    fe scale_base;
-    bool inverse = false;     // use root^-1 and multiply by n^-1
-};
 
 static const uint32_t TILE_LOG = 12;     // 4096 elements = 64 KiB per tile
 
@@ -191,8 +185,6 @@ static int tw_s_table(zkb_ctx* c, const fe& root, uint32_t log_n, uint32_t log_s
     return 0;
 }
 
-// d_in / d_out are device pointers; n = 2^log_n is the transform length; n_in <= n values
-// are read per column (the rest are zero).
 int ntt_exec(zkb_ctx* c, fe root, const fe* d_in, size_t n_in, size_t in_stride, fe* d_out,
              size_t out_stride, size_t batch, uint32_t log_n, const NttOpts& o) {
     if (batch == 0) return 0;
@@ -392,8 +384,7 @@ int zkb_poly_scale(zkb_ctx* c, const uint8_t factor[16], const void* coeffs, siz
     if (!out_dev) { ZKB_TRY(bout.alloc(c, n * sizeof(fe))); d_out = (fe*)bout.p; }
     DevPow sc;
     ZKB_TRY(get_pow_table(c, h_load(factor), ilog2_u64(next_pow2_u64(n)), &sc));
-    k_scale<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>((const fe*)d_in, d_out, n, sc);
-    c->launches++;
+    { LaunchScope ls(c, K_ELEMENTWISE); k_scale<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>((const fe*)d_in, d_out, n, sc); }
     ZKB_CUDA(c, cudaGetLastError());
     if (!out_dev) ZKB_CUDA(c, cudaMemcpyAsync(out, d_out, n * sizeof(fe), cudaMemcpyDeviceToHost, c->stream));
     if (!out_dev || bin.p) ZKB_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -482,9 +473,11 @@ static int poly_binop(zkb_ctx* c, bool divide, const uint8_t root_b[16], uint64_
         ZKB_TRY(ntt_exec(c, root, dR, order, 0, eR, 0, 1, log_n, fwd));
     }
     unsigned blocks = (unsigned)((order + 127) / 128);
-    if (divide) k_pointwise_div<<<blocks, 128, 0, c->stream>>>(eL, eR, dL, order, flag);
-    else k_pointwise_mul<<<blocks, 128, 0, c->stream>>>(eL, eR, dL, order);
-    c->launches++;
+    {
+        LaunchScope ls(c, K_ELEMENTWISE);
+        if (divide) k_pointwise_div<<<blocks, 128, 0, c->stream>>>(eL, eR, dL, order, flag);
+        else k_pointwise_mul<<<blocks, 128, 0, c->stream>>>(eL, eR, dL, order);
+    }
     ZKB_CUDA(c, cudaGetLastError());
     if (order > 1) {
         NttOpts inv; inv.inverse = true;
@@ -496,8 +489,7 @@ static int poly_binop(zkb_ctx* c, bool divide, const uint8_t root_b[16], uint64_
     if (divide) {
         DevPow sc;
         ZKB_TRY(get_pow_table(c, h_inv(h_load(offset_b)), log_n, &sc));
-        k_scale<<<(unsigned)((keep + 255) / 256), 256, 0, c->stream>>>(dR, dR, keep, sc);
-        c->launches++;
+        { LaunchScope ls(c, K_ELEMENTWISE); k_scale<<<(unsigned)((keep + 255) / 256), 256, 0, c->stream>>>(dR, dR, keep, sc); }
     }
     uint32_t hflag = 0;
     ZKB_CUDA(c, cudaMemcpyAsync(out, dR, sizeof(fe) * keep, cudaMemcpyDeviceToHost, c->stream));
