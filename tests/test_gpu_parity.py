@@ -435,3 +435,32 @@ def test_profile_counters(ctx):
     prof = ctx.profile_read()
     ctx.profile(False)
     assert prof["k_leaf_tile<false>"][1] == 1 and prof["k_leaf_tile<false>"][0] > 0
+
+
+def test_fast_multiply_trailing_zero_quirk(ctx):
+    """Operands with trailing zero coefficients longer than the shrunk transform order: the
+    reference's ntt() then runs at a longer length with a root of too small an order
+    (ntt_arithmetics.rs:38-47) - a reference quirk that the oracle restates literally and the
+    CUDA path must reproduce bit for bit."""
+    n = 64
+    w = F.primitive_nth_root(n)
+    cases = [([1, 2, 0, 0], [3, 0]), ([5, 6, 7, 0, 0, 0, 0, 0, 0], [1, 1]), ([7, 0], [9, 0, 0]), ([1, 2, 3], [4, 5, 6, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0])]
+    for _ in range(5):
+        a, b = rvals(rnd.randrange(1, 8)), rvals(rnd.randrange(1, 8))
+        cases.append((a + [0] * rnd.randrange(1, 40), b + [0] * rnd.randrange(0, 40)))
+    for a, b in cases:
+        assert zk.fast_multiply(w, n, a, b, ctx) == N.fast_multiply(w, n, a, b)
+    for a, b in cases:
+        prod = N.fast_multiply(w, n, [x for x in a if x], [x for x in b if x] or [1])
+        bb = [x for x in b if x] or [1]
+        assert zk.fast_coset_divide(w, n, F.GENERATOR, prod + [0] * 9, bb + [0] * 5, ctx) == \
+            N.fast_coset_divide(w, n, F.GENERATOR, prod + [0] * 9, bb + [0] * 5)
+
+
+def test_ntt_with_non_primitive_root_matches_reference_loop(ctx):
+    """ntt() does not check its root (ntt.rs:7-49); for lengths up to one tile the CUDA path
+    is the same radix-2 DIT op for op, so even a wrong-order root gives the reference's result."""
+    for n, order in ((8, 4), (16, 2), (64, 16), (1024, 256), (4096, 64)):
+        r = F.primitive_nth_root(order)
+        xs = rvals(n)
+        assert zk.ntt(r, xs, ctx) == N.ntt(r, xs)

@@ -421,9 +421,10 @@ int zkb_merkle_open(zkb_tree* t, const uint64_t* idx, size_t k, uint8_t* paths_o
     ZKB_CUDA(c, cudaSetDevice(c->device));
     const size_t path_bytes = (size_t)t->layout.log_n * 64;
     DevBuf buf;
-    ZKB_TRY(buf.alloc(c, k * 8 + k * path_bytes));
+    const size_t idx_bytes = (k * 8 + 63) & ~(size_t)63;       // keep the 16-byte path stores aligned
+    ZKB_TRY(buf.alloc(c, idx_bytes + k * path_bytes));
     uint64_t* d_idx = (uint64_t*)buf.p;
-    uint8_t* d_out = (uint8_t*)buf.p + k * 8;
+    uint8_t* d_out = (uint8_t*)buf.p + idx_bytes;
     ZKB_CUDA(c, cudaMemcpyAsync(d_idx, idx, k * 8, cudaMemcpyHostToDevice, c->stream));
     ZKB_TRY(merkle_open_device(c, t->vals, t->layout, t->nodes, d_idx, k, d_out));
     ZKB_CUDA(c, cudaMemcpyAsync(paths_out, d_out, k * path_bytes, cudaMemcpyDeviceToHost, c->stream));

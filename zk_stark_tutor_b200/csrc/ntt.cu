@@ -215,12 +215,17 @@ int ntt_exec(zkb_ctx* c, fe root, const fe* d_in, size_t n_in, size_t in_stride,
     const uint64_t N1 = 1ull << a, N2 = 1ull << b2, N3 = 1ull << c3, M = N2 * N3;
 
     if (passes == 1) {
+        // One tile: the literal radix-2 DIT of ntt.rs:26-46 (bit-reversed load, twiddles
+        // root^k from one table, explicit e - o*w) - op for op the reference's loop, so the
+        // result matches the reference even for a `root` that is not a primitive n-th root
+        // (ntt.rs does not check; fast_multiply's order-shrink quirk relies on it).
         PassParams p = base;
         p.in = d_in; p.out = d_out;
-        p.log_s = log_n; p.log_b = 0; p.transposed = 1; p.inner_count = 1;
-        p.ld_s = 1; p.st_k = 1;
+        p.log_s = log_n; p.log_b = 0; p.transposed = 0; p.inner_count = 1;
+        p.ld_s = 1; p.ld_b = 0; p.st_k = 1; p.st_b = 0;
         p.in_batch = in_stride; p.out_batch = out_stride;
         p.has_valid = n_in < N; p.n_valid = n_in;
+        p.skip_log = log_n - ilog2_u64(n_in ? n_in : 1);       // x[i] = 0 for i >= 2^ceil(log2 n_in)
         p.has_scale = o.has_scale; p.sc = sc;
         ZKB_TRY(tw_s_table(c, root, log_n, log_n, &p.tw_s));
         return launch_pass(c, p, 1, (uint32_t)batch);
@@ -453,25 +458,31 @@ static int poly_binop(zkb_ctx* c, bool divide, const uint8_t root_b[16], uint64_
     }
     uint64_t order = root_order;
     while (degree < order / 2) { root = h_mul(root, root); order /= 2; }   // :38-41 / :278-281
-    if (n_lhs > order || n_rhs > order)
-        return set_err(c, ZKB_ERR_TOO_LONG, "operand longer than the transform order %llu", (unsigned long long)order);
+    // Operands longer than the shrunk order (trailing zero coefficients): the reference's
+    // `extend(len..order)` is a no-op and ntt() pads to ITS next power of two while keeping the
+    // order-`order` root (:43-47); only the first `order` outputs are used.  Reproduced
+    // literally (single-tile DIT), which needs the padded operand to fit one tile.
+    const uint64_t nL = next_pow2_u64(n_lhs > order ? n_lhs : order), nR = next_pow2_u64(n_rhs > order ? n_rhs : order);
+    if (nL > order || nR > order) {
+        if (nL > (1ull << TILE_LOG) || nR > (1ull << TILE_LOG))
+            return set_err(c, ZKB_ERR_TOO_LONG, "operand with trailing zeros longer than the transform order %llu is only supported up to %u coefficients",
+                           (unsigned long long)order, 1u << TILE_LOG);
+    }
     const uint32_t log_n = ilog2_u64(order);
     DevBuf buf;
-    ZKB_TRY(buf.alloc(c, sizeof(fe) * order * 4 + 16));
-    fe* dL = (fe*)buf.p; fe* dR = dL + order; fe* eL = dR + order; fe* eR = eL + order;
-    uint32_t* flag = (uint32_t*)(eR + order);
-    ZKB_CUDA(c, cudaMemsetAsync(buf.p, 0, sizeof(fe) * order * 4 + 16, c->stream));
+    const size_t total = (size_t)(2 * nL + 2 * nR);
+    ZKB_TRY(buf.alloc(c, sizeof(fe) * total + 16));
+    fe* dL = (fe*)buf.p; fe* eL = dL + nL; fe* dR = eL + nL; fe* eR = dR + nR;
+    uint32_t* flag = (uint32_t*)(eR + nR);
+    ZKB_CUDA(c, cudaMemsetAsync(buf.p, 0, sizeof(fe) * total + 16, c->stream));
     ZKB_CUDA(c, cudaMemcpyAsync(dL, L, sizeof(fe) * n_lhs, cudaMemcpyHostToDevice, c->stream));
     ZKB_CUDA(c, cudaMemcpyAsync(dR, R, sizeof(fe) * n_rhs, cudaMemcpyHostToDevice, c->stream));
     NttOpts fwd;
     if (divide) { fwd.has_scale = true; fwd.scale_base = h_load(offset_b); }
-    if (order == 1) {
-        ZKB_CUDA(c, cudaMemcpyAsync(eL, dL, sizeof(fe), cudaMemcpyDeviceToDevice, c->stream));
-        ZKB_CUDA(c, cudaMemcpyAsync(eR, dR, sizeof(fe), cudaMemcpyDeviceToDevice, c->stream));
-    } else {
-        ZKB_TRY(ntt_exec(c, root, dL, order, 0, eL, 0, 1, log_n, fwd));
-        ZKB_TRY(ntt_exec(c, root, dR, order, 0, eR, 0, 1, log_n, fwd));
-    }
+    if (nL == 1) ZKB_CUDA(c, cudaMemcpyAsync(eL, dL, sizeof(fe), cudaMemcpyDeviceToDevice, c->stream));
+    else ZKB_TRY(ntt_exec(c, root, dL, nL, 0, eL, 0, 1, ilog2_u64(nL), fwd));
+    if (nR == 1) ZKB_CUDA(c, cudaMemcpyAsync(eR, dR, sizeof(fe), cudaMemcpyDeviceToDevice, c->stream));
+    else ZKB_TRY(ntt_exec(c, root, dR, nR, 0, eR, 0, 1, ilog2_u64(nR), fwd));
     unsigned blocks = (unsigned)((order + 127) / 128);
     {
         LaunchScope ls(c, K_ELEMENTWISE);
