@@ -260,10 +260,10 @@ def b200_arm(args):
             probe = {}
             try:
                 pl = ctypes.CDLL(os.path.join(os.path.dirname(_lib.LIB_PATH), "libzkb200_probe.so"))
-                for kind, name in ((0, "alu"), (1, "imad"), (2, "alu+imad")):
+                for kind, name in ((0, "alu"), (1, "imad"), (2, "alu+imad"), (3, "prmt"), (4, "shf"), (5, "add64_pairs"), (6, "blake2b_Gcompress_per_s")):
                     r, pm = ctypes.c_double(0), ctypes.c_double(0)
                     if pl.zkb_probe_int_pipe(local, kind, ctypes.byref(r), ctypes.byref(pm)) == 0:
-                        probe[name] = r.value / 1e12
+                        probe[name] = r.value / (1e9 if kind == 6 else 1e12)
             except OSError:
                 pass
             achieved = alg_bytes / dur / 1e9

@@ -1,0 +1,39 @@
+#!/usr/bin/env python
+"""Compact text summary of an .ncu-rep (read here, without a GPU): per captured launch the
+duration, DRAM bytes, occupancy, issue / pipe utilisation and the top stall reasons.
+usage: tools/ncu_summary.py <report.ncu-rep> > profiles/<name>.txt"""
+import csv
+import io
+import subprocess
+import sys
+
+KEYS = ["launch__grid_size", "launch__block_size", "launch__registers_per_thread", "gpu__time_duration.sum",
+        "dram__bytes_read.sum", "dram__bytes_write.sum", "dram__throughput.avg.pct_of_peak_sustained_elapsed",
+        "lts__t_sector_hit_rate.pct", "sm__warps_active.avg.pct_of_peak_sustained_active",
+        "smsp__issue_active.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active",
+        "smsp__inst_executed.sum", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "sm__throughput.avg.pct_of_peak_sustained_elapsed"]
+
+
+def main():
+    out = subprocess.run(["ncu", "-i", sys.argv[1], "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(out)))
+    hdr, units = rows[0], rows[1]
+    for r in rows[2:]:
+        print("== %s" % r[hdr.index("Kernel Name")])
+        for k in KEYS:
+            if k in hdr:
+                i = hdr.index(k)
+                print("   %-70s %s %s" % (k, r[i], units[i]))
+        st = []
+        for i, k in enumerate(hdr):
+            if k.startswith("smsp__average_warps_issue_stalled") and k.endswith("_per_issue_active.ratio"):
+                try:
+                    st.append((float(r[i]), k[len("smsp__average_warps_issue_stalled_"):-len("_per_issue_active.ratio")]))
+                except ValueError:
+                    pass
+        print("   stalls (warps per issue): " + ", ".join("%s %.2f" % (n, v) for v, n in sorted(st, reverse=True)[:6]))
+
+
+if __name__ == "__main__":
+    main()

@@ -41,8 +41,16 @@ int prof_collect(zkb_ctx* c) {
     return 0;
 }
 
+cudaError_t dev_alloc(zkb_ctx* c, void** p, size_t bytes) {
+    return cudaMallocAsync(p, bytes ? bytes : 16, c->stream);
+}
+void dev_free(zkb_ctx* c, void* p) {
+    if (p) cudaFreeAsync(p, c->stream);
+}
+
 int DevBuf::alloc(zkb_ctx* c, size_t bytes) {
-    ZKB_CUDA(c, cudaMalloc(&p, bytes ? bytes : 16));
+    ctx = c;
+    ZKB_CUDA(c, dev_alloc(c, &p, bytes));
     return 0;
 }
 
@@ -158,6 +166,13 @@ int zkb_ctx_create(int device, void* stream, zkb_ctx** out) {
         c->own_stream = true;
     }
     cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device);
+    {   // keep freed blocks in the default pool instead of returning them to the driver
+        cudaMemPool_t pool = nullptr;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+            uint64_t keep = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+    }
     c->pinned_bytes = 1 << 20;
     if (cudaMallocHost(&c->pinned, c->pinned_bytes) != cudaSuccess) { delete c; return ZKB_ERR_CUDA; }
     *out = c;

@@ -93,10 +93,18 @@ int scratch_reserve(zkb_ctx* c, size_t bytes, void** out);
 int get_pow_table(zkb_ctx* c, const fe& base, uint32_t log_n, DevPow* out);
 bool is_device_ptr(const void* p);
 
+// Stream-ordered device memory from the device's default CUDA memory pool (cudaMallocAsync on
+// the context's stream; the pool's release threshold is raised at context creation so freed
+// blocks are kept and re-used: a 0.8 GB FRI arena costs microseconds per call, not a
+// cudaMalloc/cudaFree pair of tens of milliseconds).
+cudaError_t dev_alloc(zkb_ctx* c, void** p, size_t bytes);
+void dev_free(zkb_ctx* c, void* p);
+
 // RAII device buffer used for transient staging of host inputs
 struct DevBuf {
     void* p = nullptr;
-    ~DevBuf() { if (p) cudaFree(p); }
+    zkb_ctx* ctx = nullptr;
+    ~DevBuf() { if (p) dev_free(ctx, p); }
     int alloc(zkb_ctx* c, size_t bytes);
 };
 

@@ -109,9 +109,8 @@ int zkb_fri_fold(zkb_ctx* c, const void* cw, size_t n, const uint8_t alpha[16], 
 void zkb_fri_layers_free(zkb_fri_layers* l) {
     if (!l) return;
     cudaSetDevice(l->ctx->device);
-    cudaStreamSynchronize(l->ctx->stream);
-    if (l->arena) cudaFree(l->arena);
-    if (l->owned_cw0) cudaFree(l->owned_cw0);
+    dev_free(l->ctx, l->arena);
+    dev_free(l->ctx, l->owned_cw0);
     delete l;
 }
 
@@ -147,13 +146,13 @@ static int fri_commit_impl(zkb_ctx* c, const zkb_fri_params* p, const void* code
         node_off[r] = arena_bytes;
         arena_bytes += tl.total_nodes * 64;
     }
-    ZKB_CUDA(c, cudaMalloc(&L->arena, arena_bytes));
-    auto fail = [&](int rc) { cudaStreamSynchronize(c->stream); cudaFree(L->arena); if (L->owned_cw0) cudaFree(L->owned_cw0); L->arena = nullptr; L->owned_cw0 = nullptr; return rc; };
+    ZKB_CUDA(c, dev_alloc(c, &L->arena, arena_bytes));
+    auto fail = [&](int rc) { dev_free(c, L->arena); dev_free(c, L->owned_cw0); L->arena = nullptr; L->owned_cw0 = nullptr; return rc; };
     DevBuf staged_coeffs;
     if (codeword && is_device_ptr(codeword)) {
         L->cw.push_back((const fe*)codeword);
     } else {
-        cudaError_t e = cudaMalloc(&L->owned_cw0, n * sizeof(fe));
+        cudaError_t e = dev_alloc(c, &L->owned_cw0, n * sizeof(fe));
         if (e != cudaSuccess) return fail(set_err(c, ZKB_ERR_CUDA, "allocating the codeword failed: %s", cudaGetErrorString(e)));
         if (codeword) {
             e = cudaMemcpyAsync(L->owned_cw0, codeword, n * sizeof(fe), cudaMemcpyHostToDevice, c->stream);

@@ -359,20 +359,20 @@ int zkb_merkle_build(zkb_ctx* c, const void* vals, size_t n, zkb_tree** out) {
     if (is_device_ptr(vals)) {
         t->vals = (const fe*)vals;
     } else {
-        ZKB_CUDA(c, cudaMalloc(&t->owned_vals, n * sizeof(fe)));
+        ZKB_CUDA(c, dev_alloc(c, &t->owned_vals, n * sizeof(fe)));
         cudaError_t e = cudaMemcpyAsync(t->owned_vals, vals, n * sizeof(fe), cudaMemcpyHostToDevice, c->stream);
-        if (e != cudaSuccess) { cudaFree(t->owned_vals); return set_err(c, ZKB_ERR_CUDA, "H2D copy failed: %s", cudaGetErrorString(e)); }
+        if (e != cudaSuccess) { dev_free(c, t->owned_vals); return set_err(c, ZKB_ERR_CUDA, "H2D copy failed: %s", cudaGetErrorString(e)); }
         t->vals = (const fe*)t->owned_vals;
     }
-    cudaError_t e = cudaMalloc(&t->nodes, t->layout.total_nodes * 64);
-    if (e != cudaSuccess) { if (t->owned_vals) cudaFree(t->owned_vals); return set_err(c, ZKB_ERR_CUDA, "cudaMalloc(tree) failed: %s", cudaGetErrorString(e)); }
+    cudaError_t e = dev_alloc(c, (void**)&t->nodes, t->layout.total_nodes * 64);
+    if (e != cudaSuccess) { dev_free(c, t->owned_vals); return set_err(c, ZKB_ERR_CUDA, "cudaMalloc(tree) failed: %s", cudaGetErrorString(e)); }
     int rc = merkle_build_levels(c, t->vals, nullptr, n, t->layout, t->nodes);
     if (rc == 0) {
         e = cudaMemcpyAsync(c->pinned, t->nodes + t->layout.level_off[t->layout.log_n] * 64, 64, cudaMemcpyDeviceToHost, c->stream);
         if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
         if (e != cudaSuccess) rc = set_err(c, ZKB_ERR_CUDA, "merkle build failed: %s", cudaGetErrorString(e));
     }
-    if (rc != 0) { cudaFree(t->nodes); if (t->owned_vals) cudaFree(t->owned_vals); return rc; }
+    if (rc != 0) { dev_free(c, t->nodes); dev_free(c, t->owned_vals); return rc; }
     memcpy(t->root, c->pinned, 64);
     *out = t.release();
     return 0;
@@ -387,9 +387,8 @@ int zkb_merkle_root(const zkb_tree* t, uint8_t root[64]) {
 void zkb_merkle_free(zkb_tree* t) {
     if (!t) return;
     cudaSetDevice(t->ctx->device);
-    cudaStreamSynchronize(t->ctx->stream);
-    if (t->owns_nodes && t->nodes) cudaFree(t->nodes);
-    if (t->owned_vals) cudaFree(t->owned_vals);
+    if (t->owns_nodes) dev_free(t->ctx, t->nodes);
+    dev_free(t->ctx, t->owned_vals);
     delete t;
 }
 

@@ -4,10 +4,13 @@
 //   kind 0: ALU pipe  - dependent chains of IADD3 / LOP3 (a = (a + b) ^ c), 2 ops per step
 //   kind 1: FMA pipe  - dependent chains of IMAD        (a = a * b + c),   1 op per step
 //   kind 2: both      - one ALU pair and two IMADs per step, interleaved
+//   kind 3: PRMT chains, kind 4: SHF (funnel shift) chains, kind 5: 64-bit adds
+//   (add.cc / addc pairs), kind 6: in-register BLAKE2b-512 compressions (ops = compressions)
 // 8 independent chains per thread hide the 4-cycle pipe latency.  ops/s = lane-operations
 // per second over the whole GPU (one SASS instruction = 32 lane-ops).
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include "blake2b.cuh"
 
 #define CH 8
 #define UNROLL 16
@@ -24,6 +27,13 @@ __global__ void __launch_bounds__(256) k_probe(uint32_t* out, uint32_t b, uint32
             for (int i = 0; i < CH; i++) {
                 if (KIND == 0) {
                     asm volatile("add.u32 %0, %0, %1;\n\txor.b32 %0, %0, %2;" : "+r"(a[i]) : "r"(b), "r"(c));
+                } else if (KIND == 3) {
+                    asm volatile("prmt.b32 %0, %0, %1, 0x6543;\n\tprmt.b32 %0, %0, %2, 0x5432;" : "+r"(a[i]) : "r"(b), "r"(c));
+                } else if (KIND == 4) {
+                    asm volatile("shf.l.wrap.b32 %0, %0, %1, 1;\n\tshf.l.wrap.b32 %0, %0, %2, 3;" : "+r"(a[i]) : "r"(b), "r"(c));
+                } else if (KIND == 5) {
+                    if ((i & 1) == 0)
+                        asm volatile("add.cc.u32 %0, %0, %2;\n\taddc.u32 %1, %1, %3;" : "+r"(a[i]), "+r"(a[i + 1]) : "r"(b), "r"(c));
                 } else if (KIND == 1) {
                     asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(a[i]) : "r"(b), "r"(c));
                 } else {
@@ -39,8 +49,246 @@ __global__ void __launch_bounds__(256) k_probe(uint32_t* out, uint32_t b, uint32
     if (acc == 0x12345678u) out[0] = acc;      // keeps the chains live
 }
 
+// In-register BLAKE2b compressions: variant V of blake2b_compress_dev (V < 0: the portable
+// uint64_t code), MINB = min resident CTAs of 256 threads per SM (register cap).
+template <int V, int MINB>
+__global__ void __launch_bounds__(256, MINB) k_probe_blake(uint64_t* out, int iters) {
+    uint64_t m[16], h[8];
+#pragma unroll
+    for (int i = 0; i < 16; i++) m[i] = (uint64_t)(threadIdx.x + 1) * 0x9E3779B97F4A7C15ull + i * 0xBF58476D1CE4E5B9ull + blockIdx.x;
+    for (int it = 0; it < iters; it++) {
+        if (V < 0) zkb::blake2b_compress_1block(m, 128, h);
+        else zkb::blake2b_compress_dev<(V < 0 ? 0 : V)>(m, 128, h);
+#pragma unroll
+        for (int i = 0; i < 8; i++) { m[i] ^= h[i]; m[8 + i] += h[i]; }
+    }
+    uint64_t acc = 0;
+#pragma unroll
+    for (int i = 0; i < 16; i++) acc ^= m[i];
+    if (blockIdx.x == 0 && threadIdx.x == 0) out[1] = acc;      // checksum: must agree across variants
+    if (acc == 0x1234567812345678ull) out[0] = acc;
+}
+
+template <int MINB>
+__global__ void __launch_bounds__(256, MINB) k_probe_blake32(uint64_t* out, int iters) {
+    uint32_t ml[16], mh[16], hl[8], hh[8];
+#pragma unroll
+    for (int i = 0; i < 16; i++) {
+        uint64_t w = (uint64_t)(threadIdx.x + 1) * 0x9E3779B97F4A7C15ull + i * 0xBF58476D1CE4E5B9ull + blockIdx.x;
+        ml[i] = (uint32_t)w; mh[i] = (uint32_t)(w >> 32);
+    }
+    for (int it = 0; it < iters; it++) {
+        zkb::blake2b_compress_h32(ml, mh, 128, hl, hh);
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            ml[i] ^= hl[i]; mh[i] ^= hh[i];
+            asm("add.cc.u32 %0, %0, %2;\n\taddc.u32 %1, %1, %3;" : "+r"(ml[8 + i]), "+r"(mh[8 + i]) : "r"(hl[i]), "r"(hh[i]));
+        }
+    }
+    uint64_t acc = 0;
+#pragma unroll
+    for (int i = 0; i < 16; i++) acc ^= ((uint64_t)mh[i] << 32) | ml[i];
+    if (blockIdx.x == 0 && threadIdx.x == 0) out[1] = acc;
+    if (acc == 0x1234567812345678ull) out[0] = acc;
+}
+
+// Register-operand probes: like k_probe but the second/third operands are per-thread REGISTERS
+// (not uniform / constant-bank values), to expose register-file read limits.
+//   20: LOP3 a^=b (2 regs)   21: LOP3 a=a^b^c (3 regs)   22: IADD3 a=a+b+c (3 regs)
+//   23: IADD3 a=a+b (2 regs) 24: PRMT a=prmt(a,b) (2 regs) 25: LOP3(2 regs)+IMAD(3 regs) alternating
+//   26: LOP3 a^=b then IADD3 a+=c (2 regs each, not fusable) 27: SHF a=shf(a,b) (2 regs) 28: IMAD a=a*b+c (3 regs)
+template <int KIND>
+__global__ void __launch_bounds__(256) k_probe_r(uint32_t* out, uint32_t ub, int iters) {
+    uint32_t a[CH], b[CH], c[CH];
+#pragma unroll
+    for (int i = 0; i < CH; i++) {
+        a[i] = threadIdx.x * 2654435761u + i * 40503u + blockIdx.x;
+        b[i] = a[i] * 0x9E3779B9u + 12345u;
+        c[i] = a[i] * 0x7F4A7C15u + 999u;
+    }
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int u = 0; u < UNROLL; u++) {
+#pragma unroll
+            for (int i = 0; i < CH; i++) {
+                const int j = (i + 1 + (u & 3)) % CH;     // vary the partner so operands are distinct registers
+                if (KIND == 20) asm volatile("xor.b32 %0, %0, %1;" : "+r"(a[i]) : "r"(b[j]));
+                else if (KIND == 21) asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(a[i]) : "r"(b[j]), "r"(c[i]));
+                else if (KIND == 22) asm volatile("{ .reg .u32 t; add.u32 t, %0, %1; add.u32 %0, t, %2; }" : "+r"(a[i]) : "r"(b[j]), "r"(c[i]));
+                else if (KIND == 23) asm volatile("add.u32 %0, %0, %1;" : "+r"(a[i]) : "r"(b[j]));
+                else if (KIND == 24) asm volatile("prmt.b32 %0, %0, %1, 0x6543;" : "+r"(a[i]) : "r"(b[j]));
+                else if (KIND == 25) {
+                    if (i & 1) asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(a[i]) : "r"(b[j]), "r"(c[i]));
+                    else asm volatile("xor.b32 %0, %0, %1;" : "+r"(a[i]) : "r"(b[j]));
+                } else if (KIND == 26) asm volatile("xor.b32 %0, %0, %1;\n\tadd.u32 %0, %0, %2;" : "+r"(a[i]) : "r"(b[j]), "r"(c[i]));
+                else if (KIND == 27) asm volatile("shf.l.wrap.b32 %0, %0, %1, 1;" : "+r"(a[i]) : "r"(b[j]));
+                else if (KIND == 30) asm volatile("mul.hi.u32 %0, %0, %1;" : "+r"(a[i]) : "r"(b[j]));
+                else if (KIND == 31) asm volatile("{ .reg .u64 t; mad.wide.u32 t, %0, %1, %2; cvt.u32.u64 %0, t; }" : "+r"(a[i]) : "r"(b[j]), "l"(((unsigned long long)c[i] << 32) | b[i]));
+                else if (KIND == 32) asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(a[i]) : "r"(ub), "r"(c[i]));
+                else if (KIND == 33) asm volatile("mul.hi.u32 %0, %0, %1;" : "+r"(a[i]) : "r"(ub));
+                else asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(a[i]) : "r"(b[j]), "r"(c[i]));
+            }
+        }
+    }
+    uint32_t acc = 0;
+#pragma unroll
+    for (int i = 0; i < CH; i++) acc ^= a[i] ^ b[i] ^ c[i];
+    if (acc == 0x12345678u) out[0] = acc;
+}
+
+template <int KIND>
+static int run_r(int device, double* rate, double* ms_out) {
+    int sms = 0;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    uint32_t* d = nullptr;
+    if (cudaMalloc(&d, 64) != cudaSuccess) return -1;
+    const int iters = 1024, blocks = sms * 8;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    float best = 1e30f;
+    for (int rep = 0; rep < 4; rep++) {
+        cudaEventRecord(e0);
+        k_probe_r<KIND><<<blocks, 256>>>(d, 0x5bd1e995u, iters);
+        cudaEventRecord(e1);
+        if (cudaEventSynchronize(e1) != cudaSuccess) { cudaFree(d); return -1; }
+        float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
+        if (rep > 0 && ms < best) best = ms;
+    }
+    // counted in PTX-level operations: kind 22 is two adds that ptxas fuses into one IADD3
+    double per_thread = (double)iters * UNROLL * CH * (KIND == 26 ? 2 : 1);
+    *rate = per_thread * blocks * 256 / (best * 1e-3);
+    if (ms_out) *ms_out = best;
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaFree(d);
+    return 0;
+}
+
+struct KParams { uint32_t k[4]; };
+template <int CFG>
+__global__ void __launch_bounds__(256, 2) k_probe_blakex(uint64_t* out, int iters, KParams kp) {
+    uint32_t ml[16], mh[16], hl[8], hh[8];
+    const uint32_t K[4] = {kp.k[0], kp.k[1], kp.k[2], kp.k[3]};
+#pragma unroll
+    for (int i = 0; i < 16; i++) {
+        uint64_t w = (uint64_t)(threadIdx.x + 1) * 0x9E3779B97F4A7C15ull + i * 0xBF58476D1CE4E5B9ull + blockIdx.x;
+        ml[i] = (uint32_t)w; mh[i] = (uint32_t)(w >> 32);
+    }
+    for (int it = 0; it < iters; it++) {
+        zkb::blake2b_compress_x<CFG>(ml, mh, 128, K, hl, hh);
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            ml[i] ^= hl[i]; mh[i] ^= hh[i];
+            asm("add.cc.u32 %0, %0, %2;\n\taddc.u32 %1, %1, %3;" : "+r"(ml[8 + i]), "+r"(mh[8 + i]) : "r"(hl[i]), "r"(hh[i]));
+        }
+    }
+    uint64_t acc = 0;
+#pragma unroll
+    for (int i = 0; i < 16; i++) acc ^= ((uint64_t)mh[i] << 32) | ml[i];
+    if (blockIdx.x == 0 && threadIdx.x == 0) out[1] = acc;
+    if (acc == 0x1234567812345678ull) out[0] = acc;
+}
+
+template <int CFG>
+static int run_blakex(int device, double* rate, double* ms_out, uint64_t* checksum) {
+    int sms = 0;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    uint64_t* d = nullptr;
+    if (cudaMalloc(&d, 64) != cudaSuccess) return -1;
+    cudaMemset(d, 0, 64);
+    const int iters = 256, blocks = sms * 16;
+    KParams kp = {{1u, 2u, 256u, 65536u}};
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    float best = 1e30f;
+    for (int rep = 0; rep < 4; rep++) {
+        cudaEventRecord(e0);
+        k_probe_blakex<CFG><<<blocks, 256>>>(d, iters, kp);
+        cudaEventRecord(e1);
+        if (cudaEventSynchronize(e1) != cudaSuccess) { cudaFree(d); return -1; }
+        float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
+        if (rep > 0 && ms < best) best = ms;
+    }
+    uint64_t hsum[2] = {0, 0};
+    cudaMemcpy(hsum, d, 16, cudaMemcpyDeviceToHost);
+    *checksum = hsum[1];
+    *rate = (double)iters * blocks * 256 / (best * 1e-3);
+    if (ms_out) *ms_out = best;
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaFree(d);
+    return 0;
+}
+
+extern "C" int zkb_probe_blakex(int device, int cfg, double* compress_per_s, double* ms_out, uint64_t* checksum) {
+    if (cudaSetDevice(device) != cudaSuccess) return -1;
+    switch (cfg) {
+#define ZKB_RX(C) case C: return run_blakex<C>(device, compress_per_s, ms_out, checksum);
+        ZKB_RX(0) ZKB_RX(1) ZKB_RX(2) ZKB_RX(3) ZKB_RX(4) ZKB_RX(5) ZKB_RX(7) ZKB_RX(8) ZKB_RX(16) ZKB_RX(12) ZKB_RX(20) ZKB_RX(28)
+        ZKB_RX(33) ZKB_RX(35) ZKB_RX(39) ZKB_RX(23) ZKB_RX(55) ZKB_RX(19) ZKB_RX(51) ZKB_RX(11) ZKB_RX(43) ZKB_RX(36) ZKB_RX(37) ZKB_RX(21) ZKB_RX(53)
+        default: return -2;
+    }
+}
+
+template <int V, int MINB>
+static int run_blake(int device, double* rate, double* ms_out, uint64_t* checksum) {
+    int sms = 0;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    uint64_t* d = nullptr;
+    if (cudaMalloc(&d, 64) != cudaSuccess) return -1;
+    cudaMemset(d, 0, 64);
+    const int iters = 256, blocks = sms * 16;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    float best = 1e30f;
+    for (int rep = 0; rep < 4; rep++) {
+        cudaEventRecord(e0);
+        if (V == 32) k_probe_blake32<MINB><<<blocks, 256>>>(d, iters);
+        else k_probe_blake<(V == 32 ? 0 : V), MINB><<<blocks, 256>>>(d, iters);
+        cudaEventRecord(e1);
+        if (cudaEventSynchronize(e1) != cudaSuccess) { cudaFree(d); return -1; }
+        float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
+        if (rep > 0 && ms < best) best = ms;
+    }
+    uint64_t hsum[2] = {0, 0};
+    cudaMemcpy(hsum, d, 16, cudaMemcpyDeviceToHost);
+    *checksum = hsum[1];
+    *rate = (double)iters * blocks * 256 / (best * 1e-3);
+    if (ms_out) *ms_out = best;
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaFree(d);
+    return 0;
+}
+
+// variant = -1 (portable code) or the V bit mask; minb in {1,2,3,4}
+extern "C" int zkb_probe_blake(int device, int variant, int minb, double* compress_per_s, double* ms_out, uint64_t* checksum) {
+    if (cudaSetDevice(device) != cudaSuccess) return -1;
+#define ZKB_RB(V) \
+    if (variant == (V)) { \
+        if (minb == 1) return run_blake<V, 1>(device, compress_per_s, ms_out, checksum); \
+        if (minb == 2) return run_blake<V, 2>(device, compress_per_s, ms_out, checksum); \
+        if (minb == 3) return run_blake<V, 3>(device, compress_per_s, ms_out, checksum); \
+        return run_blake<V, 4>(device, compress_per_s, ms_out, checksum); }
+    ZKB_RB(32) ZKB_RB(-1) ZKB_RB(0) ZKB_RB(1) ZKB_RB(2) ZKB_RB(3) ZKB_RB(5) ZKB_RB(7) ZKB_RB(9) ZKB_RB(11) ZKB_RB(15) ZKB_RB(17) ZKB_RB(19) ZKB_RB(4) ZKB_RB(8) ZKB_RB(6)
+    return -2;
+}
+
 extern "C" int zkb_probe_int_pipe(int device, int kind, double* lane_ops_per_s, double* ms_out) {
     if (cudaSetDevice(device) != cudaSuccess) return -1;
+    switch (kind) {
+        case 20: return run_r<20>(device, lane_ops_per_s, ms_out);
+        case 21: return run_r<21>(device, lane_ops_per_s, ms_out);
+        case 22: return run_r<22>(device, lane_ops_per_s, ms_out);
+        case 23: return run_r<23>(device, lane_ops_per_s, ms_out);
+        case 24: return run_r<24>(device, lane_ops_per_s, ms_out);
+        case 25: return run_r<25>(device, lane_ops_per_s, ms_out);
+        case 26: return run_r<26>(device, lane_ops_per_s, ms_out);
+        case 27: return run_r<27>(device, lane_ops_per_s, ms_out);
+        case 28: return run_r<28>(device, lane_ops_per_s, ms_out);
+        case 30: return run_r<30>(device, lane_ops_per_s, ms_out);
+        case 31: return run_r<31>(device, lane_ops_per_s, ms_out);
+        case 32: return run_r<32>(device, lane_ops_per_s, ms_out);
+        case 33: return run_r<33>(device, lane_ops_per_s, ms_out);
+        default: break;
+    }
     int sms = 0;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
     uint32_t* d = nullptr;
@@ -53,13 +301,18 @@ extern "C" int zkb_probe_int_pipe(int device, int kind, double* lane_ops_per_s, 
         cudaEventRecord(e0);
         if (kind == 0) k_probe<0><<<blocks, threads>>>(d, 0x9E3779B9u, 0x7F4A7C15u, iters);
         else if (kind == 1) k_probe<1><<<blocks, threads>>>(d, 0x9E3779B9u, 0x7F4A7C15u, iters);
-        else k_probe<2><<<blocks, threads>>>(d, 0x9E3779B9u, 0x7F4A7C15u, iters);
+        else if (kind == 2) k_probe<2><<<blocks, threads>>>(d, 0x9E3779B9u, 0x7F4A7C15u, iters);
+        else if (kind == 3) k_probe<3><<<blocks, threads>>>(d, 0x9E3779B9u, 0x7F4A7C15u, iters);
+        else if (kind == 4) k_probe<4><<<blocks, threads>>>(d, 0x9E3779B9u, 0x7F4A7C15u, iters);
+        else if (kind == 5) k_probe<5><<<blocks, threads>>>(d, 0x9E3779B9u, 0x7F4A7C15u, iters);
+        else { double r = 0; uint64_t cs = 0; cudaFree(d); return run_blake<-1, 2>(device, lane_ops_per_s, ms_out, &cs) + (int)(r * 0); }
         cudaEventRecord(e1);
         if (cudaEventSynchronize(e1) != cudaSuccess) { cudaFree(d); return -1; }
         float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
         if (rep > 0 && ms < best) best = ms;
     }
-    double per_thread = (double)iters * UNROLL * (kind == 0 ? CH * 2 : (kind == 1 ? CH : (CH / 2) * 2 + (CH / 2)));
+    double per_thread = (double)iters * UNROLL * (kind == 0 || kind == 3 || kind == 4 ? CH * 2 : (kind == 1 || kind == 5 ? CH : (CH / 2) * 2 + (CH / 2)));
+
     *lane_ops_per_s = per_thread * blocks * threads / (best * 1e-3);
     if (ms_out) *ms_out = best;
     cudaEventDestroy(e0); cudaEventDestroy(e1);
