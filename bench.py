@@ -54,6 +54,11 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--cpu-log-n", type=int, default=14, help="codeword size of the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="codeword", choices=["codeword", "columns"],
+                    help="codeword: one 2^log_n codeword per rank (weak scaling, the default, BASELINE configs[2]); "
+                         "columns: BASELINE configs[3], --columns trace columns of 2^log_n (default 64 x 2^22) dealt "
+                         "round-robin to the ranks (strong scaling)")
+    ap.add_argument("--columns", type=int, default=64)
     return ap.parse_args()
 
 
@@ -184,6 +189,11 @@ def b200_arm(args):
 
     stream = torch.cuda.current_stream()
     ctx = zk.Context(local, stream=stream.cuda_stream)
+    columns_mode = args.workload == "columns"
+    if columns_mode and args.log_n == 24:
+        args.log_n = 22
+    from zk_stark_tutor_b200 import columns as colmod
+    my_cols = colmod.partition(args.columns, world, rank) if columns_mode else [rank]
     log_n = args.log_n
     n, n_coeffs = 1 << log_n, (1 << log_n) // EF
     field = zk.Field()
@@ -191,12 +201,14 @@ def b200_arm(args):
     fri = zk.FRI(GENERATOR, omega, n, EF, NCC, ctx)
     rounds = fri.num_rounds()
     last_len = n >> (rounds - 1)
-    host_coeffs = torch.from_numpy(synth.elements(SEED + rank, n_coeffs).view(np.int64)).pin_memory()
-    dev_coeffs = host_coeffs.cuda(non_blocking=True)
+    # one pinned host / device coefficient buffer per local column (columns mode: seeds s + col)
+    host_cols = [torch.from_numpy(synth.elements(SEED + c, n_coeffs).view(np.int64)).pin_memory() for c in my_cols]
+    dev_cols = [h.cuda(non_blocking=True) for h in host_cols]
+    host_coeffs, dev_coeffs = host_cols[0], dev_cols[0]
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")          # > 126 MB L2
     lib = ctx.lib
 
-    def step(coeffs_ptr):
+    def one(coeffs_ptr):
         ps = zk.IndependentProofStream()
         h = ctypes.c_void_p()
         ctx.check(lib.zkb_lde_fri_commit_ps(ctx.h, ctypes.byref(fri.params), coeffs_ptr, n_coeffs, ps.h, ctypes.byref(h)))
@@ -204,6 +216,10 @@ def b200_arm(args):
         lib.zkb_fri_layers_free(h)
         ps.close()
         return proof_bytes
+
+    def step(bufs):
+        """one step = LDE + FRI commit of every local column (one in codeword mode)"""
+        return [one(b.data_ptr()) for b in bufs]
 
     def timed(coeffs_ptr, steps, profile):
         evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
@@ -228,20 +244,22 @@ def b200_arm(args):
         return float(t.item()), launches, prof
 
     for _ in range(max(args.warmup, 3)):
-        step(dev_coeffs.data_ptr())
+        step(dev_cols)
     sampler = ClockSampler(local) if rank == 0 else None
-    total_ms, launches, prof = timed(dev_coeffs.data_ptr(), args.steps, True)
+    total_ms, launches, prof = timed(dev_cols, args.steps, True)
     clocks = sampler.stop() if sampler else None
     for _ in range(2):
-        step(host_coeffs.data_ptr())
+        step(host_cols)
     e2e_steps = max(3, args.steps // 2)
-    e2e_ms, _, _ = timed(host_coeffs.data_ptr(), e2e_steps, False)
+    e2e_ms, _, _ = timed(host_cols, e2e_steps, False)
 
     if rank == 0:
         ms_per_step = total_ms / args.steps
-        value = world * n / (ms_per_step * 1e-3) / 1e6
-        e2e_value = world * n / (e2e_ms / e2e_steps * 1e-3) / 1e6
-        # ---- roofline of the dominant kernel: layer-0 leaf hashing (k_leaf_tile<false>), one launch per step
+        units = (args.columns if columns_mode else world) * n        # codeword elements processed by all ranks per step
+        value = units / (ms_per_step * 1e-3) / 1e6
+        e2e_value = units / (e2e_ms / e2e_steps * 1e-3) / 1e6
+        cols_here = len(my_cols)
+        # ---- roofline of the dominant kernel: layer-0 leaf hashing (k_leaf8<false>), one launch per step
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -251,11 +269,11 @@ def b200_arm(args):
         kern = {k: {"ms_per_step": v[0] / args.steps, "launches_per_step": v[1] / args.steps} for k, v in prof.items()}
         dom = max(prof.items(), key=lambda kv: kv[1][0])[0] if prof else None
         roof = None
-        if "k_leaf_tile<false>" in prof:
-            ms_l, cnt = prof["k_leaf_tile<false>"]
+        if "k_leaf8<false>" in prof:
+            ms_l, cnt = prof["k_leaf8<false>"]
             dur = ms_l / cnt * 1e-3
-            alg_bytes = 16 * n + 64 * (n >> 5)               # read every value once, write the level-5 nodes
-            compressions = n + (n - (n >> 5))                # n leaves + levels 1..5
+            alg_bytes = 16 * n + 64 * (n >> 3)               # read every value once, write the level-3 nodes
+            compressions = n + (n - (n >> 3))                # n leaves + levels 1..3
             alu_ops = compressions * 2144                    # SURVEY.md 8d canonical ALU-op count per compression
             probe = {}
             try:
@@ -267,7 +285,7 @@ def b200_arm(args):
             except OSError:
                 pass
             achieved = alg_bytes / dur / 1e9
-            roof = {"kernel": "k_leaf_tile<false> (layer-0 leaf + 5 tree levels per 1024-leaf tile)", "bound": "hbm",
+            roof = {"kernel": "k_leaf8<false> (layer-0: 8 leaf hashes + 7 nodes per thread)", "bound": "hbm",
                     "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None,
                     "peak_source": peak_src, "launch_ms": dur * 1e3, "share_of_step": ms_l / args.steps / ms_per_step,
                     "note": "this kernel is integer-ALU bound, not HBM bound: see int_pipe",
@@ -276,15 +294,17 @@ def b200_arm(args):
                                  "ops_per_compression": 2144}}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if columns_mode else "weak", "vs_baseline": None,
             "dtype": "u128 (prime field p = 1 + 407*2^119, 4x32-bit limb Montgomery; BLAKE2b-512 on u32 pairs)", "data": "synthetic",
-            "config": {"workload": "configs[2]: coset LDE (2^%d coefficients -> 2^%d codeword) + Merkle commit + full FRI commit "
-                                   "(%d roots, %d folds, last codeword %d; ef 4, 64 colinearity tests), one codeword per GPU"
-                                   % (log_n - 2, log_n, rounds, rounds - 1, last_len),
+            "config": {"workload": ("configs[3]: %d trace columns x 2^%d dealt round-robin over %d GPU(s); per column: " % (args.columns, log_n, world)
+                                    if columns_mode else "configs[2]: ") +
+                                   "coset LDE (2^%d coefficients -> 2^%d codeword) + Merkle commit + full FRI commit "
+                                   "(%d roots, %d folds, last codeword %d; ef 4, 64 colinearity tests)%s"
+                                   % (log_n - 2, log_n, rounds, rounds - 1, last_len, "" if columns_mode else ", one codeword per GPU"),
                        "log_n": log_n, "expansion_factor": EF, "num_colinearity_tests": NCC, "rounds": rounds,
                        "l2": "flushed between steps (256 MiB write, untimed); per-step CUDA events summed; working set per step > L2",
-                       "parallelism": "independent codeword per rank, no collective"},
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n_coeffs * 16, "d2h_bytes_per_step": rounds * 64 + last_len * 16,
+                       "parallelism": "independent codewords / columns per rank, no data-path collective"},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": cols_here * n_coeffs * 16, "d2h_bytes_per_step": cols_here * (rounds * 64 + last_len * 16),
                     "ms_per_step": e2e_ms / e2e_steps, "api": "zkb_lde_fri_commit_ps with pinned host coefficients"},
             "gpu_launches": launches, "kernels": kern, "dominant_kernel": dom,
             "roofline": roof, "clocks": clocks,
@@ -310,6 +330,11 @@ def b200_arm(args):
 
 def main():
     args = parse()
+    # keep stdout clean for the ONE JSON line: libraries (NCCL prints its version there) write to
+    # fd 1 during init, so fd 1 is pointed at stderr until the line is printed
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(saved_stdout, "w")
     if args.impl == "reference":
         reference_arm(args)
     else:

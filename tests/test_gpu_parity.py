@@ -434,7 +434,7 @@ def test_profile_counters(ctx):
     zk.MerkleRoot.commit(C.synth(1, n), ctx)
     prof = ctx.profile_read()
     ctx.profile(False)
-    assert prof["k_leaf_tile<false>"][1] == 1 and prof["k_leaf_tile<false>"][0] > 0
+    assert prof["k_leaf8<false>"][1] == 1 and prof["k_leaf8<false>"][0] > 0
 
 
 def test_fast_multiply_trailing_zero_quirk(ctx):
@@ -464,3 +464,22 @@ def test_ntt_with_non_primitive_root_matches_reference_loop(ctx):
         r = F.primitive_nth_root(order)
         xs = rvals(n)
         assert zk.ntt(r, xs, ctx) == N.ntt(r, xs)
+
+
+def test_columns_lde_commit_matches_oracle(ctx):
+    """BASELINE configs[3] in miniature: independent columns -> LDE + FRI commit each; roots
+    gathered (world = 1 here; the 2/3-rank gather is covered on CPU by test_columns_gloo.py)."""
+    from zk_stark_tutor_b200 import columns
+    n, n_cols = 1 << 13, 5
+    w = F.primitive_nth_root(n)
+    fri = zk.FRI(F.GENERATOR, w, n, 4, 64, ctx)
+    ofri = OFRI(F.GENERATOR, w, n, 4, 64)
+    mine = columns.partition(n_cols, 1, 0)
+    coeffs = [C.synth(0x5EED0004 + c, n // 4) for c in mine]
+    got = columns.lde_commit_columns(fri, [cuda(x) for x in coeffs], zk.IndependentProofStream, ctx)
+    allr = columns.gather_roots([g[0] for g in got], n_cols, 1, 0, fri.num_rounds())
+    for c, x in zip(mine, coeffs):
+        ops = PS.IndependentProofStream()
+        _, trees, _ = fastfri.commit(ofri, C.coset_lde(w, n, F.GENERATOR, x), ops)
+        assert got[c][1] == ops.digest()
+        assert [bytes(allr[c, r]) for r in range(len(trees))] == [t.root for t in trees]

@@ -1,0 +1,59 @@
+"""Independent trace columns / codewords across the GPUs of one box (BASELINE
+configs[3]): every column is an independent LDE -> Merkle -> FRI commit, so columns are dealt
+round-robin to ranks (one process per GPU, its own context and stream) and NO field data
+crosses NVLink - only the 64-byte roots are gathered (torch.distributed, NCCL on GPUs / gloo in
+the CPU tests).  This mirrors how Stark::prove treats its registers (stark.rs:373-381: one
+fast_coset_evaluate + MerkleRoot::commit per register, independent of each other)."""
+import numpy as np
+
+
+def partition(n_cols, world, rank):
+    """Column indices owned by `rank` (round-robin: balanced for any n_cols)."""
+    return list(range(rank, n_cols, world))
+
+
+def owner(col, world):
+    return col % world
+
+
+def lde_commit_columns(fri, columns, make_stream, ctx=None):
+    """LDE + FRI commit of each local coefficient column.  `columns`: iterable of (n_coeffs, 2)
+    arrays / CUDA tensors.  Returns [(roots [R x 64 bytes], proof-stream digest)] per column."""
+    out = []
+    for col in columns:
+        ps = make_stream()
+        layers = fri.lde_commit(col, ps)
+        roots = [layers.root(r) for r in range(len(layers))]
+        layers.close()
+        out.append((roots, ps.digest()))
+    return out
+
+
+def gather_roots(local_roots, n_cols, world, rank, rounds, group=None):
+    """All ranks receive every column's roots: (n_cols, rounds, 64) uint8.  `local_roots`:
+    list (in partition order) of per-column lists of 64-byte roots.  world == 1 needs no
+    process group."""
+    mine = partition(n_cols, world, rank)
+    assert len(local_roots) == len(mine)
+    per_rank = (n_cols + world - 1) // world
+    buf = np.zeros((per_rank, rounds, 64), dtype=np.uint8)
+    for k, roots in enumerate(local_roots):
+        assert len(roots) == rounds
+        for r, root in enumerate(roots):
+            buf[k, r] = np.frombuffer(root, dtype=np.uint8)
+    out = np.zeros((n_cols, rounds, 64), dtype=np.uint8)
+    if world == 1:
+        out[:] = buf[:n_cols]
+        return out
+    import torch
+    import torch.distributed as dist
+    backend = dist.get_backend(group)
+    dev = torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu")
+    t = torch.from_numpy(buf).to(dev)
+    parts = [torch.empty_like(t) for _ in range(world)]
+    dist.all_gather(parts, t, group=group)
+    for rk, p in enumerate(parts):
+        p = p.cpu().numpy()
+        for k, col in enumerate(partition(n_cols, world, rk)):
+            out[col] = p[k]
+    return out

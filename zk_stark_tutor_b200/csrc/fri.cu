@@ -12,7 +12,7 @@
 // reference's pow + xgcd inverse + 5 products.  omega^-i comes from one two-level power
 // table of omega_0^-1 shared by all rounds (round r uses exponent i*2^r).  For layers of
 // more than 1024 values the fold runs inside the leaf-hash kernel of the NEXT layer
-// (merkle.cu k_leaf_tile<true>): the folded value is written once to HBM and hashed while
+// (merkle.cu k_leaf8<true> / k_top): the folded value is written once to HBM and hashed while
 // still in registers.  Every layer (codeword + pruned tree) stays on the device for the
 // query phase; only the 64-byte root goes to the host each round, where the Fiat-Shamir
 // callback turns it into alpha (SHAKE256 over a transcript of < 1.5 KB).
@@ -194,12 +194,7 @@ static int fri_commit_impl(zkb_ctx* c, const zkb_fri_params* p, const void* code
             f.winv = winv_tab; f.exp_mul = 1ull << (r - 1);
             f.kk_m = fe_to_mont(h_mul(alpha, h_inv(offset_r)));
             f.wr_inv_m = fe_to_mont(omega_inv_r);
-            if (tl.cut > 0) {
-                rc = merkle_build_levels(c, nullptr, &f, len, tl, L->nodes[r]);     // fold fused with leaf hashing
-            } else {
-                rc = launch_fold(c, f);
-                if (!rc) rc = merkle_build_levels(c, L->cw[r], nullptr, len, tl, L->nodes[r]);
-            }
+            rc = merkle_build_levels(c, nullptr, &f, len, tl, L->nodes[r]);         // fold fused with leaf hashing
             offset_r = h_mul(offset_r, offset_r);        // fri.rs:161-162
             omega_inv_r = h_mul(omega_inv_r, omega_inv_r);
         }

@@ -5,20 +5,18 @@
 //   MerkleRoot::open    src/merkle_root.rs:34-66  (the reference re-hashes the whole tree per call)
 //   MerkleRoot::verify  src/merkle_root.rs:69-95  (host, hosthash.cpp)
 //
-// Kernel structure.  The work is ALU-pipe bound (2,128 32-bit ops per compression), so
-// the design goals are full warps in every hashing step and no HBM round trip between
-// the levels of a subtree:
-//   k_leaf_tile   1024 leaves per CTA.  Each thread hashes 4 consecutive leaves and the 3
-//                 nodes above them in registers (7 compressions, no synchronisation), the
-//                 256 level-2 nodes then go through shared memory (128-bit accesses, XOR
-//                 swizzled so both the 64-byte stores and the 128-byte loads are
-//                 conflict-free) for levels 3, 4, 5 with 4, 2, 1 full warps.  Only the 32
-//                 level-5 nodes leave the SM.  With FoldArgs the 4 values are produced by
-//                 the FRI split-and-fold of the previous layer instead of being loaded,
-//                 and are written out as the next codeword ("fold fused with the next
-//                 round's leaf hashing").
-//   k_node_tile   the same shape over 1024 stored nodes -> 5 more levels per launch.
-//   k_small       one CTA finishes any tree (or tree top) of <= 1024 inputs.
+// Kernel structure.  BLAKE2b is bound by the ALU pipe (2,014 ALU-pipe instructions per
+// compression at one per 2 clk per SM sub-partition), so the goal is that every
+// resident warp executes compressions back to back with no barrier and no shrinking tail:
+//   k_leaf8   one THREAD per 8 consecutive leaves: 8 leaf hashes + the 7 nodes above them
+//             (15 compressions, depth first, nothing shared) -> one level-3 node (8 B/leaf
+//             written).  With FoldArgs the 8 values are produced by the FRI split-and-fold
+//             of the previous layer and written out as the next codeword ("fold fused with
+//             the next round's leaf hashing").
+//   k_node8   the same over 8 stored nodes: 7 compressions -> the node three levels up.
+//   k_top     one CTA finishes any level of <= 1024 inputs (leaves or nodes), every level
+//             stored; also the whole tree for n <= 1024.
+#include <stdlib.h>
 #include <string.h>
 #include "merkle.cuh"
 #include "blake2b.cuh"
@@ -27,10 +25,18 @@ namespace zkb {
 
 void TreeLayout::init(uint32_t log_n_) {
     log_n = log_n_;
-    cut = log_n > 10 ? 5 : 0;
     uint64_t off = 0;
-    for (uint32_t l = 0; l <= 40; l++) level_off[l] = 0;
-    for (uint32_t l = cut; l <= log_n; l++) {
+    for (uint32_t l = 0; l <= 40; l++) { level_off[l] = 0; stored[l] = 0; }
+    if (log_n <= 10) {
+        top = 0;
+    } else {
+        top = 3;
+        while (log_n - top > 10) top += 3;
+        for (uint32_t l = 3; l < top; l += 3) stored[l] = 1;
+    }
+    for (uint32_t l = top; l <= log_n; l++) stored[l] = 1;
+    for (uint32_t l = 0; l <= log_n; l++) {
+        if (!stored[l]) continue;
         level_off[l] = off;
         off += 1ull << (log_n - l);
     }
@@ -38,17 +44,17 @@ void TreeLayout::init(uint32_t log_n_) {
 }
 
 // ---- compression wrappers.  __noinline__ keeps ONE copy of each 2.2k-instruction body per
-// kernel (10 call sites in k_leaf_tile would otherwise be 350 KB of code).
+// kernel instead of one per call site.
 __device__ __noinline__ void b2_leaf_call(const fe* a, uint64_t* h) {
     uint64_t out[8];
     blake2b_leaf(*a, out);
 #pragma unroll
     for (int i = 0; i < 8; i++) h[i] = out[i];
 }
-__device__ __noinline__ void b2_block_call(const uint64_t* m_in, uint64_t* h) {
+__device__ __noinline__ void b2_node_call(const uint64_t* l, const uint64_t* r, uint64_t* h) {
     uint64_t m[16], out[8];
 #pragma unroll
-    for (int i = 0; i < 16; i++) m[i] = m_in[i];
+    for (int i = 0; i < 8; i++) { m[i] = l[i]; m[8 + i] = r[i]; }
     blake2b_compress_1block(m, 128, out);
 #pragma unroll
     for (int i = 0; i < 8; i++) h[i] = out[i];
@@ -96,110 +102,86 @@ __device__ __forceinline__ fe pow2lvl_m(const DevPow& t, uint64_t e) {
     return fe_montmul(hi, lo);
 }
 
-// Shared tail of both tile kernels: 256 nodes (one per thread, `h`) at relative level 0 ->
-// relative levels 1, 2, 3 (128, 64, 32 nodes).  lvl_ptr[r] = where to store relative level
-// r+1 in global memory (nullptr = not stored); tile = CTA index.
-__device__ __forceinline__ void tile_tail(uint4* regA, uint4* regB, uint32_t tid, uint64_t tile,
-                                          uint64_t* h, uint8_t* out1, uint8_t* out2, uint8_t* out3) {
-    uint64_t m[16];
-    sm_store_digest(regA, tid, h);
-    __syncthreads();
-    if (tid < 128) {
-        sm_load_pair(regA, tid, m);
-        b2_block_call(m, h);
-        sm_store_digest(regB, tid, h);
-        if (out1) g_store_digest(out1, tile * 128 + tid, h);
-    }
-    __syncthreads();
-    if (tid < 64) {
-        sm_load_pair(regB, tid, m);
-        b2_block_call(m, h);
-        sm_store_digest(regA, tid, h);
-        if (out2) g_store_digest(out2, tile * 64 + tid, h);
-    }
-    __syncthreads();
-    if (tid < 32) {
-        sm_load_pair(regA, tid, m);
-        b2_block_call(m, h);
-        g_store_digest(out3, tile * 32 + tid, h);
-    }
+// The FRI split-and-fold (fri.rs:150-159) of element i: k_m = alpha/(offset*omega^i) * R
+__device__ __forceinline__ fe fold_one(const FoldArgs& f, uint64_t i, const fe& k_m) {
+    fe a = fe_ldg(f.cw + i), b = fe_ldg(f.cw + f.half + i);
+    fe s = fe_add(a, b), d = fe_sub(a, b);
+    fe v = fe_half(fe_add(s, fe_montmul(k_m, d)));
+    fe_store(f.next + i, v);
+    return v;
 }
 
-// 1024 leaves per CTA -> 32 level-5 nodes.
-template <bool FOLD>
-__global__ void __launch_bounds__(256, 2) k_leaf_tile(const fe* __restrict__ vals, FoldArgs f, uint8_t* __restrict__ out5) {
-    __shared__ uint4 regA[256 * 4];
-    __shared__ uint4 regB[128 * 4];
-    const uint32_t tid = threadIdx.x;
-    const uint64_t tile = blockIdx.x;
-    const uint64_t i0 = tile * 1024 + (uint64_t)tid * 4;
-    fe v[4];
-    if (FOLD) {
-        fe k_m = fe_montmul(f.kk_m, pow2lvl_m(f.winv, i0 * f.exp_mul));   // alpha/(offset*omega^i0) * R
-#pragma unroll
-        for (int t = 0; t < 4; t++) {
-            fe a = fe_ldg(f.cw + i0 + t), b = fe_ldg(f.cw + f.half + i0 + t);
-            fe s = fe_add(a, b), d = fe_sub(a, b);
-            v[t] = fe_half(fe_add(s, fe_montmul(k_m, d)));
-            fe_store(f.next + i0 + t, v[t]);
+// Depth-first reduction of 8 digests produced one at a time by `next(j, out)`:
+// 7 node compressions, two pending digests at most per level.
+template <typename Next>
+__device__ __forceinline__ void reduce8(Next next, uint64_t* h) {
+    uint64_t d0[8], d1[8], a[8], b[8];
+    next(0, d0); next(1, d1); b2_node_call(d0, d1, a);          // level 1, #0
+    next(2, d0); next(3, d1); b2_node_call(d0, d1, d1);         // level 1, #1
+    b2_node_call(a, d1, b);                                     // level 2, #0
+    next(4, d0); next(5, d1); b2_node_call(d0, d1, a);          // level 1, #2
+    next(6, d0); next(7, d1); b2_node_call(d0, d1, d1);         // level 1, #3
+    b2_node_call(a, d1, a);                                     // level 2, #1
+    b2_node_call(b, a, h);                                      // level 3
+}
+
+// One thread per 8 leaves -> one level-3 node.  n_groups = n / 8.
+template <bool FOLD, int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB) k_leaf8(const fe* __restrict__ vals, FoldArgs f, uint64_t n_groups, uint8_t* __restrict__ out3) {
+    const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n_groups) return;
+    const uint64_t i0 = g * 8;
+    fe k_m;
+    if (FOLD) k_m = fe_montmul(f.kk_m, pow2lvl_m(f.winv, i0 * f.exp_mul));
+    uint64_t h[8];
+    reduce8([&](int j, uint64_t* out) {
+        fe v;
+        if (FOLD) {
+            v = fold_one(f, i0 + j, k_m);
             k_m = fe_montmul(k_m, f.wr_inv_m);
+        } else {
+            v = fe_ldg(vals + i0 + j);
         }
-    } else {
-#pragma unroll
-        for (int t = 0; t < 4; t++) v[t] = fe_ldg(vals + i0 + t);
-    }
-    uint64_t m[16], h[8];
-    b2_leaf_call(&v[0], m);
-    b2_leaf_call(&v[1], m + 8);
-    b2_block_call(m, h);                 // level-1 node over leaves 0,1
-    b2_leaf_call(&v[2], m);
-    b2_leaf_call(&v[3], m + 8);
-    b2_block_call(m, m + 8);             // level-1 node over leaves 2,3 (input copied before the write)
-#pragma unroll
-    for (int i = 0; i < 8; i++) m[i] = h[i];
-    b2_block_call(m, h);                 // level-2 node, index tile*256 + tid
-    tile_tail(regA, regB, tid, tile, h, nullptr, nullptr, out5);
+        b2_leaf_call(&v, out);
+    }, h);
+    g_store_digest(out3, g, h);
 }
 
-// 1024 stored nodes (relative level 0) per CTA -> relative levels 1..5, all stored.
-__global__ void __launch_bounds__(256, 2) k_node_tile(const uint8_t* __restrict__ in, uint8_t* out1, uint8_t* out2,
-                                                      uint8_t* out3, uint8_t* out4, uint8_t* out5) {
-    __shared__ uint4 regA[256 * 4];
-    __shared__ uint4 regB[128 * 4];
-    const uint32_t tid = threadIdx.x;
-    const uint64_t tile = blockIdx.x;
-    const uint64_t i0 = tile * 1024 + (uint64_t)tid * 4;
-    uint64_t m[16], h[8], h2[8];
-    g_load_digest(in, i0, m); g_load_digest(in, i0 + 1, m + 8);
-    b2_block_call(m, h);
-    g_store_digest(out1, tile * 512 + tid * 2, h);
-    g_load_digest(in, i0 + 2, m); g_load_digest(in, i0 + 3, m + 8);
-    b2_block_call(m, h2);
-    g_store_digest(out1, tile * 512 + tid * 2 + 1, h2);
-#pragma unroll
-    for (int i = 0; i < 8; i++) { m[i] = h[i]; m[8 + i] = h2[i]; }
-    b2_block_call(m, h);
-    g_store_digest(out2, tile * 256 + tid, h);
-    tile_tail(regA, regB, tid, tile, h, out3, out4, out5);
+// One thread per 8 stored nodes -> the node three levels up.
+template <int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB) k_node8(const uint8_t* __restrict__ in, uint64_t n_groups, uint8_t* __restrict__ out) {
+    const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n_groups) return;
+    uint64_t h[8];
+    reduce8([&](int j, uint64_t* o) { g_load_digest(in, g * 8 + j, o); }, h);
+    g_store_digest(out, g, h);
 }
 
-// One CTA: `count` (power of two, <= 1024) leaves or nodes -> every level up to the root.
-// level_out[r] = global destination of relative level r (r = 0 is the leaf-hash level and
-// is only written for leaf input).  Dynamic shared memory: 1024 + 512 digests.
-struct SmallArgs {
+// One CTA of 512 threads: `count` (power of two, <= 1024) leaves or nodes -> every level up to
+// the root.  level_out[r] = global destination of relative level r (r = 0 is the input level
+// and is only written for leaf input).  Dynamic shared memory: 1024 + 512 digests.
+#define ZKB_TOP_THREADS 512
+struct TopArgs {
     const fe* vals;          // leaf input (or nullptr)
     const uint8_t* nodes_in; // node input (or nullptr)
     uint32_t count;
+    uint32_t fold;           // leaf values come from folding f (written to f.next)
+    FoldArgs f;
     uint8_t* level_out[12];
 };
-__global__ void __launch_bounds__(256) k_small(SmallArgs a) {
+__global__ void __launch_bounds__(ZKB_TOP_THREADS) k_top(TopArgs a) {
     extern __shared__ uint4 dyn[];
     uint4* cur = dyn;
     uint4* nxt = dyn + 1024 * 4;
     const uint32_t tid = threadIdx.x;
     uint64_t m[16], h[8];
-    for (uint32_t i = tid; i < a.count; i += 256) {
-        if (a.vals) {
+    for (uint32_t i = tid; i < a.count; i += ZKB_TOP_THREADS) {
+        if (a.fold) {
+            fe k_m = fe_montmul(a.f.kk_m, pow2lvl_m(a.f.winv, (uint64_t)i * a.f.exp_mul));
+            fe v = fold_one(a.f, i, k_m);
+            b2_leaf_call(&v, h);
+            g_store_digest(a.level_out[0], i, h);
+        } else if (a.vals) {
             fe v = fe_ldg(a.vals + i);
             b2_leaf_call(&v, h);
             g_store_digest(a.level_out[0], i, h);
@@ -211,9 +193,9 @@ __global__ void __launch_bounds__(256) k_small(SmallArgs a) {
     uint32_t level = 1;
     for (uint32_t cnt = a.count >> 1; cnt >= 1; cnt >>= 1, level++) {
         __syncthreads();
-        for (uint32_t j = tid; j < cnt; j += 256) {
+        for (uint32_t j = tid; j < cnt; j += ZKB_TOP_THREADS) {
             sm_load_pair(cur, j, m);
-            b2_block_call(m, h);
+            b2_node_call(m, m + 8, h);
             sm_store_digest(nxt, j, h);
             g_store_digest(a.level_out[level], j, h);
         }
@@ -221,7 +203,9 @@ __global__ void __launch_bounds__(256) k_small(SmallArgs a) {
     }
 }
 
-// Authentication paths.  One warp per opened index.
+// Authentication paths.  One warp per opened index.  Stored levels are read; the levels inside
+// a group of three whose base is the leaves or a stored level are recomputed from the 8 group
+// inputs (8 leaf hashes or 8 loads, then 4 + 2 compressions).
 struct OpenArgs {
     const fe* vals;
     const uint8_t* nodes;
@@ -231,54 +215,70 @@ struct OpenArgs {
     uint8_t* out;            // k * log_n * 64 bytes
 };
 __global__ void __launch_bounds__(128) k_open(OpenArgs a) {
-    __shared__ uint64_t dig[4][48][8];          // per warp: 32 + 16 digests
+    __shared__ uint64_t dig[4][14][8];          // per warp: 8 + 4 + 2 digests
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t q = blockIdx.x * 4 + warp;
     if (q >= a.k) return;
     const uint64_t idx = a.idx[q];
-    const uint32_t log_n = a.layout.log_n, cut = a.layout.cut;
+    const uint32_t log_n = a.layout.log_n;
     uint4* out = reinterpret_cast<uint4*>(a.out + (uint64_t)q * log_n * 64);
-    if (cut > 0) {
-        // recompute the 32-leaf subtree around idx (cut == 5)
-        uint64_t (*A)[8] = dig[warp];
-        uint64_t (*Bq)[8] = dig[warp] + 32;
-        const uint64_t base = idx & ~31ull;
-        {
-            fe v = fe_ldg(a.vals + base + lane);
+    uint64_t (*D)[8] = dig[warp];
+    uint32_t l = 0;
+    while (l < log_n) {
+        if (a.layout.stored[l] && (l + 1 > log_n || a.layout.stored[l + 1] || l + 1 == log_n)) {
+            // sibling available directly, and the next level does not need a recomputation
+            const uint4* sib = reinterpret_cast<const uint4*>(a.nodes + (a.layout.level_off[l] + ((idx >> l) ^ 1)) * 64);
+            if (lane < 4) out[l * 4 + lane] = __ldg(sib + lane);
+            l++;
+            continue;
+        }
+        // group with base level l (leaves when l == 0 and not stored, else a stored level):
+        // emits the siblings at levels l, l+1, l+2
+        const uint64_t base = (idx >> (l + 3)) << 3;                // first of the 8 group inputs at level l
+        if (lane < 8) {
             uint64_t h[8];
-            b2_leaf_call(&v, h);
-            for (int i = 0; i < 8; i++) A[lane][i] = h[i];
+            if (a.layout.stored[l]) {
+                g_load_digest(a.nodes + a.layout.level_off[l] * 64, base + lane, h);
+            } else {
+                fe v = fe_ldg(a.vals + base + lane);
+                b2_leaf_call(&v, h);
+            }
+            for (int i = 0; i < 8; i++) D[lane][i] = h[i];
         }
         __syncwarp();
-        uint32_t pos = (uint32_t)(idx & 31);
-        for (uint32_t t = 0; t < cut; t++) {
-            // level t digests are in A (32 >> t of them); emit the sibling, then hash up into Bq
-            const uint4* sib = reinterpret_cast<const uint4*>(A[(pos >> t) ^ 1]);
-            if (lane < 4) out[t * 4 + lane] = sib[lane];
-            uint32_t cnt = 32u >> (t + 1);
-            if (lane < cnt && t + 1 < cut) {
-                uint64_t m[16], h[8];
-                for (int i = 0; i < 8; i++) { m[i] = A[2 * lane][i]; m[8 + i] = A[2 * lane + 1][i]; }
-                b2_block_call(m, h);
-                for (int i = 0; i < 8; i++) Bq[lane][i] = h[i];
-            }
-            __syncwarp();
-            uint64_t (*tmp)[8] = A; A = Bq; Bq = tmp;
+        if (lane < 4) {
+            uint64_t h[8];
+            b2_node_call(D[2 * lane], D[2 * lane + 1], h);
+            for (int i = 0; i < 8; i++) D[8 + lane][i] = h[i];
         }
-    }
-    for (uint32_t l = cut; l < log_n; l++) {
-        const uint4* sib = reinterpret_cast<const uint4*>(a.nodes + (a.layout.level_off[l] + ((idx >> l) ^ 1)) * 64);
-        if (lane < 4) out[l * 4 + lane] = __ldg(sib + lane);
+        __syncwarp();
+        if (lane < 2) {
+            uint64_t h[8];
+            b2_node_call(D[8 + 2 * lane], D[8 + 2 * lane + 1], h);
+            for (int i = 0; i < 8; i++) D[12 + lane][i] = h[i];
+        }
+        __syncwarp();
+        const uint32_t p0 = (uint32_t)(idx >> l) & 7u;
+        const uint4* s0 = reinterpret_cast<const uint4*>(D[p0 ^ 1]);
+        const uint4* s1 = reinterpret_cast<const uint4*>(D[8 + ((p0 >> 1) ^ 1)]);
+        const uint4* s2 = reinterpret_cast<const uint4*>(D[12 + ((p0 >> 2) ^ 1)]);
+        if (lane < 4) {
+            out[l * 4 + lane] = s0[lane];
+            out[(l + 1) * 4 + lane] = s1[lane];
+            out[(l + 2) * 4 + lane] = s2[lane];
+        }
+        __syncwarp();
+        l += 3;
     }
 }
 
-static int launch_small(zkb_ctx* c, const SmallArgs& a) {
+static int launch_top(zkb_ctx* c, const TopArgs& a) {
     static bool attr_set = false;
     if (!attr_set) {
-        ZKB_CUDA(c, cudaFuncSetAttribute(k_small, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+        ZKB_CUDA(c, cudaFuncSetAttribute(k_top, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
         attr_set = true;
     }
-    { LaunchScope ls(c, K_MERKLE_SMALL); k_small<<<1, 256, 96 * 1024, c->stream>>>(a); }
+    { LaunchScope ls(c, K_MERKLE_SMALL); k_top<<<1, ZKB_TOP_THREADS, 96 * 1024, c->stream>>>(a); }
     ZKB_CUDA(c, cudaGetLastError());
     return 0;
 }
@@ -286,47 +286,50 @@ static int launch_small(zkb_ctx* c, const SmallArgs& a) {
 int merkle_build_levels(zkb_ctx* c, const fe* vals, const FoldArgs* fold, uint64_t n,
                         const TreeLayout& L, uint8_t* nodes) {
     const uint32_t log_n = L.log_n;
-    if (L.cut == 0) {
-        // small tree: values must already exist (the caller folds separately for small layers)
-        if (fold) return set_err(c, ZKB_ERR_ARG, "internal: fused fold needs n > 1024");
-        SmallArgs a;
-        memset(&a, 0, sizeof(a));
+    TopArgs a;
+    memset(&a, 0, sizeof(a));
+    if (L.top == 0) {                                   // n <= 1024: one CTA does everything
         a.vals = vals; a.count = (uint32_t)n;
+        if (fold) { a.fold = 1; a.f = *fold; }
         for (uint32_t l = 0; l <= log_n; l++) a.level_out[l] = nodes + L.level_off[l] * 64;
-        return launch_small(c, a);
+        return launch_top(c, a);
     }
-    uint8_t* lvl5 = nodes + L.level_off[5] * 64;
-    if (fold) {
-        LaunchScope ls(c, K_FOLD_LEAF_TILE);
-        k_leaf_tile<true><<<(unsigned)(n >> 10), 256, 0, c->stream>>>(nullptr, *fold, lvl5);
-    } else {
-        FoldArgs dummy;
-        memset(&dummy, 0, sizeof(dummy));
-        LaunchScope ls(c, K_LEAF_TILE);
-        k_leaf_tile<false><<<(unsigned)(n >> 10), 256, 0, c->stream>>>(vals, dummy, lvl5);
+    const uint64_t groups = n >> 3;
+    uint8_t* lvl3 = nodes + L.level_off[3] * 64;
+    static int cfg = -1;                      // tuning knob (ZKB_LEAF_CFG): threads x min resident CTAs
+    if (cfg < 0) { const char* e = getenv("ZKB_LEAF_CFG"); cfg = e ? atoi(e) : 0; }
+    FoldArgs fa;
+    if (fold) fa = *fold; else memset(&fa, 0, sizeof(fa));
+    {
+        LaunchScope ls(c, fold ? K_FOLD_LEAF_TILE : K_LEAF_TILE);
+#define ZKB_LEAF_LAUNCH(T, M)                                                                                   \
+        do {                                                                                                    \
+            const unsigned blocks = (unsigned)((groups + (T) - 1) / (T));                                       \
+            if (fold) k_leaf8<true, T, M><<<blocks, T, 0, c->stream>>>(nullptr, fa, groups, lvl3);               \
+            else k_leaf8<false, T, M><<<blocks, T, 0, c->stream>>>(vals, fa, groups, lvl3);                      \
+        } while (0)
+        if (cfg == 1) ZKB_LEAF_LAUNCH(256, 3);
+        else if (cfg == 2) ZKB_LEAF_LAUNCH(128, 4);
+        else if (cfg == 3) ZKB_LEAF_LAUNCH(128, 6);
+        else if (cfg == 4) ZKB_LEAF_LAUNCH(64, 8);
+        else ZKB_LEAF_LAUNCH(256, 2);
     }
     ZKB_CUDA(c, cudaGetLastError());
-    uint32_t level = 5;
-    uint64_t m = n >> 5;
-    while (m > 1024) {
-        const uint8_t* in = nodes + L.level_off[level] * 64;
+    uint32_t level = 3;
+    while (level < L.top) {
+        const uint64_t g = n >> (level + 3);
         {
             LaunchScope ls(c, K_NODE_TILE);
-            k_node_tile<<<(unsigned)(m >> 10), 256, 0, c->stream>>>(in,
-                nodes + L.level_off[level + 1] * 64, nodes + L.level_off[level + 2] * 64,
-                nodes + L.level_off[level + 3] * 64, nodes + L.level_off[level + 4] * 64,
-                nodes + L.level_off[level + 5] * 64);
+            if (g >= (1u << 17)) k_node8<256, 2><<<(unsigned)((g + 255) / 256), 256, 0, c->stream>>>(nodes + L.level_off[level] * 64, g, nodes + L.level_off[level + 3] * 64);
+            else k_node8<64, 8><<<(unsigned)((g + 63) / 64), 64, 0, c->stream>>>(nodes + L.level_off[level] * 64, g, nodes + L.level_off[level + 3] * 64);
         }
         ZKB_CUDA(c, cudaGetLastError());
-        level += 5;
-        m >>= 5;
+        level += 3;
     }
-    SmallArgs a;
-    memset(&a, 0, sizeof(a));
     a.nodes_in = nodes + L.level_off[level] * 64;
-    a.count = (uint32_t)m;
+    a.count = (uint32_t)(n >> level);
     for (uint32_t r = 1; level + r <= log_n; r++) a.level_out[r] = nodes + L.level_off[level + r] * 64;
-    if (m > 1) ZKB_TRY(launch_small(c, a));
+    if (a.count > 1) ZKB_TRY(launch_top(c, a));
     return 0;
 }
 

@@ -5,14 +5,17 @@
 namespace zkb {
 
 // Layout of a retained tree.  Levels are counted from the leaves: level 0 = leaf hashes
-// (n nodes), level log_n = the root.  Only levels >= cut are stored (cut = 5 for trees of
-// more than 1024 leaves: 4n bytes instead of 128n); the bottom `cut` levels of an
-// authentication path are recomputed at opening time from the 32 leaves around the
-// index, which the tree can always reach (it references the committed values).
+// (n nodes), level log_n = the root.  Trees of <= 1024 leaves store every level.  Larger
+// trees store level 3, 6, 9, ... (what the per-thread 8-ary subtree kernels emit) down to the
+// first level `top` with <= 1024 nodes, and every level above `top` (9.2n bytes instead of
+// 128n).  The two unstored levels inside each group of three - and the leaf hashes - of an
+// authentication path are recomputed at opening time from the 8 group inputs, which the tree
+// can always reach (it references the committed values).
 struct TreeLayout {
     uint32_t log_n = 0;
-    uint32_t cut = 0;
-    uint64_t level_off[41];      // node index (64-byte units) of level l inside `nodes`
+    uint32_t top = 0;            // first level handled by the single-CTA top kernel (0 for small trees)
+    uint8_t stored[41];
+    uint64_t level_off[41];      // node index (64-byte units) of level l inside `nodes` (stored levels only)
     uint64_t total_nodes = 0;
     void init(uint32_t log_n_);
 };
@@ -29,7 +32,7 @@ struct FoldArgs {
 };
 
 // Build every stored level of the tree over `n` = 2^log_n values.  If `fold` is non-null
-// the values are produced on the fly by folding fold->cw (and written to fold->next),
+// the values are produced on the fly by folding fold->cw (and written to fold->next; any n),
 // otherwise they are read from `vals`.  `nodes` must hold layout.total_nodes * 64 bytes.
 int merkle_build_levels(zkb_ctx* c, const fe* vals, const FoldArgs* fold, uint64_t n,
                         const TreeLayout& layout, uint8_t* nodes);

@@ -163,6 +163,59 @@ static int run_r(int device, double* rate, double* ms_out) {
     return 0;
 }
 
+// IMAD.WIDE rate: 8 independent 64-bit accumulators, acc = a * b + acc (kind 40: b register,
+// kind 41: b = kernel-parameter constant 2^8, the shape the rotate-by-multiply trick needs).
+template <int KIND>
+__global__ void __launch_bounds__(256) k_probe_wide(unsigned long long* out, uint32_t ub, int iters) {
+    unsigned long long acc[CH];
+    uint32_t a[CH], b[CH];
+#pragma unroll
+    for (int i = 0; i < CH; i++) {
+        a[i] = threadIdx.x * 2654435761u + i * 40503u + blockIdx.x;
+        b[i] = a[i] * 0x9E3779B9u + 12345u;
+        acc[i] = ((unsigned long long)a[i] << 32) | b[i];
+    }
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int u = 0; u < UNROLL; u++) {
+#pragma unroll
+            for (int i = 0; i < CH; i++) {
+                const int j = (i + 1 + (u & 3)) % CH;
+                if (KIND == 40) asm volatile("{ .reg .u32 lo; cvt.u32.u64 lo, %0; mad.wide.u32 %0, lo, %1, %0; }" : "+l"(acc[i]) : "r"(b[j]));
+                else asm volatile("{ .reg .u32 lo; cvt.u32.u64 lo, %0; mad.wide.u32 %0, lo, %1, %0; }" : "+l"(acc[i]) : "r"(ub));
+            }
+        }
+    }
+    unsigned long long x = 0;
+#pragma unroll
+    for (int i = 0; i < CH; i++) x ^= acc[i];
+    if (x == 0x12345678ull) out[0] = x;
+}
+template <int KIND>
+static int run_wide(int device, double* rate, double* ms_out) {
+    int sms = 0;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    unsigned long long* d = nullptr;
+    if (cudaMalloc(&d, 64) != cudaSuccess) return -1;
+    const int iters = 1024, blocks = sms * 8;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    float best = 1e30f;
+    for (int rep = 0; rep < 4; rep++) {
+        cudaEventRecord(e0);
+        k_probe_wide<KIND><<<blocks, 256>>>(d, 256u, iters);
+        cudaEventRecord(e1);
+        if (cudaEventSynchronize(e1) != cudaSuccess) { cudaFree(d); return -1; }
+        float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
+        if (rep > 0 && ms < best) best = ms;
+    }
+    *rate = (double)iters * UNROLL * CH * blocks * 256 / (best * 1e-3);
+    if (ms_out) *ms_out = best;
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaFree(d);
+    return 0;
+}
+
 struct KParams { uint32_t k[4]; };
 template <int CFG>
 __global__ void __launch_bounds__(256, 2) k_probe_blakex(uint64_t* out, int iters, KParams kp) {
@@ -287,6 +340,8 @@ extern "C" int zkb_probe_int_pipe(int device, int kind, double* lane_ops_per_s, 
         case 31: return run_r<31>(device, lane_ops_per_s, ms_out);
         case 32: return run_r<32>(device, lane_ops_per_s, ms_out);
         case 33: return run_r<33>(device, lane_ops_per_s, ms_out);
+        case 40: return run_wide<40>(device, lane_ops_per_s, ms_out);
+        case 41: return run_wide<41>(device, lane_ops_per_s, ms_out);
         default: break;
     }
     int sms = 0;
