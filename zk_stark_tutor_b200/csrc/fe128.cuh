@@ -135,7 +135,83 @@ ZKB_HD fe fe_half(const fe& a) {
 
 // Montgomery product a*b*2^-128 mod p.  Needs a*b < p*2^128 (true when either operand
 // is canonical); result canonical.
+#if defined(__CUDA_ARCH__)
+// Device version in PTX.  The 4x4 product is accumulated in two interleaved 8-limb accumulators
+// ("even" holds a_i*b_j with i+j even at limb i+j, "odd" those with i+j odd) so that every
+// 32x32->64 product lands on a fixed, aligned register pair and maps to one IMAD.WIDE with
+// carry-out, rows chained by carry; the two are merged with one 7-limb add.  The reduction
+// uses p = 1 (mod 2^96): m = -T mod 2^96 clears three limbs with three products m_i*P3, a
+// fourth clears limb 3; one conditional subtraction makes the result canonical.
+__device__ __forceinline__ fe fe_montmul_ptx(const fe& a, const fe& b) {
+    fe r;
+    asm("{\n\t"
+        ".reg .u32 e0,e1,e2,e3,e4,e5,e6,e7,o0,o1,o2,o3,o4,o5,o6;\n\t"
+        ".reg .u32 t1,t2,t3,t4,t5,t6,t7,m0,m1,m2,m3,nz,c3,u3,u4,u5,u6,u7,u8;\n\t"
+        ".reg .u32 q0l,q0h,q1l,q1h,q2l,q2h,q3l,q3h,r0,r1,r2,r3,top,d0,d1,d2,d3,k;\n\t"
+        ".reg .pred keep;\n\t"
+        ".reg .u64 w0,w1,w2,w3;\n\t"
+        // ---- even accumulator: row b0
+        "mul.wide.u32 w0, %4, %8;\n\t" "mov.b64 {e0,e1}, w0;\n\t"
+        "mul.wide.u32 w1, %6, %8;\n\t" "mov.b64 {e2,e3}, w1;\n\t"
+        // odd accumulator: row b0 (a1*b0 at limb 1, a3*b0 at limb 3)
+        "mul.wide.u32 w2, %5, %8;\n\t" "mov.b64 {o0,o1}, w2;\n\t"
+        "mul.wide.u32 w3, %7, %8;\n\t" "mov.b64 {o2,o3}, w3;\n\t"
+        // ---- row b1: odd += a0*b1 (limb 1), a2*b1 (limb 3); even += a1*b1 (limb 2), a3*b1 (limb 4)
+        "mad.lo.cc.u32 o0, %4, %9, o0;\n\t"  "madc.hi.cc.u32 o1, %4, %9, o1;\n\t"
+        "madc.lo.cc.u32 o2, %6, %9, o2;\n\t" "madc.hi.cc.u32 o3, %6, %9, o3;\n\t"
+        "addc.u32 o4, 0, 0;\n\t"
+        "mad.lo.cc.u32 e2, %5, %9, e2;\n\t"  "madc.hi.cc.u32 e3, %5, %9, e3;\n\t"
+        "madc.lo.cc.u32 e4, %7, %9, 0;\n\t"  "madc.hi.cc.u32 e5, %7, %9, 0;\n\t"
+        "addc.u32 e6, 0, 0;\n\t"
+        // ---- row b2: even += a0*b2 (limb 2), a2*b2 (limb 4); odd += a1*b2 (limb 3), a3*b2 (limb 5)
+        "mad.lo.cc.u32 e2, %4, %10, e2;\n\t" "madc.hi.cc.u32 e3, %4, %10, e3;\n\t"
+        "madc.lo.cc.u32 e4, %6, %10, e4;\n\t" "madc.hi.cc.u32 e5, %6, %10, e5;\n\t"
+        "addc.u32 e6, e6, 0;\n\t"
+        "mad.lo.cc.u32 o2, %5, %10, o2;\n\t" "madc.hi.cc.u32 o3, %5, %10, o3;\n\t"
+        "madc.lo.cc.u32 o4, %7, %10, o4;\n\t" "madc.hi.cc.u32 o5, %7, %10, 0;\n\t"
+        "addc.u32 o6, 0, 0;\n\t"
+        // ---- row b3: odd += a0*b3 (limb 3), a2*b3 (limb 5); even += a1*b3 (limb 4), a3*b3 (limb 6)
+        "mad.lo.cc.u32 o2, %4, %11, o2;\n\t" "madc.hi.cc.u32 o3, %4, %11, o3;\n\t"
+        "madc.lo.cc.u32 o4, %6, %11, o4;\n\t" "madc.hi.cc.u32 o5, %6, %11, o5;\n\t"
+        "addc.u32 o6, o6, 0;\n\t"
+        "mad.lo.cc.u32 e4, %5, %11, e4;\n\t" "madc.hi.cc.u32 e5, %5, %11, e5;\n\t"
+        "madc.lo.cc.u32 e6, %7, %11, e6;\n\t" "madc.hi.u32 e7, %7, %11, 0;\n\t"
+        // ---- merge: T = even + (odd << 32); T0 = e0
+        "add.cc.u32 t1, e1, o0;\n\t"  "addc.cc.u32 t2, e2, o1;\n\t" "addc.cc.u32 t3, e3, o2;\n\t"
+        "addc.cc.u32 t4, e4, o3;\n\t" "addc.cc.u32 t5, e5, o4;\n\t" "addc.cc.u32 t6, e6, o5;\n\t"
+        "addc.u32 t7, e7, o6;\n\t"
+        // ---- m = -T mod 2^96 ; nz = (T mod 2^96 != 0)
+        "sub.cc.u32 m0, 0, e0;\n\t" "subc.cc.u32 m1, 0, t1;\n\t" "subc.cc.u32 m2, 0, t2;\n\t"
+        "subc.u32 nz, 0, 0;\n\t"    "and.b32 nz, nz, 1;\n\t"
+        "mul.wide.u32 w0, m0, 0xCB800000;\n\t" "mov.b64 {q0l,q0h}, w0;\n\t"
+        "mul.wide.u32 w1, m1, 0xCB800000;\n\t" "mov.b64 {q1l,q1h}, w1;\n\t"
+        "mul.wide.u32 w2, m2, 0xCB800000;\n\t" "mov.b64 {q2l,q2h}, w2;\n\t"
+        // U = T[3..7] + nz + (m * P3) : two carry chains
+        "add.cc.u32 u3, t3, q0l;\n\t"  "addc.cc.u32 u4, t4, q0h;\n\t" "addc.cc.u32 u5, t5, q1h;\n\t"
+        "addc.cc.u32 u6, t6, q2h;\n\t" "addc.cc.u32 u7, t7, 0;\n\t"   "addc.u32 u8, 0, 0;\n\t"
+        "add.cc.u32 u3, u3, nz;\n\t"   "addc.cc.u32 u4, u4, q1l;\n\t" "addc.cc.u32 u5, u5, q2l;\n\t"
+        "addc.cc.u32 u6, u6, 0;\n\t"   "addc.cc.u32 u7, u7, 0;\n\t"   "addc.u32 u8, u8, 0;\n\t"
+        // ---- clear limb 3: m3 = -u3, carry c3 = (u3 != 0), m3*P3 lands on limbs 6,7
+        "sub.cc.u32 m3, 0, u3;\n\t" "subc.u32 c3, 0, 0;\n\t" "and.b32 c3, c3, 1;\n\t"
+        "mul.wide.u32 w3, m3, 0xCB800000;\n\t" "mov.b64 {q3l,q3h}, w3;\n\t"
+        "add.cc.u32 r0, u4, c3;\n\t"  "addc.cc.u32 r1, u5, 0;\n\t" "addc.cc.u32 r2, u6, q3l;\n\t"
+        "addc.cc.u32 r3, u7, q3h;\n\t" "addc.u32 top, u8, 0;\n\t"
+        // ---- conditional subtraction of p = {1, 0, 0, P3}: keep r iff (top:r) < p
+        "sub.cc.u32 d0, r0, 1;\n\t" "subc.cc.u32 d1, r1, 0;\n\t" "subc.cc.u32 d2, r2, 0;\n\t"
+        "subc.cc.u32 d3, r3, 0xCB800000;\n\t" "subc.u32 k, top, 0;\n\t"
+        "setp.ne.u32 keep, k, 0;\n\t"
+        "selp.u32 %0, r0, d0, keep;\n\t" "selp.u32 %1, r1, d1, keep;\n\t"
+        "selp.u32 %2, r2, d2, keep;\n\t" "selp.u32 %3, r3, d3, keep;\n\t"
+        "}"
+        : "=r"(r.v[0]), "=r"(r.v[1]), "=r"(r.v[2]), "=r"(r.v[3])
+        : "r"(a.v[0]), "r"(a.v[1]), "r"(a.v[2]), "r"(a.v[3]), "r"(b.v[0]), "r"(b.v[1]), "r"(b.v[2]), "r"(b.v[3]));
+    return r;
+}
+#endif
 ZKB_HD fe fe_montmul(const fe& a, const fe& b) {
+#if defined(__CUDA_ARCH__)
+    return fe_montmul_ptx(a, b);
+#else
     uint32_t t[9];
     // ---- 4x4 schoolbook product, row by row with 64-bit accumulation
     uint64_t acc;
@@ -186,6 +262,7 @@ ZKB_HD fe fe_montmul(const fe& a, const fe& b) {
     r.v[2] = take ? d2 : r.v[2];
     r.v[3] = take ? d3 : r.v[3];
     return r;
+#endif
 }
 
 ZKB_HD fe fe_mont_one() { fe r = ZKB_FE_R; return r; }

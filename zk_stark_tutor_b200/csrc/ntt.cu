@@ -156,6 +156,136 @@ __global__ void __launch_bounds__(ZKB_NTT_THREADS) k_ntt_pass(const PassParams p
     }
 }
 
+
+// ---- register-radix pass ------------------------------------------------------------------
+// The same tile (S x B values) as k_ntt_pass, but the S = R1*R2-point transform of each column is
+// done as two in-register radix-R passes (R <= 16, fully unrolled DIF, bit reversal = register
+// renaming) around ONE shared-memory exchange instead of log2(S) shared-memory stages:
+//   step 1: thread (s0, b) loads x[R2*s1 + s0], s1 < R1, straight from HBM, R1-point DFT,
+//           multiplies by w_S^(s0*ka), writes Y[ka][s0][b] to shared memory
+//   step 3: thread (ka, b) reads Y[ka][s0][b], s0 < R2, R2-point DFT -> X[ka + R1*kb], applies the
+//           inter-pass twiddle (running product over kb) / n^-1 and stores to HBM.
+// Trivial twiddles (w^0) cost nothing: 17 multiplications per 16-point DFT instead of 32.
+template <int LOGR>
+__device__ __forceinline__ void dft_dif(fe (&x)[1 << LOGR], const fe* __restrict__ tw, uint32_t tw_stride) {
+    constexpr int R = 1 << LOGR;
+#pragma unroll
+    for (int lh = LOGR - 1; lh >= 0; lh--) {
+        const int h = 1 << lh;
+#pragma unroll
+        for (int i = 0; i < R / 2; i++) {
+            const int j = i & (h - 1);
+            const int s0 = ((i >> lh) << (lh + 1)) | j;
+            fe u = x[s0], v = x[s0 + h];
+            x[s0] = fe_add(u, v);
+            fe d = fe_sub(u, v);
+            x[s0 + h] = (j == 0) ? d : fe_montmul(d, tw[(uint32_t)(j << (LOGR - 1 - lh)) * tw_stride]);
+        }
+    }
+}
+template <int LOGR> __host__ __device__ constexpr int brev_c(int i) {
+    int r = 0;
+    for (int k = 0; k < LOGR; k++) r |= ((i >> k) & 1) << (LOGR - 1 - k);
+    return r;
+}
+
+template <int LR1, int LR2, bool TRANSPOSED>
+__global__ void __launch_bounds__(ZKB_NTT_THREADS, 2) k_ntt_rr(const PassParams p) {
+    extern __shared__ uint4 smem_raw[];
+    constexpr uint32_t R1 = 1u << LR1, R2 = 1u << LR2, S = R1 * R2;
+    fe* sm = reinterpret_cast<fe*>(smem_raw);
+    const uint32_t B = 1u << p.log_b, pitch = B + 1;
+    fe* tws = sm + (size_t)S * pitch;                      // w_S^j * R, j < S
+    const uint32_t tid = threadIdx.x;
+    const uint32_t outer = blockIdx.x / p.inner_count, inner = blockIdx.x % p.inner_count;
+    const uint64_t in_base = (uint64_t)outer * p.ld_outer + (uint64_t)inner * p.ld_inner;
+    const fe* in = p.in + (uint64_t)blockIdx.y * p.in_batch;
+    fe* out = p.out + (uint64_t)blockIdx.y * p.out_batch + (uint64_t)outer * p.st_outer + (uint64_t)inner * p.st_inner;
+    for (uint32_t j = tid; j < S; j += ZKB_NTT_THREADS) tws[j] = fe_ldg(p.tw_s + j);
+    __syncthreads();
+    // ---- step 1
+    for (uint32_t d = tid; d < R2 * B; d += ZKB_NTT_THREADS) {
+        const uint32_t s0 = TRANSPOSED ? (d & (R2 - 1)) : (d >> p.log_b);
+        const uint32_t b = TRANSPOSED ? (d >> LR2) : (d & (B - 1));
+        fe x[R1];
+#pragma unroll
+        for (uint32_t s1 = 0; s1 < R1; s1++) {
+            const uint64_t lin = in_base + (uint64_t)(R2 * s1 + s0) * p.ld_s + (uint64_t)b * p.ld_b;
+            x[s1] = fe_zero();
+            if (!p.has_valid || lin < p.n_valid) {
+                x[s1] = fe_ldg(in + lin);
+                if (p.has_scale) x[s1] = fe_montmul(x[s1], pow2lvl(p.sc, lin));
+            }
+        }
+        dft_dif<LR1>(x, tws, R2);
+#pragma unroll
+        for (uint32_t i = 0; i < R1; i++) {
+            const uint32_t ka = brev_c<LR1>(i);
+            fe y = x[i];
+            const uint32_t e = s0 * ka;                    // < S
+            if (ka != 0 && s0 != 0) y = fe_montmul(y, tws[e]);
+            sm[(size_t)(ka * R2 + s0) * pitch + b] = y;
+        }
+    }
+    __syncthreads();
+    // ---- step 3
+    for (uint32_t d = tid; d < R1 * B; d += ZKB_NTT_THREADS) {
+        const uint32_t ka = d >> p.log_b, b = d & (B - 1);
+        fe x[R2];
+#pragma unroll
+        for (uint32_t s0 = 0; s0 < R2; s0++) x[s0] = sm[(size_t)(ka * R2 + s0) * pitch + b];
+        dft_dif<LR2>(x, tws, R1);
+        fe t, step;
+        if (p.has_tw) {
+            const uint64_t col = (uint64_t)inner * B + b;
+            t = pow2lvl(p.tw, (uint64_t)ka * col * p.tw_mul);
+            step = pow2lvl(p.tw, (uint64_t)R1 * col * p.tw_mul);
+        }
+#pragma unroll
+        for (uint32_t kb = 0; kb < R2; kb++) {
+            fe y = x[brev_c<LR2>(kb)];
+            if (p.has_tw) {
+                y = fe_montmul(y, t);
+                if (kb + 1 < R2) t = fe_montmul(t, step);
+            }
+            if (p.has_post) y = fe_montmul(y, p.post);
+            fe_store(out + (uint64_t)(ka + R1 * kb) * p.st_k + (uint64_t)b * p.st_b, y);
+        }
+    }
+}
+
+template <int LR1, int LR2>
+static int launch_rr_t(zkb_ctx* c, const PassParams& p, uint32_t tiles, uint32_t batch) {
+    const size_t S = (size_t)1 << (LR1 + LR2), B = (size_t)1 << p.log_b;
+    const size_t smem = (S * (B + 1) + S) * sizeof(fe);
+    dim3 grid(tiles, batch);
+    LaunchScope ls(c, K_NTT_PASS);
+    if (p.transposed) {
+        static bool set_t = false;
+        if (!set_t) { ZKB_CUDA(c, cudaFuncSetAttribute(k_ntt_rr<LR1, LR2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)); set_t = true; }
+        k_ntt_rr<LR1, LR2, true><<<grid, ZKB_NTT_THREADS, smem, c->stream>>>(p);
+    } else {
+        static bool set_n = false;
+        if (!set_n) { ZKB_CUDA(c, cudaFuncSetAttribute(k_ntt_rr<LR1, LR2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)); set_n = true; }
+        k_ntt_rr<LR1, LR2, false><<<grid, ZKB_NTT_THREADS, smem, c->stream>>>(p);
+    }
+    return 0;
+}
+// register-radix pass for log_s in 5..8
+static int launch_pass_rr(zkb_ctx* c, const PassParams& p, uint32_t tiles, uint32_t batch) {
+    int rc;
+    switch (p.log_s) {
+        case 8: rc = launch_rr_t<4, 4>(c, p, tiles, batch); break;
+        case 7: rc = launch_rr_t<4, 3>(c, p, tiles, batch); break;
+        case 6: rc = launch_rr_t<3, 3>(c, p, tiles, batch); break;
+        case 5: rc = launch_rr_t<3, 2>(c, p, tiles, batch); break;
+        default: return set_err(c, ZKB_ERR_ARG, "internal: register-radix pass needs 5 <= log_s <= 8");
+    }
+    ZKB_TRY(rc);
+    ZKB_CUDA(c, cudaGetLastError());
+    return 0;
+}
+
 static size_t pass_smem_bytes(const PassParams& p) {
     size_t S = (size_t)1 << p.log_s, B = (size_t)1 << p.log_b;
     return ((p.transposed ? B * (S + 1) : S * B) + S / 2) * sizeof(fe);
@@ -209,9 +339,25 @@ int ntt_exec(zkb_ctx* c, fe root, const fe* d_in, size_t n_in, size_t in_stride,
 
     uint32_t a, b2 = 0, c3;
     int passes;
+    // 2^13..2^24: every pass is 5..8 bits wide and runs in the register-radix kernel
+    const bool fast = log_n > TILE_LOG && log_n <= 24;
     if (log_n <= TILE_LOG) { passes = 1; a = 0; c3 = log_n; }
+    else if (log_n <= 16) { passes = 2; a = (log_n + 1) / 2; c3 = log_n - a; }
+    else if (fast) { passes = 3; a = (log_n + 2) / 3; b2 = (log_n - a + 1) / 2; c3 = log_n - a - b2; }
     else if (log_n <= 20) { passes = 2; a = (log_n + 1) / 2; c3 = log_n - a; }
     else { passes = 3; a = (log_n + 2) / 3; b2 = (log_n - a + 1) / 2; c3 = log_n - a - b2; }
+    auto tw_table = [&](uint32_t log_s, const fe** out) -> int {
+        if (!fast) return tw_s_table(c, root, log_n, log_s, out);
+        fe ws = root;                                        // full table w_S^j * R, j < S
+        for (uint32_t i = 0; i < log_n - log_s; i++) ws = h_mul(ws, ws);
+        DevPow t;
+        ZKB_TRY(get_pow_table(c, ws, log_s, &t));
+        *out = t.lo;
+        return 0;
+    };
+    auto launch = [&](const PassParams& p, uint32_t tiles) -> int {
+        return fast ? launch_pass_rr(c, p, tiles, (uint32_t)batch) : launch_pass(c, p, tiles, (uint32_t)batch);
+    };
     const uint64_t N1 = 1ull << a, N2 = 1ull << b2, N3 = 1ull << c3, M = N2 * N3;
 
     if (passes == 1) {
@@ -253,8 +399,8 @@ int ntt_exec(zkb_ctx* c, fe root, const fe* d_in, size_t n_in, size_t in_stride,
         p.skip_log = a - rl;
         p.has_tw = 1; p.tw = tw; p.tw_mul = 1;
         p.has_scale = o.has_scale; p.sc = sc;
-        ZKB_TRY(tw_s_table(c, root, log_n, a, &p.tw_s));
-        ZKB_TRY(launch_pass(c, p, p.inner_count, (uint32_t)batch));
+        ZKB_TRY(tw_table(a, &p.tw_s));
+        ZKB_TRY(launch(p, p.inner_count));
     }
     if (passes == 3) {   // pass 2: N2-point transforms inside each row k1 (stride N3), in place
         PassParams p = base;
@@ -269,8 +415,8 @@ int ntt_exec(zkb_ctx* c, fe root, const fe* d_in, size_t n_in, size_t in_stride,
         p.st_k = N3; p.st_b = 1; p.st_outer = M; p.st_inner = 1ull << lb;
         p.in_batch = N; p.out_batch = N;
         p.has_tw = 1; p.tw = tw; p.tw_mul = N1;
-        ZKB_TRY(tw_s_table(c, root, log_n, b2, &p.tw_s));
-        ZKB_TRY(launch_pass(c, p, (uint32_t)(N1 * p.inner_count), (uint32_t)batch));
+        ZKB_TRY(tw_table(b2, &p.tw_s));
+        ZKB_TRY(launch(p, (uint32_t)(N1 * p.inner_count)));
     }
     {   // final pass: N3-point transforms along contiguous runs, transposing store
         PassParams p = base;
@@ -283,8 +429,8 @@ int ntt_exec(zkb_ctx* c, fe root, const fe* d_in, size_t n_in, size_t in_stride,
         p.ld_s = 1; p.ld_b = M; p.ld_outer = N3; p.ld_inner = (1ull << lb) * M;
         p.st_k = N1 * N2; p.st_b = 1; p.st_outer = N1; p.st_inner = 1ull << lb;
         p.in_batch = N; p.out_batch = out_stride;
-        ZKB_TRY(tw_s_table(c, root, log_n, c3, &p.tw_s));
-        ZKB_TRY(launch_pass(c, p, (uint32_t)(N2 * p.inner_count), (uint32_t)batch));
+        ZKB_TRY(tw_table(c3, &p.tw_s));
+        ZKB_TRY(launch(p, (uint32_t)(N2 * p.inner_count)));
     }
     return 0;
 }
