@@ -187,7 +187,8 @@ def b200_arm(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream()                 # one explicit stream: library kernels, L2 flush and timing events
+    torch.cuda.set_stream(stream)
     ctx = zk.Context(local, stream=stream.cuda_stream)
     columns_mode = args.workload == "columns"
     if columns_mode and args.log_n == 24:

@@ -50,8 +50,9 @@ typedef struct zkb_fri_layers zkb_fri_layers;
 typedef struct zkb_ps zkb_ps;
 
 /* ---- context ------------------------------------------------------------------------ */
-/* One context per GPU.  `stream` = a cudaStream_t to run on (e.g. torch's current stream),
- * or NULL to let the context create its own non-blocking stream. */
+/* One context per GPU.  `stream` = a cudaStream_t to run on (e.g. torch's current stream; pass
+ * cudaStreamLegacy = (void*)1 for the legacy default stream), or NULL to let the context create
+ * its own non-blocking stream. */
 int zkb_ctx_create(int device, void* stream, zkb_ctx** out);
 void zkb_ctx_destroy(zkb_ctx* ctx);
 const char* zkb_last_error(const zkb_ctx* ctx);
@@ -88,6 +89,12 @@ int zkb_intt(zkb_ctx* ctx, const uint8_t root[16], const void* in, size_t n_in, 
  * elements / out + c*out_stride elements (trace columns). */
 int zkb_ntt_batch(zkb_ctx* ctx, const uint8_t root[16], int inverse, const void* in, size_t n_in,
                   size_t in_stride, void* out, size_t out_stride, size_t batch);
+
+/* `count` interleaved transforms of length n (power of two <= 4096): element j of sequence q is
+ * in[j*stride + q]; same layout out; DEVICE pointers.  The cross-GPU stage of the four-step NTT
+ * (n = number of GPUs, after the all-to-all). */
+int zkb_ntt_strided(zkb_ctx* ctx, const uint8_t root[16], int inverse, const void* in, size_t n, size_t stride,
+                    size_t count, void* out);
 
 /* ---- polynomial helpers : src/field/polynomial.rs, src/fft/ntt_arithmetics.rs --------- */
 /* Polynomial::scale polynomial.rs:109-121: out[i] = factor^i * coeffs[i] */

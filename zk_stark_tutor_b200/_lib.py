@@ -46,6 +46,7 @@ PROTOTYPES = {
     "zkb_ntt": (ctypes.c_int, [vp, c_u8p, vp, sz, vp]),
     "zkb_intt": (ctypes.c_int, [vp, c_u8p, vp, sz, vp]),
     "zkb_ntt_batch": (ctypes.c_int, [vp, c_u8p, ctypes.c_int, vp, sz, sz, vp, sz, sz]),
+    "zkb_ntt_strided": (ctypes.c_int, [vp, c_u8p, ctypes.c_int, vp, sz, sz, sz, vp]),
     "zkb_poly_scale": (ctypes.c_int, [vp, c_u8p, vp, sz, vp]),
     "zkb_coset_lde": (ctypes.c_int, [vp, c_u8p, u64, c_u8p, vp, sz, vp]),
     "zkb_coset_lde_batch": (ctypes.c_int, [vp, c_u8p, u64, c_u8p, vp, sz, sz, vp, sz, sz]),

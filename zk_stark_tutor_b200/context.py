@@ -80,12 +80,26 @@ class Vec:
 
 
 class Context:
-    """One per GPU (zkb_ctx).  `stream`: a raw cudaStream_t (e.g.
-    torch.cuda.current_stream().cuda_stream); None = the library's own stream."""
+    """One per GPU (zkb_ctx).  `stream`: a raw cudaStream_t; "torch" (default) = torch's current
+    stream on that device, so calls on CUDA tensors are ordered with the caller's torch work;
+    "own" = a private non-blocking stream (the caller must ctx.sync() before touching results
+    from another stream)."""
 
-    def __init__(self, device=0, stream=None):
+    def __init__(self, device=0, stream="torch"):
         self.lib = _lib.lib()
         self.device = device
+        if stream == "torch":
+            stream = None
+            try:
+                import torch
+                if torch.cuda.is_available():
+                    # torch's default stream is the legacy NULL stream: its explicit handle is
+                    # cudaStreamLegacy (0x1); a NULL argument would mean "create a private stream"
+                    stream = torch.cuda.current_stream(device).cuda_stream or 1
+            except ImportError:
+                pass
+        elif stream == "own":
+            stream = None
         h = ctypes.c_void_p()
         rc = self.lib.zkb_ctx_create(device, ctypes.c_void_p(stream) if stream else None, ctypes.byref(h))
         if rc != 0 or not h.value:

@@ -516,6 +516,50 @@ int zkb_ntt_batch(zkb_ctx* c, const uint8_t root[16], int inverse, const void* i
     return 0;
 }
 
+// `count` interleaved transforms of length n (power of two, <= 4096): element j of sequence q is
+// in[j * stride + q] (stride >= count).  Same layout out.  This is the cross-GPU stage of the
+// four-step NTT (n = number of GPUs) and runs as one strided tile pass.
+int zkb_ntt_strided(zkb_ctx* c, const uint8_t root[16], int inverse, const void* in, size_t n, size_t stride,
+                    size_t count, void* out) {
+    if (!c || !root || !in || !out) return ZKB_ERR_ARG;
+    if (n == 0 || (n & (n - 1)) || n > (1u << TILE_LOG)) return set_err(c, ZKB_ERR_ARG, "ntt_strided: length %zu must be a power of two <= 4096", n);
+    if (stride < count) return set_err(c, ZKB_ERR_ARG, "ntt_strided: stride shorter than the sequence count");
+    if (!is_device_ptr(in) || !is_device_ptr(out)) return set_err(c, ZKB_ERR_ARG, "ntt_strided takes device pointers");
+    if (count == 0) return 0;
+    ZKB_CUDA(c, cudaSetDevice(c->device));
+    if (n == 1) {
+        if (in != out) ZKB_CUDA(c, cudaMemcpyAsync(out, in, count * sizeof(fe), cudaMemcpyDeviceToDevice, c->stream));
+        return 0;
+    }
+    const uint32_t log_n = ilog2_u64(n);
+    fe r = h_load(root);
+    PassParams p;
+    memset(&p, 0, sizeof(p));
+    if (inverse) {
+        r = h_inv(r);
+        p.has_post = 1;
+        p.post = fe_to_mont(h_inv(h_from_u64(n)));
+    }
+    p.in = (const fe*)in; p.out = (fe*)out;
+    p.log_s = log_n; p.transposed = 0;
+    p.ld_s = stride; p.ld_b = 1; p.st_k = stride; p.st_b = 1;
+    ZKB_TRY(tw_s_table(c, r, log_n, log_n, &p.tw_s));
+    // columns are processed in tiles of B = 2^log_b (a ragged tail gets narrower tiles)
+    size_t done = 0;
+    while (done < count) {
+        uint32_t lb = TILE_LOG - log_n;
+        while (lb > 0 && ((size_t)1 << lb) > count - done) lb--;
+        const size_t B = (size_t)1 << lb, tiles = (count - done) >> lb;
+        PassParams q = p;
+        q.in = p.in + done; q.out = p.out + done;
+        q.log_b = lb; q.inner_count = (uint32_t)tiles;
+        q.ld_inner = B; q.st_inner = B;
+        ZKB_TRY(launch_pass(c, q, (uint32_t)tiles, 1));
+        done += tiles * B;
+    }
+    return 0;
+}
+
 int zkb_ntt(zkb_ctx* c, const uint8_t root[16], const void* in, size_t n_in, void* out) {
     return zkb_ntt_batch(c, root, 0, in, n_in, 0, out, 0, 1);
 }
