@@ -54,10 +54,11 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--cpu-log-n", type=int, default=14, help="codeword size of the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", default="codeword", choices=["codeword", "columns"],
+    ap.add_argument("--workload", default="codeword", choices=["codeword", "columns", "ntt", "ntt4step"],
                     help="codeword: one 2^log_n codeword per rank (weak scaling, the default, BASELINE configs[2]); "
                          "columns: BASELINE configs[3], --columns trace columns of 2^log_n (default 64 x 2^22) dealt "
-                         "round-robin to the ranks (strong scaling)")
+                         "round-robin to the ranks (strong scaling); ntt: configs[1], forward + inverse NTT of 2^log_n per rank; "
+                         "ntt4step: configs[4], ONE 2^log_n NTT (default 2^26) across all ranks, NCCL all-to-all")
     ap.add_argument("--columns", type=int, default=64)
     return ap.parse_args()
 
@@ -190,6 +191,8 @@ def b200_arm(args):
     stream = torch.cuda.Stream()                 # one explicit stream: library kernels, L2 flush and timing events
     torch.cuda.set_stream(stream)
     ctx = zk.Context(local, stream=stream.cuda_stream)
+    if args.workload in ("ntt", "ntt4step"):
+        return ntt_arm(args, ctx, stream, rank, world, local, barrier)
     columns_mode = args.workload == "columns"
     if columns_mode and args.log_n == 24:
         args.log_n = 22
@@ -323,6 +326,81 @@ def b200_arm(args):
             line["cpu_baseline"] = {"value": (1 << cl) / dt / 1e6, "unit": UNIT, "cores": 1, "kind": "port",
                                     "sample": "%d x (LDE + FRI commit of one 2^%d codeword), reference algorithm (bit-serial mul_mod, per-element "
                                               "pow/xgcd, recursive Merkle) restated in C; the Rust reference cannot be built here" % (reps, cl)}
+        print(json.dumps(line), flush=True)
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def ntt_arm(args, ctx, stream, rank, world, local, barrier):
+    """configs[1] (forward + inverse NTT per rank) and configs[4] (one NTT over all ranks)."""
+    import torch
+    import torch.distributed as dist
+    import zk_stark_tutor_b200 as zk
+    from zk_stark_tutor_b200 import synth, ntt_4step as fs
+    four = args.workload == "ntt4step"
+    log_n = 26 if (four and args.log_n == 24) else args.log_n
+    n = 1 << log_n
+    field = zk.Field()
+    w = field.primitive_nth_root(n)
+    L = n // world if four else n
+    x = torch.from_numpy(synth.elements(SEED + rank, L).view(np.int64)).cuda()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    eng = fs.CudaEngine(ctx)
+
+    def step():
+        if four:
+            return fs.ntt_4step(eng, w, x, rank, world)
+        return zk.intt(w, zk.ntt(w, x, ctx), ctx)
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    ctx.profile(True, reset=True)
+    l0 = ctx.launches
+    for a, b in evs:
+        flush.fill_(1)
+        a.record(stream)
+        step()
+        b.record(stream)
+    barrier()
+    launches = ctx.launches - l0
+    prof = ctx.profile_read()
+    ctx.profile(False)
+    ms = sum(a.elapsed_time(b) for a, b in evs)
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        ms_per_step = float(t.item()) / args.steps
+        units = n if four else 2 * n * world                       # elements transformed per step
+        log_l = (L.bit_length() - 1)
+        muls = (L // 2) * log_l * (world if four else 2 * world) + (n if not four else 0)
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except OSError:
+            pass
+        hbm_peak = peaks.get("hbm_gbs", 6650.0)
+        kms, kcnt = prof.get("k_ntt_pass", (0.0, 1))
+        alg_bytes = 32 * L                                          # one pass: every element read once, written once
+        achieved = alg_bytes / (kms / max(kcnt, 1) * 1e-3) / 1e9 if kms else None
+        line = {
+            "metric": "NTT throughput, elements/s" + (" (one 2^%d NTT over %d GPUs, four-step + NCCL all-to-all)" % (log_n, world) if four
+                                                       else " (forward + inverse NTT of 2^%d per GPU)" % log_n),
+            "value": units / (ms_per_step * 1e-3) / 1e6, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if four else "weak", "vs_baseline": None,
+            "dtype": "u128 (prime field, 4x32-bit limb Montgomery)", "data": "synthetic",
+            "config": {"workload": ("configs[4]: one 2^%d-element NTT split over %d GPU(s): local 2^%d NTT, twiddle, NCCL all-to-all, %d-point cross-GPU NTT"
+                                    % (log_n, world, log_l, world)) if four else "configs[1]: forward + inverse NTT of 2^%d elements" % log_n,
+                       "log_n": log_n, "l2": "flushed between steps (256 MiB write, untimed)"},
+            "field_mul_per_s": muls / (ms_per_step * 1e-3),
+            "gpu_launches": launches, "kernels": {k: {"ms_per_step": v[0] / args.steps, "launches_per_step": v[1] / args.steps} for k, v in prof.items()},
+            "roofline": {"kernel": "k_ntt_pass / k_ntt_rr (one HBM pass of the NTT)", "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                         "frac": (achieved / hbm_peak) if achieved else None, "traffic": None,
+                         "note": "per pass: 32 B per element algorithmic; the pass is integer-pipe bound (DESIGN.md 4)"},
+        }
         print(json.dumps(line), flush=True)
     ctx.close()
     if world > 1:

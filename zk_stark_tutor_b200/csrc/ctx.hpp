@@ -49,6 +49,7 @@ struct zkb_ctx {
     size_t pinned_bytes = 0;
     std::vector<std::unique_ptr<zkb::PowTable>> pow_tables;
     uint64_t clock = 0;
+    uint32_t root_seq = 0;   // sequence number of the last root signalled through pinned memory
     uint64_t launches = 0;   // kernels launched through this context (bench "gpu_launches")
     // optional per-kernel-class device timing (CUDA events on the launching stream)
     bool profiling = false;

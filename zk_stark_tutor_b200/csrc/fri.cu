@@ -182,27 +182,47 @@ static int fri_commit_impl(zkb_ctx* c, const zkb_fri_params* p, const void* code
     if (rc) return fail(rc);
 
     fe alpha = fe_zero();
-    fe offset_r = offset, omega_inv_r = omega_inv0;      // round-r offset and omega^-1
+    fe omega_inv_r = omega_inv0;                         // round-r omega^-1
+    // 1/offset_r for every round up front (offset_r = offset^(2^r), fri.rs:161-162): independent
+    // of the challenges, so it stays off the per-round critical path
+    std::vector<fe> inv_offset(rounds);
+    {
+        fe io = h_inv(offset);
+        for (uint64_t r = 0; r < rounds; r++) { inv_offset[r] = io; io = h_mul(io, io); }
+    }
+    // roots come back through mapped pinned memory: the top kernel writes root + sequence flag,
+    // the host polls (no D2H copy, no stream synchronisation on the critical path)
+    RootSignal sig;
+    sig.host_root = c->pinned + 128;
+    sig.host_flag = reinterpret_cast<volatile uint32_t*>(c->pinned + 64);
     for (uint64_t r = 0; r < rounds; r++) {
         const uint64_t len = L->len[r];
         const TreeLayout& tl = L->layout[r];
+        sig.seq = ++c->root_seq;
+        const bool polled = len > 1;
         if (r == 0) {
-            rc = merkle_build_levels(c, L->cw[0], nullptr, len, tl, L->nodes[0]);
+            rc = merkle_build_levels(c, L->cw[0], nullptr, len, tl, L->nodes[0], &sig);
         } else {
             FoldArgs f;
             f.cw = L->cw[r - 1]; f.next = (fe*)L->cw[r]; f.half = len;
             f.winv = winv_tab; f.exp_mul = 1ull << (r - 1);
-            f.kk_m = fe_to_mont(h_mul(alpha, h_inv(offset_r)));
+            f.kk_m = fe_to_mont(h_mul(alpha, inv_offset[r - 1]));
             f.wr_inv_m = fe_to_mont(omega_inv_r);
-            rc = merkle_build_levels(c, nullptr, &f, len, tl, L->nodes[r]);         // fold fused with leaf hashing
-            offset_r = h_mul(offset_r, offset_r);        // fri.rs:161-162
+            rc = merkle_build_levels(c, nullptr, &f, len, tl, L->nodes[r], &sig);   // fold fused with leaf hashing
             omega_inv_r = h_mul(omega_inv_r, omega_inv_r);
         }
         if (rc) return fail(rc);
-        cudaError_t e = cudaMemcpyAsync(c->pinned, L->nodes[r] + tl.level_off[tl.log_n] * 64, 64, cudaMemcpyDeviceToHost, c->stream);
-        if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
-        if (e != cudaSuccess) return fail(set_err(c, ZKB_ERR_CUDA, "FRI round %llu failed: %s", (unsigned long long)r, cudaGetErrorString(e)));
-        L->roots.emplace_back(c->pinned, c->pinned + 64);
+        if (polled) {
+            uint8_t root[64];
+            rc = wait_root(c, sig, root);
+            if (rc) return fail(rc);
+            L->roots.emplace_back(root, root + 64);
+        } else {
+            cudaError_t e = cudaMemcpyAsync(c->pinned, L->nodes[r] + tl.level_off[tl.log_n] * 64, 64, cudaMemcpyDeviceToHost, c->stream);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+            if (e != cudaSuccess) return fail(set_err(c, ZKB_ERR_CUDA, "FRI round %llu failed: %s", (unsigned long long)r, cudaGetErrorString(e)));
+            L->roots.emplace_back(c->pinned, c->pinned + 64);
+        }
         const int want_alpha = r + 1 < rounds;
         uint8_t alpha_le[16] = {0};
         if (fs(user, (uint32_t)r, L->roots.back().data(), want_alpha, alpha_le) != 0)

@@ -168,6 +168,9 @@ struct TopArgs {
     uint32_t fold;           // leaf values come from folding f (written to f.next)
     FoldArgs f;
     uint8_t* level_out[12];
+    uint8_t* host_root;      // mapped pinned host memory (or nullptr)
+    volatile uint32_t* host_flag;
+    uint32_t seq;
 };
 __global__ void __launch_bounds__(ZKB_TOP_THREADS) k_top(TopArgs a) {
     extern __shared__ uint4 dyn[];
@@ -198,6 +201,11 @@ __global__ void __launch_bounds__(ZKB_TOP_THREADS) k_top(TopArgs a) {
             b2_node_call(m, m + 8, h);
             sm_store_digest(nxt, j, h);
             g_store_digest(a.level_out[level], j, h);
+            if (cnt == 1 && a.host_root) {              // the root: hand it to the polling host
+                g_store_digest(a.host_root, 0, h);
+                __threadfence_system();
+                *a.host_flag = a.seq;
+            }
         }
         uint4* t = cur; cur = nxt; nxt = t;
     }
@@ -283,11 +291,28 @@ static int launch_top(zkb_ctx* c, const TopArgs& a) {
     return 0;
 }
 
+int wait_root(zkb_ctx* c, const RootSignal& s, uint8_t root_out[64]) {
+    uint64_t spins = 0;
+    while (*s.host_flag != s.seq) {
+        if ((++spins & 0xFFFF) == 0) {                  // every ~64k polls make sure the kernel is still alive
+            cudaError_t e = cudaStreamQuery(c->stream);
+            if (e != cudaSuccess && e != cudaErrorNotReady)
+                return set_err(c, ZKB_ERR_CUDA, "Merkle kernel failed: %s", cudaGetErrorString(e));
+            if (e == cudaSuccess && *s.host_flag != s.seq)
+                return set_err(c, ZKB_ERR_CUDA, "Merkle kernel finished without signalling its root");
+        }
+    }
+    __sync_synchronize();
+    memcpy(root_out, s.host_root, 64);
+    return 0;
+}
+
 int merkle_build_levels(zkb_ctx* c, const fe* vals, const FoldArgs* fold, uint64_t n,
-                        const TreeLayout& L, uint8_t* nodes) {
+                        const TreeLayout& L, uint8_t* nodes, const RootSignal* signal) {
     const uint32_t log_n = L.log_n;
     TopArgs a;
     memset(&a, 0, sizeof(a));
+    if (signal && n > 1) { a.host_root = signal->host_root; a.host_flag = signal->host_flag; a.seq = signal->seq; }
     if (L.top == 0) {                                   // n <= 1024: one CTA does everything
         a.vals = vals; a.count = (uint32_t)n;
         if (fold) { a.fold = 1; a.f = *fold; }

@@ -34,8 +34,18 @@ struct FoldArgs {
 // Build every stored level of the tree over `n` = 2^log_n values.  If `fold` is non-null
 // the values are produced on the fly by folding fold->cw (and written to fold->next; any n),
 // otherwise they are read from `vals`.  `nodes` must hold layout.total_nodes * 64 bytes.
+// If `signal` is non-null the top kernel also writes the 64-byte root to signal->host_root and
+// then stores signal->seq to *signal->host_flag (both in mapped pinned host memory), so the host
+// can pick the root up by polling instead of a D2H copy + stream synchronisation.
+struct RootSignal {
+    uint8_t* host_root;
+    volatile uint32_t* host_flag;
+    uint32_t seq;
+};
 int merkle_build_levels(zkb_ctx* c, const fe* vals, const FoldArgs* fold, uint64_t n,
-                        const TreeLayout& layout, uint8_t* nodes);
+                        const TreeLayout& layout, uint8_t* nodes, const RootSignal* signal = nullptr);
+// Spin until *signal->host_flag == signal->seq (falls back to a stream sync on a CUDA error).
+int wait_root(zkb_ctx* c, const RootSignal& signal, uint8_t root_out[64]);
 
 // Authentication paths for k indices: out[k][log_n][64] (device), leaf sibling first.
 int merkle_open_device(zkb_ctx* c, const fe* vals, const TreeLayout& layout, const uint8_t* nodes,
