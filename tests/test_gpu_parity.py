@@ -483,3 +483,121 @@ def test_columns_lde_commit_matches_oracle(ctx):
         _, trees, _ = fastfri.commit(ofri, C.coset_lde(w, n, F.GENERATOR, x), ops)
         assert got[c][1] == ops.digest()
         assert [bytes(allr[c, r]) for r in range(len(trees))] == [t.root for t in trees]
+
+
+# ---------------------------------------------------------------- a10: domain algorithms ----
+def test_domain_algorithms_vs_oracle(ctx):
+    """fast_zerofier / fast_evaluate_domain / fast_interpolate_domain (ntt_arithmetics.rs:66-237;
+    reference property tests :382-468) - NTT products on the GPU, scalar glue on the host."""
+    from oracle import poly as PL
+    n = 64
+    w = F.primitive_nth_root(n)
+    for size in (0, 1, 2, 5, 16, 23):
+        domain = rvals(size)
+        z = zk.fast_zerofier(w, n, domain, ctx)
+        assert z == PL.fast_zerofier(w, n, domain) == (PL.zerofier_domain(domain) if size else [])
+        poly = rvals(rnd.randrange(1, 31))
+        ev = zk.fast_evaluate_domain(w, n, poly, domain, ctx)
+        assert ev == PL.fast_evaluate_domain(w, n, poly, domain) == [PL.evaluate(poly, x) for x in domain]
+        values = rvals(size)
+        interp = zk.fast_interpolate_domain(w, n, domain, values, ctx)
+        assert interp == PL.fast_interpolate_domain(w, n, domain, values)
+        assert [PL.evaluate(interp, x) for x in domain] == values
+    # the Stark prover's use (stark.rs:305-326): interpolate a 284-row trace column on omicron^i
+    n = 1024
+    w = F.primitive_nth_root(n)
+    domain = [F.fpow(w, i) for i in range(284)]
+    values = rvals(284)
+    interp = zk.fast_interpolate_domain(w, n, domain, values, ctx)
+    assert interp == PL.fast_interpolate_domain(w, n, domain, values)
+    with pytest.raises(zk.ZkbError) as e:
+        zk.fast_zerofier(w, 512, domain, ctx)
+    assert e.value.code == -6
+
+
+# ---------------------------------------------------------------- the caller's sequence -----
+def _stark_like_prove(B, seed, n_regs=2, omicron_len=1024, ef=4, ncc=64, trace_len=284, tc_degree=3):
+    """The hot-path call sequence of Stark::prove (stark.rs:363-562) with synthetic quotient
+    polynomials in place of the Rescue-Prime AIR (which is out of scope): per register LDE +
+    Merkle commit, randomizer LDE + commit, Fiat-Shamir weights (incl. the reference's
+    all-weights-equal quirk, stark.rs:262-274), x^shift products via fast_multiply, weighted
+    combination, LDE, FRI::prove, quadrupled sorted indices, Value + Path openings.
+    `B` bundles the backend functions; the same function runs on the oracle and on the GPU."""
+    r = random.Random(seed)
+    fri_len = omicron_len * ef
+    omega, omicron = F.primitive_nth_root(fri_len), F.primitive_nth_root(omicron_len)
+    g = F.GENERATOR
+    ps = B["stream"]()
+    fri = B["fri"](g, omega, fri_len, ef, ncc)
+    bq = [[r.randrange(P) for _ in range(trace_len - 2)] for _ in range(n_regs)]          # boundary quotients
+    max_deg = (1 << (tc_degree * (trace_len - 1)).bit_length()) - 1                         # stark.rs:186-200
+    tq_bound = tc_degree * (trace_len - 1) - (trace_len - 256 - 1)
+    tq = [[r.randrange(P) for _ in range(tq_bound + 1)] for _ in range(n_regs)]             # transition quotients
+    bq_cw = []
+    for s in range(n_regs):
+        cw = B["lde"](omega, fri_len, g, bq[s])
+        ps.push((PS.ROOT, B["commit"](cw)))
+        bq_cw.append(cw)
+    randomizer = [F.sample(bytes(r.randrange(256) for _ in range(17))) for _ in range(max_deg + 1)]
+    r_cw = B["lde"](omega, fri_len, g, randomizer)
+    ps.push((PS.ROOT, B["commit"](r_cw)))
+    randomness = ps.fiat_shamir_prover(32)
+    weights = [F.sample(bytes(i) + randomness) for i in range(1 + 2 * len(tq) + 2 * len(bq))]
+    assert len(set(weights)) == 1                                                           # SURVEY A.6 quirk
+    x_pow = lambda k: [0] * k + [1]
+    terms = [randomizer]
+    for t in tq:
+        terms += [t, B["mul"](omicron, omicron_len, x_pow(max_deg - tq_bound), t)]
+    for b in bq:
+        terms += [b, B["mul"](omicron, omicron_len, x_pow(max_deg - (len(b) - 1)), b)]
+    from oracle import poly as PL
+    comb = []
+    for wgt, term in zip(weights, terms):
+        comb = PL.add(comb, PL.mul([wgt], term)) if comb else PL.mul([wgt], term)
+    comb_cw = B["lde"](omega, fri_len, g, comb)
+    idx = B["prove"](fri, comb_cw, ps)
+    dup = idx + [(i + ef) % fri_len for i in idx]
+    quad = sorted(dup + [(i + fri_len // 2) % fri_len for i in dup])
+    for cw in bq_cw + [r_cw]:
+        paths = B["open_many"](cw, quad)
+        for i, path in zip(quad, paths):
+            ps.push((PS.VALUE, cw[i]))
+            ps.push((PS.PATH, path))
+    return ps.digest()
+
+
+def test_stark_call_sequence_proof_bytes(ctx):
+    """GPU-backed and oracle-backed runs of the Stark prover's hot-path sequence produce the same
+    proof bytes, of exactly the size the reference quotes for these shapes (src/rpsss.rs:89)."""
+    def oracle_open_many(cw, idxs):
+        t = fastfri.Tree(C.to_arr(cw))
+        return [t.open(i) for i in idxs]
+
+    def oracle_prove(fri, cw, ps):
+        top, _, _ = fastfri.prove(fri, C.to_arr(cw), ps)
+        return top
+
+    oracle = {"stream": PS.IndependentProofStream, "fri": OFRI,
+              "lde": N.fast_coset_evaluate, "commit": M.commit, "mul": N.fast_multiply,
+              "prove": oracle_prove, "open_many": oracle_open_many}
+
+    def gpu_open_many(cw, idxs):
+        t = zk.MerkleTree(cw, ctx)
+        try:
+            return t.open_many(idxs)
+        finally:
+            t.close()
+
+    gpu = {"stream": zk.IndependentProofStream, "fri": lambda *a: zk.FRI(*a, ctx=ctx),
+           "lde": lambda w, n, off, p: zk.fast_coset_evaluate(w, n, off, p, ctx),
+           "commit": lambda cw: zk.MerkleRoot.commit(cw, ctx),
+           "mul": lambda w, n, a, b: zk.fast_multiply(w, n, a, b, ctx),
+           "prove": lambda fri, cw, ps: fri.prove(cw, ps), "open_many": gpu_open_many}
+    want = _stark_like_prove(oracle, 4242)
+    got = _stark_like_prove(gpu, 4242)
+    assert len(want) == 1156888                                   # src/rpsss.rs:89
+    assert got == want
+    # the signature flavour (document-prefixed Fiat-Shamir, rescue_prime/proof_stream.rs)
+    oracle["stream"] = lambda: PS.SignatureProofStream(b"a document")
+    gpu["stream"] = lambda: zk.SignatureProofStream(b"a document")
+    assert _stark_like_prove(gpu, 7) == _stark_like_prove(oracle, 7)

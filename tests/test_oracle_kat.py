@@ -206,3 +206,25 @@ def test_colinearity():
     assert colinear([(1, 3), (2, 5), (5, 11)])
     assert not colinear([(1, 3), (2, 5), (5, 12)])
     assert not colinear([(1, 3), (2, 3), (5, 3)])      # degree 0 is rejected (polynomial.rs:172)
+
+
+def test_domain_algorithms_vs_schoolbook():
+    # src/fft/ntt_arithmetics.rs:382-468: fast_zerofier / fast_evaluate_domain /
+    # fast_interpolate_domain against their schoolbook counterparts on random domains
+    import random
+    from oracle import poly as PL
+    rnd = random.Random(11)
+    n = 64
+    w = F.primitive_nth_root(n)
+    for size in (1, 2, 5, 16, 23):
+        domain = [rnd.randrange(P) for _ in range(size)]
+        assert PL.fast_zerofier(w, n, domain) == PL.zerofier_domain(domain)
+        poly = [rnd.randrange(P) for _ in range(rnd.randrange(1, 31))]
+        assert PL.fast_evaluate_domain(w, n, poly, domain) == [PL.evaluate(poly, x) for x in domain]
+        values = [rnd.randrange(P) for _ in range(size)]
+        interp = PL.fast_interpolate_domain(w, n, domain, values)
+        assert [PL.evaluate(interp, x) for x in domain] == values
+        assert (N.degree(interp) or 0) < size
+    assert PL.fast_zerofier(w, n, []) == [] and PL.fast_interpolate_domain(w, n, [], []) == []
+    q, r = PL.divide_with_rem([1, 2, 3, 4], [1, 1])
+    assert PL.add(PL.mul(q, [1, 1]), r)[:4] == [1, 2, 3, 4]

@@ -7,7 +7,7 @@ compute call raises."""
 from .context import Context, ZkbError, default_context, pack, unpack, P      # noqa: F401
 from .field import Field, FIELD_PRIME                                           # noqa: F401
 from .fft import (ntt, intt, ntt_batch, scale, fast_coset_evaluate, coset_lde_batch,   # noqa: F401
-                  fast_multiply, fast_coset_divide)
+                  fast_multiply, fast_coset_divide, fast_zerofier, fast_evaluate_domain, fast_interpolate_domain)
 from .merkle_root import MerkleRoot, MerkleTree                                  # noqa: F401
 from .proof_stream import IndependentProofStream, SignatureProofStream           # noqa: F401
 from .fri import FRI, FriLayers                                                  # noqa: F401

@@ -166,6 +166,16 @@ __global__ void __launch_bounds__(ZKB_NTT_THREADS) k_ntt_pass(const PassParams p
 //   step 3: thread (ka, b) reads Y[ka][s0][b], s0 < R2, R2-point DFT -> X[ka + R1*kb], applies the
 //           inter-pass twiddle (running product over kb) / n^-1 and stores to HBM.
 // Trivial twiddles (w^0) cost nothing: 17 multiplications per 16-point DFT instead of 32.
+// One out-of-line copy of the multiplication per kernel: the fully unrolled pass has ~130
+// multiplication sites; inlined that is 190 KB of SASS and the pass stalls on instruction
+// fetch (ncu: no_instruction is the top stall) - as calls it fits the instruction cache.
+__device__ __noinline__ fe mm(fe a, fe b) { return fe_montmul(a, b); }
+
+__device__ __forceinline__ fe pow2lvl_c(const DevPow& t, uint64_t e) {
+    fe lo = fe_ldg(t.lo + (e & ((1ull << t.lo_bits) - 1)));
+    fe hi = fe_ldg(t.hi + (e >> t.lo_bits));
+    return mm(hi, lo);
+}
 template <int LOGR>
 __device__ __forceinline__ void dft_dif(fe (&x)[1 << LOGR], const fe* __restrict__ tw, uint32_t tw_stride) {
     constexpr int R = 1 << LOGR;
@@ -179,7 +189,7 @@ __device__ __forceinline__ void dft_dif(fe (&x)[1 << LOGR], const fe* __restrict
             fe u = x[s0], v = x[s0 + h];
             x[s0] = fe_add(u, v);
             fe d = fe_sub(u, v);
-            x[s0 + h] = (j == 0) ? d : fe_montmul(d, tw[(uint32_t)(j << (LOGR - 1 - lh)) * tw_stride]);
+            x[s0 + h] = (j == 0) ? d : mm(d, tw[(uint32_t)(j << (LOGR - 1 - lh)) * tw_stride]);
         }
     }
 }
@@ -214,7 +224,7 @@ __global__ void __launch_bounds__(ZKB_NTT_THREADS, 2) k_ntt_rr(const PassParams 
             x[s1] = fe_zero();
             if (!p.has_valid || lin < p.n_valid) {
                 x[s1] = fe_ldg(in + lin);
-                if (p.has_scale) x[s1] = fe_montmul(x[s1], pow2lvl(p.sc, lin));
+                if (p.has_scale) x[s1] = mm(x[s1], pow2lvl_c(p.sc, lin));
             }
         }
         dft_dif<LR1>(x, tws, R2);
@@ -223,7 +233,7 @@ __global__ void __launch_bounds__(ZKB_NTT_THREADS, 2) k_ntt_rr(const PassParams 
             const uint32_t ka = brev_c<LR1>(i);
             fe y = x[i];
             const uint32_t e = s0 * ka;                    // < S
-            if (ka != 0 && s0 != 0) y = fe_montmul(y, tws[e]);
+            if (ka != 0 && s0 != 0) y = mm(y, tws[e]);
             sm[(size_t)(ka * R2 + s0) * pitch + b] = y;
         }
     }
@@ -238,17 +248,17 @@ __global__ void __launch_bounds__(ZKB_NTT_THREADS, 2) k_ntt_rr(const PassParams 
         fe t, step;
         if (p.has_tw) {
             const uint64_t col = (uint64_t)inner * B + b;
-            t = pow2lvl(p.tw, (uint64_t)ka * col * p.tw_mul);
-            step = pow2lvl(p.tw, (uint64_t)R1 * col * p.tw_mul);
+            t = pow2lvl_c(p.tw, (uint64_t)ka * col * p.tw_mul);
+            step = pow2lvl_c(p.tw, (uint64_t)R1 * col * p.tw_mul);
         }
 #pragma unroll
         for (uint32_t kb = 0; kb < R2; kb++) {
             fe y = x[brev_c<LR2>(kb)];
             if (p.has_tw) {
-                y = fe_montmul(y, t);
-                if (kb + 1 < R2) t = fe_montmul(t, step);
+                y = mm(y, t);
+                if (kb + 1 < R2) t = mm(t, step);
             }
-            if (p.has_post) y = fe_montmul(y, p.post);
+            if (p.has_post) y = mm(y, p.post);
             fe_store(out + (uint64_t)(ka + R1 * kb) * p.st_k + (uint64_t)b * p.st_b, y);
         }
     }

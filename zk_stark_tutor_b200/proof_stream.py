@@ -42,7 +42,8 @@ class IndependentProofStream:
             self.lib.zkb_ps_push_value(self.h, le16(x))
         else:
             raise ValueError("Unknown code")
-        self.objects.append(obj)
+        if self.objects is not None:       # None once a C-side call (zkb_fri_prove) has appended objects itself
+            self.objects.append(obj)
 
     def digest(self):
         n = self.lib.zkb_ps_digest(self.h, None, 0)
