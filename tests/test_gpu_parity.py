@@ -430,11 +430,12 @@ def test_lde_fri_commit_pipeline(ctx, log_n, n_coeffs):
 
 def test_profile_counters(ctx):
     ctx.profile(True, reset=True)
-    n = 1 << 12
+    n = 1 << 20
     zk.MerkleRoot.commit(C.synth(1, n), ctx)
     prof = ctx.profile_read()
     ctx.profile(False)
     assert prof["k_leaf8<false>"][1] == 1 and prof["k_leaf8<false>"][0] > 0
+    assert prof["k_tree"][1] == 1
 
 
 def test_fast_multiply_trailing_zero_quirk(ctx):

@@ -218,7 +218,7 @@ int zkb_ctx_profile_read(zkb_ctx* c, int kernel_id, double* total_ms, uint64_t* 
 }
 const char* zkb_kernel_name(int kernel_id) {
     static const char* names[K_COUNT] = {"k_pow_table", "k_ntt_pass", "k_elementwise", "k_leaf8<false>", "k_leaf8<true>",
-                                         "k_node8", "k_top", "k_open", "k_fold", "k_gather3"};
+                                         "k_node8", "k_tree", "k_open", "k_fold", "k_gather3"};
     return (kernel_id >= 0 && kernel_id < K_COUNT) ? names[kernel_id] : nullptr;
 }
 

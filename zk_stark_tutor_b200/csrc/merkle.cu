@@ -14,24 +14,41 @@
 //             of the previous layer and written out as the next codeword ("fold fused with
 //             the next round's leaf hashing").
 //   k_node8   the same over 8 stored nodes: 7 compressions -> the node three levels up.
-//   k_top     one CTA finishes any level of <= 1024 inputs (leaves or nodes), every level
-//             stored; also the whole tree for n <= 1024.
+//   k_tree    everything above a level of <= 2^15 nodes, and whole trees of <= 2^17 leaves:
+//             level by level, one compression per thread per level, grid-wide barrier between
+//             levels (cooperative launch), every level stored.  These phases are bound by the
+//             latency of a chain of log2(n) compressions, not by throughput, so the tree is
+//             walked with maximal parallelism per level instead of per-thread subtrees.
 #include <stdlib.h>
 #include <string.h>
 #include "merkle.cuh"
 #include "blake2b.cuh"
+#include <cooperative_groups.h>
+namespace cg = cooperative_groups;
 
 namespace zkb {
+
+// thresholds (tunable through ZKB_TREE_LEAF_LOG / ZKB_TREE_NODE_LOG for experiments)
+static uint32_t tree_leaf_log() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("ZKB_TREE_LEAF_LOG"); v = e ? atoi(e) : ZKB_TREE_LEAF_LOG; if (v > 22) v = 22; if (v < 1) v = 1; }
+    return (uint32_t)v;
+}
+static uint32_t tree_node_log() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("ZKB_TREE_NODE_LOG"); v = e ? atoi(e) : ZKB_TREE_NODE_LOG; if (v > 22) v = 22; if (v < 1) v = 1; }
+    return (uint32_t)v;
+}
 
 void TreeLayout::init(uint32_t log_n_) {
     log_n = log_n_;
     uint64_t off = 0;
     for (uint32_t l = 0; l <= 40; l++) { level_off[l] = 0; stored[l] = 0; }
-    if (log_n <= 10) {
-        top = 0;
+    if (log_n <= tree_leaf_log()) {
+        top = 0;                                   // the level-by-level kernel takes the leaves directly
     } else {
         top = 3;
-        while (log_n - top > 10) top += 3;
+        while (log_n - top > tree_node_log()) top += 3;
         for (uint32_t l = 3; l < top; l += 3) stored[l] = 1;
     }
     for (uint32_t l = top; l <= log_n; l++) stored[l] = 1;
@@ -157,57 +174,80 @@ __global__ void __launch_bounds__(THREADS, MINB) k_node8(const uint8_t* __restri
     g_store_digest(out, g, h);
 }
 
-// One CTA of 512 threads: `count` (power of two, <= 1024) leaves or nodes -> every level up to
-// the root.  level_out[r] = global destination of relative level r (r = 0 is the input level
-// and is only written for leaf input).  Dynamic shared memory: 1024 + 512 digests.
-#define ZKB_TOP_THREADS 512
+// Level-by-level tree: `count` (power of two, <= 2^19) leaves or nodes -> every level up to the
+// root.  One compression per thread per level, grid-wide barrier between levels while more than
+// one CTA has work; CTA 0 finishes the last levels alone.  level_out[r] = global destination of
+// relative level r (r = 0 is the input level and is only written for leaf input).
+#define ZKB_TREE_THREADS 256
 struct TopArgs {
     const fe* vals;          // leaf input (or nullptr)
     const uint8_t* nodes_in; // node input (or nullptr)
     uint32_t count;
     uint32_t fold;           // leaf values come from folding f (written to f.next)
     FoldArgs f;
-    uint8_t* level_out[12];
+    uint8_t* level_out[26];
     uint8_t* host_root;      // mapped pinned host memory (or nullptr)
     volatile uint32_t* host_flag;
     uint32_t seq;
 };
-__global__ void __launch_bounds__(ZKB_TOP_THREADS) k_top(TopArgs a) {
-    extern __shared__ uint4 dyn[];
-    uint4* cur = dyn;
-    uint4* nxt = dyn + 1024 * 4;
-    const uint32_t tid = threadIdx.x;
-    uint64_t m[16], h[8];
-    for (uint32_t i = tid; i < a.count; i += ZKB_TOP_THREADS) {
-        if (a.fold) {
-            fe k_m = fe_montmul(a.f.kk_m, pow2lvl_m(a.f.winv, (uint64_t)i * a.f.exp_mul));
-            fe v = fold_one(a.f, i, k_m);
+// loads of nodes written earlier IN THIS kernel must not take the non-coherent path
+__device__ __forceinline__ void g_load_digest_coherent(const uint8_t* nodes, uint64_t idx, uint64_t* h) {
+    const uint4* src = reinterpret_cast<const uint4*>(nodes + idx * 64);
+#pragma unroll
+    for (int cidx = 0; cidx < 4; cidx++) {
+        uint4 x = __ldcg(src + cidx);
+        h[2 * cidx] = ((uint64_t)x.y << 32) | x.x;
+        h[2 * cidx + 1] = ((uint64_t)x.w << 32) | x.z;
+    }
+}
+__global__ void __launch_bounds__(ZKB_TREE_THREADS, 2) k_tree(TopArgs a) {
+    cg::grid_group grid = cg::this_grid();
+    const uint32_t gtid = blockIdx.x * ZKB_TREE_THREADS + threadIdx.x;
+    const uint32_t gthreads = gridDim.x * ZKB_TREE_THREADS;
+    uint64_t l[8], r[8], h[8];
+    const uint8_t* prev = a.nodes_in;
+    if (!prev) {                                   // leaf level
+        for (uint32_t i = gtid; i < a.count; i += gthreads) {
+            fe v;
+            if (a.fold) {
+                fe k_m = fe_montmul(a.f.kk_m, pow2lvl_m(a.f.winv, (uint64_t)i * a.f.exp_mul));
+                v = fold_one(a.f, i, k_m);
+            } else {
+                v = fe_ldg(a.vals + i);
+            }
             b2_leaf_call(&v, h);
             g_store_digest(a.level_out[0], i, h);
-        } else if (a.vals) {
-            fe v = fe_ldg(a.vals + i);
-            b2_leaf_call(&v, h);
-            g_store_digest(a.level_out[0], i, h);
-        } else {
-            g_load_digest(a.nodes_in, i, h);
         }
-        sm_store_digest(cur, i, h);
+        prev = a.level_out[0];
+        if (a.count > 1) {
+            if (gridDim.x > 1) grid.sync(); else __syncthreads();
+        }
     }
     uint32_t level = 1;
+    bool alone = gridDim.x == 1;
     for (uint32_t cnt = a.count >> 1; cnt >= 1; cnt >>= 1, level++) {
-        __syncthreads();
-        for (uint32_t j = tid; j < cnt; j += ZKB_TOP_THREADS) {
-            sm_load_pair(cur, j, m);
-            b2_node_call(m, m + 8, h);
-            sm_store_digest(nxt, j, h);
+        for (uint32_t j = gtid; j < cnt; j += gthreads) {
+            g_load_digest_coherent(prev, 2 * (uint64_t)j, l);
+            g_load_digest_coherent(prev, 2 * (uint64_t)j + 1, r);
+            b2_node_call(l, r, h);
             g_store_digest(a.level_out[level], j, h);
-            if (cnt == 1 && a.host_root) {              // the root: hand it to the polling host
+            if (cnt == 1 && a.host_root) {          // the root: hand it to the polling host
                 g_store_digest(a.host_root, 0, h);
                 __threadfence_system();
                 *a.host_flag = a.seq;
             }
         }
-        uint4* t = cur; cur = nxt; nxt = t;
+        prev = a.level_out[level];
+        if (cnt == 1) break;
+        if (alone) {
+            __syncthreads();
+        } else if ((cnt >> 1) > ZKB_TREE_THREADS) {
+            grid.sync();                           // the next level still spans several CTAs
+        } else {
+            grid.sync();                           // last grid-wide barrier: CTA 0 goes on alone
+            if (blockIdx.x != 0) return;
+            alone = true;
+        }
     }
 }
 
@@ -281,12 +321,23 @@ __global__ void __launch_bounds__(128) k_open(OpenArgs a) {
 }
 
 static int launch_top(zkb_ctx* c, const TopArgs& a) {
-    static bool attr_set = false;
-    if (!attr_set) {
-        ZKB_CUDA(c, cudaFuncSetAttribute(k_top, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-        attr_set = true;
+    static int max_blocks = 0;
+    if (!max_blocks) {
+        int per_sm = 0;
+        ZKB_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_tree, ZKB_TREE_THREADS, 0));
+        max_blocks = per_sm * c->sm_count;
+        if (max_blocks < 1) return set_err(c, ZKB_ERR_CUDA, "k_tree cannot be made resident");
     }
-    { LaunchScope ls(c, K_MERKLE_SMALL); k_top<<<1, ZKB_TOP_THREADS, 96 * 1024, c->stream>>>(a); }
+    // enough CTAs for the widest level (the input level for leaves, half of it for nodes)
+    uint32_t widest = a.nodes_in ? (a.count >> 1) : a.count;
+    int blocks = (int)((widest + ZKB_TREE_THREADS - 1) / ZKB_TREE_THREADS);
+    if (blocks < 1) blocks = 1;
+    if (blocks > max_blocks) blocks = max_blocks;
+    void* args[] = {(void*)&a};
+    {
+        LaunchScope ls(c, K_MERKLE_SMALL);
+        ZKB_CUDA(c, cudaLaunchCooperativeKernel((const void*)k_tree, dim3(blocks), dim3(ZKB_TREE_THREADS), args, 0, c->stream));
+    }
     ZKB_CUDA(c, cudaGetLastError());
     return 0;
 }
@@ -313,7 +364,7 @@ int merkle_build_levels(zkb_ctx* c, const fe* vals, const FoldArgs* fold, uint64
     TopArgs a;
     memset(&a, 0, sizeof(a));
     if (signal && n > 1) { a.host_root = signal->host_root; a.host_flag = signal->host_flag; a.seq = signal->seq; }
-    if (L.top == 0) {                                   // n <= 1024: one CTA does everything
+    if (L.top == 0) {                                   // n <= 2^19: the level-by-level kernel does everything
         a.vals = vals; a.count = (uint32_t)n;
         if (fold) { a.fold = 1; a.f = *fold; }
         for (uint32_t l = 0; l <= log_n; l++) a.level_out[l] = nodes + L.level_off[l] * 64;

@@ -5,15 +5,17 @@
 namespace zkb {
 
 // Layout of a retained tree.  Levels are counted from the leaves: level 0 = leaf hashes
-// (n nodes), level log_n = the root.  Trees of <= 1024 leaves store every level.  Larger
+// (n nodes), level log_n = the root.  Trees of <= 2^17 leaves store every level.  Larger
 // trees store level 3, 6, 9, ... (what the per-thread 8-ary subtree kernels emit) down to the
-// first level `top` with <= 1024 nodes, and every level above `top` (9.2n bytes instead of
-// 128n).  The two unstored levels inside each group of three - and the leaf hashes - of an
+// first level `top` with <= 2^15 nodes, and every level above `top` (<= 9.2n bytes + 4 MiB
+// instead of 128n).  The two unstored levels inside each group of three - and the leaf hashes - of an
 // authentication path are recomputed at opening time from the 8 group inputs, which the tree
 // can always reach (it references the committed values).
+#define ZKB_TREE_LEAF_LOG 17     // trees up to 2^17 leaves: level-by-level kernel from the leaves
+#define ZKB_TREE_NODE_LOG 15     // larger trees: 8-ary subtree kernels down to <= 2^15 nodes, then level by level
 struct TreeLayout {
     uint32_t log_n = 0;
-    uint32_t top = 0;            // first level handled by the single-CTA top kernel (0 for small trees)
+    uint32_t top = 0;            // first level handled by the level-by-level kernel (0: it starts from the leaves)
     uint8_t stored[41];
     uint64_t level_off[41];      // node index (64-byte units) of level l inside `nodes` (stored levels only)
     uint64_t total_nodes = 0;
