@@ -60,6 +60,7 @@ def parse():
                          "round-robin to the ranks (strong scaling); ntt: configs[1], forward + inverse NTT of 2^log_n per rank; "
                          "ntt4step: configs[4], ONE 2^log_n NTT (default 2^26) across all ranks, NCCL all-to-all")
     ap.add_argument("--columns", type=int, default=64)
+    ap.add_argument("--lanes", type=int, default=4, help="columns in flight per GPU in the columns workload (streams + host threads)")
     return ap.parse_args()
 
 
@@ -221,26 +222,39 @@ def b200_arm(args):
         ps.close()
         return proof_bytes
 
+    pipe = None
+    if columns_mode and args.lanes > 1:
+        pipe = colmod.ColumnPipeline(local, (GENERATOR, omega, n, EF, NCC), lanes=args.lanes)
+
     def step(bufs):
         """one step = LDE + FRI commit of every local column (one in codeword mode)"""
+        if pipe is not None:
+            torch.cuda.current_stream().synchronize()
+            return pipe.run(bufs, zk.IndependentProofStream, keep_roots=False)
         return [one(b.data_ptr()) for b in bufs]
 
     def timed(coeffs_ptr, steps, profile):
         evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
         barrier()
+        ctxs = pipe.ctxs if pipe is not None else [ctx]
         if profile:
-            ctx.profile(True, reset=True)
-        l0 = ctx.launches
+            for cx in ctxs:
+                cx.profile(True, reset=True)
+        l0 = sum(cx.launches for cx in ctxs)
         for a, b in evs:
             flush.fill_(1)                                   # L2 flush between steps (untimed)
             a.record(stream)
-            step(coeffs_ptr)
+            step(coeffs_ptr)                                 # host-synchronous: returns when the GPU work is done
             b.record(stream)
         barrier()
-        launches = ctx.launches - l0
-        prof = ctx.profile_read() if profile else {}
+        launches = sum(cx.launches for cx in ctxs) - l0
+        prof = {}
         if profile:
-            ctx.profile(False)
+            for cx in ctxs:
+                for k, (ms, cnt) in cx.profile_read().items():
+                    pm, pc = prof.get(k, (0.0, 0))
+                    prof[k] = (pm + ms, pc + cnt)
+                cx.profile(False)
         ms = sum(a.elapsed_time(b) for a, b in evs)
         t = torch.tensor([ms], dtype=torch.float64, device="cuda")
         if world > 1:
@@ -320,7 +334,8 @@ def b200_arm(args):
                                    % (log_n - 2, log_n, rounds, rounds - 1, last_len, "" if columns_mode else ", one codeword per GPU"),
                        "log_n": log_n, "expansion_factor": EF, "num_colinearity_tests": NCC, "rounds": rounds,
                        "l2": "flushed between steps (256 MiB write, untimed); per-step CUDA events summed; working set per step > L2",
-                       "parallelism": "independent codewords / columns per rank, no data-path collective"},
+                       "parallelism": "independent codewords / columns per rank, no data-path collective"
+                                      + (", %d columns in flight per GPU" % args.lanes if pipe is not None else "")},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": cols_here * n_coeffs * 16, "d2h_bytes_per_step": cols_here * (rounds * 64 + last_len * 16),
                     "ms_per_step": e2e_ms / e2e_steps, "api": "zkb_lde_fri_commit_ps with pinned host coefficients"},
             "gpu_launches": launches, "kernels": kern, "dominant_kernel": dom,

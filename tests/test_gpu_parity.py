@@ -484,6 +484,13 @@ def test_columns_lde_commit_matches_oracle(ctx):
         _, trees, _ = fastfri.commit(ofri, C.coset_lde(w, n, F.GENERATOR, x), ops)
         assert got[c][1] == ops.digest()
         assert [bytes(allr[c, r]) for r in range(len(trees))] == [t.root for t in trees]
+    # the same columns with several in flight on one GPU (3 streams, 3 host threads)
+    import torch
+    torch.cuda.synchronize()
+    pipe = columns.ColumnPipeline(0, (F.GENERATOR, w, n, 4, 64), lanes=3)
+    got2 = pipe.run([cuda(x) for x in coeffs], zk.IndependentProofStream)
+    pipe.close()
+    assert [g[1] for g in got2] == [g[1] for g in got] and [g[0] for g in got2] == [g[0] for g in got]
 
 
 # ---------------------------------------------------------------- a10: domain algorithms ----

@@ -29,6 +29,52 @@ def lde_commit_columns(fri, columns, make_stream, ctx=None):
     return out
 
 
+class ColumnPipeline:
+    """Several columns in flight on ONE GPU: `lanes` contexts (each with its own CUDA stream)
+    driven by `lanes` host threads.  A single column's FRI commit is a serial chain (round r+1
+    needs the challenge derived from round r's root) whose small rounds are latency-bound and
+    leave most SMs idle; independent columns fill them.  The C calls release the GIL."""
+
+    def __init__(self, device, fri_params, lanes=3):
+        import zk_stark_tutor_b200 as zk
+        self.zk = zk
+        self.ctxs = [zk.Context(device, stream="own") for _ in range(lanes)]
+        offset, omega, n, ef, ncc = fri_params
+        self.fris = [zk.FRI(offset, omega, n, ef, ncc, c) for c in self.ctxs]
+
+    def run(self, columns, make_stream, keep_roots=True):
+        """columns: list of device tensors / host arrays.  Returns per column (roots, digest)."""
+        import threading
+        results = [None] * len(columns)
+        errors = []
+
+        def worker(lane):
+            try:
+                for i in range(lane, len(columns), len(self.ctxs)):
+                    ps = make_stream()
+                    layers = self.fris[lane].lde_commit(columns[i], ps)
+                    roots = [layers.root(r) for r in range(len(layers))] if keep_roots else None
+                    layers.close()
+                    results[i] = (roots, ps.digest())
+            except Exception as e:       # noqa: BLE001 - re-raised in the caller's thread
+                errors.append(e)
+
+        threads = [threading.Thread(target=worker, args=(k,)) for k in range(len(self.ctxs))]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+        for c in self.ctxs:
+            c.sync()
+        if errors:
+            raise errors[0]
+        return results
+
+    def close(self):
+        for c in self.ctxs:
+            c.close()
+
+
 def gather_roots(local_roots, n_cols, world, rank, rounds, group=None):
     """All ranks receive every column's roots: (n_cols, rounds, 64) uint8.  `local_roots`:
     list (in partition order) of per-column lists of 64-byte roots.  world == 1 needs no
