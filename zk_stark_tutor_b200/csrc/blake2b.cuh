@@ -366,6 +366,70 @@ __device__ __forceinline__ void blake2b_compress_x(const uint32_t (&ml)[16], con
 }
 #endif
 
+#if defined(__CUDACC__)
+// ---- one compression on FOUR lanes (latency mode) ----------------------------------------------
+// The upper levels of a tree are a chain of dependent compressions with almost no parallelism
+// across nodes; there the time per level is the latency of ONE compression (~3.4 us for a
+// single lane executing all 96 G functions).  Here lane q of a quad owns column q of the 4x4
+// BLAKE2b state (a_q, b_q, c_q, d_q): the four column G's run in parallel, the rows are rotated
+// across the quad with shuffles for the diagonal G's and rotated back: ~4x fewer instructions
+// on the critical path.  The 16 message words are read from shared memory (contiguous, 128 B
+// at `msg`); which word a lane needs is a compile-time table indexed by q: the four byte
+// offsets of one (round, slot) are packed into one 32-bit constant and picked with ONE PRMT
+// (`sel` = 0x4440 | q), so a message word costs PRMT + IADD + LDS.64.
+struct B2Sigma { uint8_t s[12][16]; };
+__host__ __device__ constexpr B2Sigma b2_sigma() {
+    return B2Sigma{{{0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15}, {14, 10, 4, 8, 9, 15, 13, 6, 1, 12, 0, 2, 11, 7, 5, 3},
+                    {11, 8, 12, 0, 5, 2, 15, 13, 10, 14, 3, 6, 7, 1, 9, 4}, {7, 9, 3, 1, 13, 12, 11, 14, 2, 6, 5, 10, 4, 0, 15, 8},
+                    {9, 0, 5, 7, 2, 4, 10, 15, 14, 1, 11, 12, 6, 8, 3, 13}, {2, 12, 6, 10, 0, 11, 8, 3, 4, 13, 7, 5, 15, 14, 1, 9},
+                    {12, 5, 1, 15, 14, 13, 4, 10, 0, 7, 6, 3, 9, 2, 8, 11}, {13, 11, 7, 14, 12, 1, 3, 9, 5, 0, 15, 4, 8, 6, 2, 10},
+                    {6, 15, 14, 9, 11, 3, 0, 8, 12, 2, 13, 7, 1, 4, 10, 5}, {10, 2, 8, 4, 7, 6, 1, 5, 15, 11, 9, 14, 3, 12, 13, 0},
+                    {0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15}, {14, 10, 4, 8, 9, 15, 13, 6, 1, 12, 0, 2, 11, 7, 5, 3}}};
+}
+// message word for lane q: slot 0/1 = column x/y (sigma[2q], sigma[2q+1]), slot 2/3 = diagonal x/y
+template <int R, int SLOT>
+__device__ __forceinline__ uint64_t b2q_msg(const uint8_t* msg, uint32_t sel) {
+    constexpr B2Sigma S = b2_sigma();
+    constexpr int o = (SLOT & 1) + 8 * (SLOT >> 1);
+    constexpr uint32_t packed = (uint32_t)(S.s[R][o] * 8) | ((uint32_t)(S.s[R][o + 2] * 8) << 8) |
+                                ((uint32_t)(S.s[R][o + 4] * 8) << 16) | ((uint32_t)(S.s[R][o + 6] * 8) << 24);
+    return *reinterpret_cast<const uint64_t*>(msg + __byte_perm(packed, 0u, sel));
+}
+template <int R>
+__device__ __forceinline__ void b2q_round(uint64_t& a, uint64_t& b, uint64_t& c, uint64_t& d, const uint8_t* msg, uint32_t sel,
+                                          uint32_t l1, uint32_t l2, uint32_t l3) {
+    uint64_t x = b2q_msg<R, 0>(msg, sel), y = b2q_msg<R, 1>(msg, sel);
+    uint64_t x2 = b2q_msg<R, 2>(msg, sel), y2 = b2q_msg<R, 3>(msg, sel);
+    ZKB_B2_G(a, b, c, d, x, y);
+    b = __shfl_sync(0xFFFFFFFFu, b, l1);
+    c = __shfl_sync(0xFFFFFFFFu, c, l2);
+    d = __shfl_sync(0xFFFFFFFFu, d, l3);
+    ZKB_B2_G(a, b, c, d, x2, y2);
+    b = __shfl_sync(0xFFFFFFFFu, b, l3);
+    c = __shfl_sync(0xFFFFFFFFu, c, l2);
+    d = __shfl_sync(0xFFFFFFFFu, d, l1);
+}
+// One block of t bytes (final): lane q returns digest words q (h_lo) and q + 4 (h_hi).
+// All 32 lanes of the warp must call it (shuffles); quads without work pass any readable msg.
+__device__ __forceinline__ void blake2b_quad(const uint8_t* msg, uint64_t t, uint32_t lane, uint64_t& h_lo, uint64_t& h_hi) {
+    const uint32_t q = lane & 3u, lane_base = lane & ~3u, sel = 0x4440u | q;
+    const uint32_t l1 = lane_base | ((q + 1) & 3), l2 = lane_base | ((q + 2) & 3), l3 = lane_base | ((q + 3) & 3);
+    const uint64_t iv_lo = q == 0 ? ZKB_B2_IV0 : q == 1 ? ZKB_B2_IV1 : q == 2 ? ZKB_B2_IV2 : ZKB_B2_IV3;
+    const uint64_t iv_hi = q == 0 ? ZKB_B2_IV4 : q == 1 ? ZKB_B2_IV5 : q == 2 ? ZKB_B2_IV6 : ZKB_B2_IV7;
+    const uint64_t h0 = q == 0 ? ZKB_B2_H0 : iv_lo;
+    uint64_t a = h0, b = iv_hi, c = iv_lo;
+    uint64_t d = iv_hi ^ (q == 0 ? t : 0ull) ^ (q == 2 ? ~0ull : 0ull);
+    b2q_round<0>(a, b, c, d, msg, sel, l1, l2, l3);  b2q_round<1>(a, b, c, d, msg, sel, l1, l2, l3);
+    b2q_round<2>(a, b, c, d, msg, sel, l1, l2, l3);  b2q_round<3>(a, b, c, d, msg, sel, l1, l2, l3);
+    b2q_round<4>(a, b, c, d, msg, sel, l1, l2, l3);  b2q_round<5>(a, b, c, d, msg, sel, l1, l2, l3);
+    b2q_round<6>(a, b, c, d, msg, sel, l1, l2, l3);  b2q_round<7>(a, b, c, d, msg, sel, l1, l2, l3);
+    b2q_round<8>(a, b, c, d, msg, sel, l1, l2, l3);  b2q_round<9>(a, b, c, d, msg, sel, l1, l2, l3);
+    b2q_round<10>(a, b, c, d, msg, sel, l1, l2, l3); b2q_round<11>(a, b, c, d, msg, sel, l1, l2, l3);
+    h_lo = h0 ^ a ^ c;
+    h_hi = iv_hi ^ b ^ d;
+}
+#endif
+
 // node = H(left || right)
 ZKB_HD void blake2b_node(const uint64_t (&l)[8], const uint64_t (&r)[8], uint64_t (&h)[8]) {
     uint64_t m[16];

@@ -187,6 +187,7 @@ void zkb_ctx_destroy(zkb_ctx* c) {
     for (auto& r : c->prof_recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
     for (auto e : c->prof_pool) cudaEventDestroy(e);
     if (c->scratch) cudaFree(c->scratch);
+    if (c->tree_bars) cudaFree(c->tree_bars);
     if (c->pinned) cudaFreeHost(c->pinned);
     if (c->own_stream) cudaStreamDestroy(c->stream);
     delete c;
@@ -218,7 +219,7 @@ int zkb_ctx_profile_read(zkb_ctx* c, int kernel_id, double* total_ms, uint64_t* 
 }
 const char* zkb_kernel_name(int kernel_id) {
     static const char* names[K_COUNT] = {"k_pow_table", "k_ntt_pass", "k_elementwise", "k_leaf8<false>", "k_leaf8<true>",
-                                         "k_node8", "k_tree", "k_open", "k_fold", "k_gather3"};
+                                         "k_node8", "k_tree", "k_open", "k_fold", "k_gather3", "k_leaf1"};
     return (kernel_id >= 0 && kernel_id < K_COUNT) ? names[kernel_id] : nullptr;
 }
 

@@ -49,6 +49,7 @@ struct zkb_ctx {
     size_t pinned_bytes = 0;
     std::vector<std::unique_ptr<zkb::PowTable>> pow_tables;
     uint64_t clock = 0;
+    uint32_t* tree_bars = nullptr;   // k_tree's arrival counter (device; zero between launches)
     uint32_t root_seq = 0;   // sequence number of the last root signalled through pinned memory
     uint64_t launches = 0;   // kernels launched through this context (bench "gpu_launches")
     // optional per-kernel-class device timing (CUDA events on the launching stream)
@@ -80,7 +81,7 @@ int set_err(zkb_ctx* c, int code, const char* fmt, ...);
 
 // kernel classes for zkb_ctx_profile_* (keep in sync with zkb_kernel_name)
 enum KernelId { K_POW_TABLE = 0, K_NTT_PASS = 1, K_ELEMENTWISE = 2, K_LEAF_TILE = 3, K_FOLD_LEAF_TILE = 4,
-                K_NODE_TILE = 5, K_MERKLE_SMALL = 6, K_OPEN = 7, K_FOLD = 8, K_GATHER = 9, K_COUNT = 10 };
+                K_NODE_TILE = 5, K_MERKLE_SMALL = 6, K_OPEN = 7, K_FOLD = 8, K_GATHER = 9, K_LEAF1 = 10, K_COUNT = 11 };
 
 // Brackets one launch with events when profiling is on; always counts the launch.
 struct LaunchScope {

@@ -23,8 +23,6 @@
 #include <string.h>
 #include "merkle.cuh"
 #include "blake2b.cuh"
-#include <cooperative_groups.h>
-namespace cg = cooperative_groups;
 
 namespace zkb {
 
@@ -174,80 +172,118 @@ __global__ void __launch_bounds__(THREADS, MINB) k_node8(const uint8_t* __restri
     g_store_digest(out, g, h);
 }
 
-// Level-by-level tree: `count` (power of two, <= 2^19) leaves or nodes -> every level up to the
-// root.  One compression per thread per level, grid-wide barrier between levels while more than
-// one CTA has work; CTA 0 finishes the last levels alone.  level_out[r] = global destination of
-// relative level r (r = 0 is the input level and is only written for leaf input).
-#define ZKB_TREE_THREADS 256
+// ---- latency-mode tree -------------------------------------------------------------------------
+// Everything above a level of <= 2^17 nodes (and, after k_leaf1, whole layers of <= 2^17 leaves)
+// is a chain of log2(n) dependent compressions with too little parallelism to fill the GPU, so
+// it is organised for latency.  The `count` input nodes are cut into <= 128 chunks (one CTA, one
+// SM each); a CTA takes its chunk into shared memory and reduces it to one node without leaving
+// the SM, each node compressed by a QUAD of lanes (blake2b_quad: ~1.2 us per level instead of
+// ~6 us for a thread-per-node level with a grid barrier); warps without a live quad skip the
+// level.  The last CTA to arrive (one atomic counter, no spinning, no cooperative launch)
+// gathers the chunk roots and finishes the tree the same way, then hands the root to the
+// polling host.  Every level is also written to global memory: the tree stores them for
+// openings.  Shared layout: digest i at 8-byte word 8i + (i >> 1), i.e. the two children of a
+// node are one contiguous 128-byte message and consecutive messages are 136 B apart (banks).
+#define ZKB_TREE_MAX_CHUNK 1024
 struct TopArgs {
-    const fe* vals;          // leaf input (or nullptr)
-    const uint8_t* nodes_in; // node input (or nullptr)
+    const uint8_t* nodes_in; // `count` input nodes (power of two, <= 2^20)
     uint32_t count;
-    uint32_t fold;           // leaf values come from folding f (written to f.next)
-    FoldArgs f;
-    uint8_t* level_out[26];
+    uint32_t chunk_log;      // nodes per CTA = 2^chunk_log (== count: a single CTA does everything)
+    uint8_t* level_out[26];  // global destination of relative level r >= 1
+    uint32_t* bar;           // arrival counter (zero between launches: the last CTA resets it)
     uint8_t* host_root;      // mapped pinned host memory (or nullptr)
     volatile uint32_t* host_flag;
     uint32_t seq;
 };
-// loads of nodes written earlier IN THIS kernel must not take the non-coherent path
-__device__ __forceinline__ void g_load_digest_coherent(const uint8_t* nodes, uint64_t idx, uint64_t* h) {
-    const uint4* src = reinterpret_cast<const uint4*>(nodes + idx * 64);
-#pragma unroll
-    for (int cidx = 0; cidx < 4; cidx++) {
-        uint4 x = __ldcg(src + cidx);
-        h[2 * cidx] = ((uint64_t)x.y << 32) | x.x;
-        h[2 * cidx + 1] = ((uint64_t)x.w << 32) | x.z;
+
+// One thread per leaf -> level-0 digests (the input of k_tree for small layers).
+template <bool FOLD>
+__global__ void __launch_bounds__(256, 2) k_leaf1(const fe* __restrict__ vals, FoldArgs f, uint32_t n, uint8_t* __restrict__ out0) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    fe v;
+    if (FOLD) {
+        fe k_m = fe_montmul(f.kk_m, pow2lvl_m(f.winv, (uint64_t)i * f.exp_mul));
+        v = fold_one(f, i, k_m);
+    } else {
+        v = fe_ldg(vals + i);
+    }
+    uint64_t h[8];
+    b2_leaf_call(&v, h);
+    g_store_digest(out0, i, h);
+}
+
+__device__ __forceinline__ uint32_t dig_word(uint32_t i) { return i * 8 + (i >> 1); }
+static size_t dig_words_host(size_t i) { return i * 8 + (i >> 1); }
+
+// Reduce `n_in` digests held in `cur` to one, level by level, in shared memory.  The k-th
+// reduction (k = 0, 1, ...) produces relative level first_level + k, written to
+// out[first_level + k] at node offset (base >> (k + 1)) + j; `base` = global index of the first
+// input digest at its level.
+__device__ __forceinline__ void reduce_in_smem(uint64_t* cur, uint64_t* nxt, uint32_t n_in, uint8_t* const* out, uint32_t first_level,
+                                               uint64_t base, const TopArgs& a, bool is_root_chunk) {
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, q = lane & 3u;
+    const uint32_t quad = tid >> 2, quads = blockDim.x >> 2, warp_quad0 = (tid >> 5) << 3;
+    uint32_t level = first_level;
+    for (uint32_t cnt = n_in >> 1; cnt >= 1; cnt >>= 1, level++) {
+        base >>= 1;
+        for (uint32_t j0 = 0; j0 < cnt; j0 += quads) {
+            if (j0 + warp_quad0 >= cnt) break;                      // no live quad in this warp
+            const uint32_t j = j0 + quad;
+            const bool live = j < cnt;
+            uint64_t h_lo, h_hi;
+            blake2b_quad(reinterpret_cast<const uint8_t*>(cur + (live ? 17u * j : 0u)), 128, lane, h_lo, h_hi);
+            if (live) {
+                uint64_t* s = nxt + dig_word(j);
+                s[q] = h_lo; s[4 + q] = h_hi;
+                unsigned long long* g = reinterpret_cast<unsigned long long*>(out[level] + (base + j) * 64);
+                g[q] = h_lo; g[4 + q] = h_hi;
+                if (cnt == 1 && is_root_chunk && a.host_root) {   // the root: hand it to the polling host
+                    unsigned long long* hr = reinterpret_cast<unsigned long long*>(a.host_root);
+                    hr[q] = h_lo; hr[4 + q] = h_hi;
+                    __threadfence_system();
+                    __syncwarp(0xFu);
+                    if (q == 0) *a.host_flag = a.seq;
+                }
+            }
+        }
+        __syncthreads();
+        uint64_t* t = cur; cur = nxt; nxt = t;
     }
 }
-__global__ void __launch_bounds__(ZKB_TREE_THREADS, 2) k_tree(TopArgs a) {
-    cg::grid_group grid = cg::this_grid();
-    const uint32_t gtid = blockIdx.x * ZKB_TREE_THREADS + threadIdx.x;
-    const uint32_t gthreads = gridDim.x * ZKB_TREE_THREADS;
-    uint64_t l[8], r[8], h[8];
-    const uint8_t* prev = a.nodes_in;
-    if (!prev) {                                   // leaf level
-        for (uint32_t i = gtid; i < a.count; i += gthreads) {
-            fe v;
-            if (a.fold) {
-                fe k_m = fe_montmul(a.f.kk_m, pow2lvl_m(a.f.winv, (uint64_t)i * a.f.exp_mul));
-                v = fold_one(a.f, i, k_m);
-            } else {
-                v = fe_ldg(a.vals + i);
-            }
-            b2_leaf_call(&v, h);
-            g_store_digest(a.level_out[0], i, h);
+__device__ __forceinline__ void load_chunk(uint64_t* buf, const uint8_t* src, uint32_t n_nodes, bool coherent) {
+    const unsigned long long* p = reinterpret_cast<const unsigned long long*>(src);
+    for (uint32_t w = threadIdx.x; w < n_nodes * 8; w += blockDim.x)
+        buf[dig_word(w >> 3) + (w & 7)] = coherent ? __ldcg(p + w) : __ldg(p + w);
+    __syncthreads();
+}
+__global__ void __launch_bounds__(512, 1) k_tree(TopArgs a) {
+    extern __shared__ uint64_t tree_smem[];
+    __shared__ uint32_t s_last;
+    const uint32_t chunk = 1u << a.chunk_log, chunks = a.count >> a.chunk_log;
+    const uint32_t nmax = chunk > chunks ? chunk : chunks;
+    uint64_t* bufA = tree_smem;
+    uint64_t* bufB = tree_smem + dig_word(nmax) + 8;
+    // stage 0: this CTA's chunk; stage 1 (last CTA to arrive only): the chunk roots
+    const uint8_t* src = a.nodes_in + (size_t)blockIdx.x * chunk * 64;
+    uint32_t n_in = chunk, first_level = 1;
+    uint64_t base = (uint64_t)blockIdx.x * chunk;
+    bool last_stage = chunks == 1;
+#pragma unroll 1
+    for (;;) {
+        load_chunk(bufA, src, n_in, first_level != 1);
+        reduce_in_smem(bufA, bufB, n_in, a.level_out, first_level, base, a, last_stage);
+        if (last_stage) return;
+        if (threadIdx.x == 0) {                // (the __syncthreads closing the reduction ordered the CTA's stores before this)
+            __threadfence();
+            const uint32_t arrived = atomicAdd(a.bar, 1u);
+            s_last = arrived == gridDim.x - 1;
+            if (s_last) { *a.bar = 0; __threadfence(); }
         }
-        prev = a.level_out[0];
-        if (a.count > 1) {
-            if (gridDim.x > 1) grid.sync(); else __syncthreads();
-        }
-    }
-    uint32_t level = 1;
-    bool alone = gridDim.x == 1;
-    for (uint32_t cnt = a.count >> 1; cnt >= 1; cnt >>= 1, level++) {
-        for (uint32_t j = gtid; j < cnt; j += gthreads) {
-            g_load_digest_coherent(prev, 2 * (uint64_t)j, l);
-            g_load_digest_coherent(prev, 2 * (uint64_t)j + 1, r);
-            b2_node_call(l, r, h);
-            g_store_digest(a.level_out[level], j, h);
-            if (cnt == 1 && a.host_root) {          // the root: hand it to the polling host
-                g_store_digest(a.host_root, 0, h);
-                __threadfence_system();
-                *a.host_flag = a.seq;
-            }
-        }
-        prev = a.level_out[level];
-        if (cnt == 1) break;
-        if (alone) {
-            __syncthreads();
-        } else if ((cnt >> 1) > ZKB_TREE_THREADS) {
-            grid.sync();                           // the next level still spans several CTAs
-        } else {
-            grid.sync();                           // last grid-wide barrier: CTA 0 goes on alone
-            if (blockIdx.x != 0) return;
-            alone = true;
-        }
+        __syncthreads();
+        if (!s_last) return;
+        src = a.level_out[a.chunk_log];
+        n_in = chunks; first_level = a.chunk_log + 1; base = 0; last_stage = true;
     }
 }
 
@@ -320,23 +356,45 @@ __global__ void __launch_bounds__(128) k_open(OpenArgs a) {
     }
 }
 
+static uint32_t tree_split_log() {   // trees of up to 2^this nodes are reduced by ONE CTA (ZKB_TREE_SPLIT_LOG)
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("ZKB_TREE_SPLIT_LOG"); v = e ? atoi(e) : 8; if (v > 10) v = 10; if (v < 1) v = 1; }
+    return (uint32_t)v;
+}
+static uint32_t tree_chunks_log() {  // larger ones are cut into 2^this chunks (ZKB_TREE_CHUNKS_LOG; 7: 128 CTAs <= 148 SMs)
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("ZKB_TREE_CHUNKS_LOG"); v = e ? atoi(e) : 7; if (v > 10) v = 10; if (v < 1) v = 1; }
+    return (uint32_t)v;
+}
 static int launch_top(zkb_ctx* c, const TopArgs& a) {
-    static int max_blocks = 0;
-    if (!max_blocks) {
-        int per_sm = 0;
-        ZKB_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_tree, ZKB_TREE_THREADS, 0));
-        max_blocks = per_sm * c->sm_count;
-        if (max_blocks < 1) return set_err(c, ZKB_ERR_CUDA, "k_tree cannot be made resident");
+    static bool attr_set = false;
+    const size_t max_smem = (size_t)(dig_words_host(ZKB_TREE_MAX_CHUNK) + 8 + dig_words_host(ZKB_TREE_MAX_CHUNK / 2) + 8) * sizeof(uint64_t);
+    if (!attr_set) {
+        ZKB_CUDA(c, cudaFuncSetAttribute(k_tree, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem));
+        attr_set = true;
     }
-    // enough CTAs for the widest level (the input level for leaves, half of it for nodes)
-    uint32_t widest = a.nodes_in ? (a.count >> 1) : a.count;
-    int blocks = (int)((widest + ZKB_TREE_THREADS - 1) / ZKB_TREE_THREADS);
-    if (blocks < 1) blocks = 1;
-    if (blocks > max_blocks) blocks = max_blocks;
-    void* args[] = {(void*)&a};
+    if (a.count > (1u << 20) || a.count < 2) return set_err(c, ZKB_ERR_ARG, "internal: k_tree takes 2..2^20 nodes");
+    const uint32_t log_c = ilog2_u64(a.count);
+    TopArgs b = a;
+    if (log_c <= tree_split_log()) b.chunk_log = log_c;
+    else {
+        b.chunk_log = log_c > tree_chunks_log() + 1 ? log_c - tree_chunks_log() : 1;
+        if (b.chunk_log > 10) b.chunk_log = 10;
+    }
+    const uint32_t chunk = 1u << b.chunk_log, chunks = a.count >> b.chunk_log;
+    const uint32_t nmax = chunk > chunks ? chunk : chunks;
+    uint32_t threads = 2 * nmax;                          // one quad per node of the widest level computed
+    if (threads < 128) threads = 128;
+    if (threads > 512) threads = 512;
+    const size_t smem = (size_t)(dig_words_host(nmax) + 8 + dig_words_host(nmax / 2) + 8) * sizeof(uint64_t);
+    if (!c->tree_bars) {
+        ZKB_CUDA(c, cudaMalloc(&c->tree_bars, 64));
+        ZKB_CUDA(c, cudaMemsetAsync(c->tree_bars, 0, 64, c->stream));
+    }
+    b.bar = c->tree_bars;
     {
         LaunchScope ls(c, K_MERKLE_SMALL);
-        ZKB_CUDA(c, cudaLaunchCooperativeKernel((const void*)k_tree, dim3(blocks), dim3(ZKB_TREE_THREADS), args, 0, c->stream));
+        k_tree<<<chunks, threads, smem, c->stream>>>(b);
     }
     ZKB_CUDA(c, cudaGetLastError());
     return 0;
@@ -364,10 +422,20 @@ int merkle_build_levels(zkb_ctx* c, const fe* vals, const FoldArgs* fold, uint64
     TopArgs a;
     memset(&a, 0, sizeof(a));
     if (signal && n > 1) { a.host_root = signal->host_root; a.host_flag = signal->host_flag; a.seq = signal->seq; }
-    if (L.top == 0) {                                   // n <= 2^19: the level-by-level kernel does everything
-        a.vals = vals; a.count = (uint32_t)n;
-        if (fold) { a.fold = 1; a.f = *fold; }
-        for (uint32_t l = 0; l <= log_n; l++) a.level_out[l] = nodes + L.level_off[l] * 64;
+    if (L.top == 0) {                                   // small layer: thread per leaf, then the latency-mode tree
+        FoldArgs fa;
+        if (fold) fa = *fold; else memset(&fa, 0, sizeof(fa));
+        {
+            LaunchScope ls(c, K_LEAF1);
+            const unsigned blocks = (unsigned)((n + 255) / 256);
+            if (fold) k_leaf1<true><<<blocks, 256, 0, c->stream>>>(nullptr, fa, (uint32_t)n, nodes + L.level_off[0] * 64);
+            else k_leaf1<false><<<blocks, 256, 0, c->stream>>>(vals, fa, (uint32_t)n, nodes + L.level_off[0] * 64);
+        }
+        ZKB_CUDA(c, cudaGetLastError());
+        if (n == 1) return 0;
+        a.nodes_in = nodes + L.level_off[0] * 64;
+        a.count = (uint32_t)n;
+        for (uint32_t l = 1; l <= log_n; l++) a.level_out[l] = nodes + L.level_off[l] * 64;
         return launch_top(c, a);
     }
     const uint64_t groups = n >> 3;

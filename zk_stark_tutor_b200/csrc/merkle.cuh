@@ -12,7 +12,7 @@ namespace zkb {
 // authentication path are recomputed at opening time from the 8 group inputs, which the tree
 // can always reach (it references the committed values).
 #define ZKB_TREE_LEAF_LOG 17     // trees up to 2^17 leaves: level-by-level kernel from the leaves
-#define ZKB_TREE_NODE_LOG 15     // larger trees: 8-ary subtree kernels down to <= 2^15 nodes, then level by level
+#define ZKB_TREE_NODE_LOG 17     // larger trees: 8-ary subtree kernels down to <= 2^17 nodes, then the latency-mode tree
 struct TreeLayout {
     uint32_t log_n = 0;
     uint32_t top = 0;            // first level handled by the level-by-level kernel (0: it starts from the leaves)
