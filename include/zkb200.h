@@ -211,6 +211,10 @@ int zkb_lde_fri_commit_ps(zkb_ctx* ctx, const zkb_fri_params* p, const void* coe
  * receives num_colinearity_tests indices (the function's return value in the reference). */
 int zkb_fri_prove(zkb_ctx* ctx, const zkb_fri_params* p, const void* codeword, size_t n, zkb_ps* ps,
                   uint64_t* top_indices_out);
+/* The opening loop of Stark::prove, stark.rs:546-560 (`for i in quadrupled_indices: push Value(cw[i]);
+ * push Path(MerkleRoot::open(i, cw))`) for one committed codeword: k indices opened in one batch from
+ * the retained tree (the reference rebuilds the tree per index), objects appended to `ps` in index order. */
+int zkb_merkle_open_ps(zkb_tree* tree, const uint64_t* idx, size_t k, zkb_ps* ps);
 
 #ifdef __cplusplus
 }

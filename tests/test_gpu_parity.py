@@ -567,6 +567,9 @@ def _stark_like_prove(B, seed, n_regs=2, omicron_len=1024, ef=4, ncc=64, trace_l
     dup = idx + [(i + ef) % fri_len for i in idx]
     quad = sorted(dup + [(i + fri_len // 2) % fri_len for i in dup])
     for cw in bq_cw + [r_cw]:
+        if "open_into" in B:                          # the same loop as one C call (zkb_merkle_open_ps)
+            B["open_into"](cw, quad, ps)
+            continue
         paths = B["open_many"](cw, quad)
         for i, path in zip(quad, paths):
             ps.push((PS.VALUE, cw[i]))
@@ -605,7 +608,74 @@ def test_stark_call_sequence_proof_bytes(ctx):
     got = _stark_like_prove(gpu, 4242)
     assert len(want) == 1156888                                   # src/rpsss.rs:89
     assert got == want
+    # the opening loop as one batched C call appending Value/Path objects itself
+    def gpu_open_into(cw, idxs, ps):
+        t = zk.MerkleTree(cw, ctx)
+        try:
+            t.open_into(idxs, ps)
+        finally:
+            t.close()
+    assert _stark_like_prove(dict(gpu, open_into=gpu_open_into), 4242) == want
     # the signature flavour (document-prefixed Fiat-Shamir, rescue_prime/proof_stream.rs)
     oracle["stream"] = lambda: PS.SignatureProofStream(b"a document")
     gpu["stream"] = lambda: zk.SignatureProofStream(b"a document")
     assert _stark_like_prove(gpu, 7) == _stark_like_prove(oracle, 7)
+
+
+# ---------------------------------------------------------------- RPSSS-shaped proof batch ---
+def _oracle_hot_path(shape, columns, combination, ps):
+    """proofs.prove_hot_path restated on the oracle (same inputs, same transcript)."""
+    n = shape.fri_len
+    w = F.primitive_nth_root(n)
+    cws = []
+    for col in columns:
+        cw = C.coset_lde(w, n, F.GENERATOR, col)
+        cws.append(cw)
+        ps.push((PS.ROOT, fastfri.Tree(cw).root))
+    fri = OFRI(F.GENERATOR, w, n, shape.ef, shape.ncc)
+    top, _, _ = fastfri.prove(fri, C.coset_lde(w, n, F.GENERATOR, combination), ps)
+    from zk_stark_tutor_b200.proofs import quadrupled_indices
+    quad = quadrupled_indices(top, n, shape.ef)
+    for cw in cws:
+        t = fastfri.Tree(cw)
+        vals = C.from_arr(cw)
+        for i in quad:
+            ps.push((PS.VALUE, vals[i]))
+            ps.push((PS.PATH, t.open(i)))
+    return top
+
+
+def test_rpsss_shaped_proof_batch(ctx):
+    """BASELINE configs[4], second half: a batch of signature-shaped proofs through the native call
+    sequence, several in flight per GPU; every proof's bytes == the oracle's, 1,156,888 bytes each."""
+    from zk_stark_tutor_b200 import proofs
+    shape = proofs.ProofShape()
+    n_proofs = 5
+    inputs = []
+    for p in range(n_proofs):
+        cols = [C.synth(0x5EED0005 + 16 * p + k, ln) for k, ln in enumerate(shape.column_lengths())]
+        inputs.append((cols, C.synth(0x5EED0005 + 16 * p + 15, shape.comb_len)))
+    want = []
+    for cols, comb in inputs[:2]:
+        ops = PS.SignatureProofStream(b"a document")
+        top = _oracle_hot_path(shape, cols, comb, ops)
+        want.append((top, ops.digest()))
+    assert len(want[0][1]) == 1156888                                   # src/rpsss.rs:89
+    w = F.primitive_nth_root(shape.fri_len)
+    fri = zk.FRI(F.GENERATOR, w, shape.fri_len, shape.ef, shape.ncc, ctx)
+    for (cols, comb), (top, digest) in zip(inputs[:2], want):
+        ps = zk.SignatureProofStream(b"a document")
+        assert proofs.prove_hot_path(ctx, fri, shape, cols, comb, ps) == top
+        assert ps.digest() == digest
+    # the whole batch, 3 lanes, device-resident inputs; lanes must not disturb each other
+    import torch
+    torch.cuda.synchronize()
+    pipe = proofs.ProofPipeline(0, shape, F.GENERATOR, w, lanes=3)
+    dev_inputs = [([cuda(c) for c in cols], cuda(comb)) for cols, comb in inputs]
+    got = pipe.run(dev_inputs, lambda: zk.SignatureProofStream(b"a document"), keep_digest=True)
+    again = pipe.run(dev_inputs, lambda: zk.SignatureProofStream(b"a document"), keep_digest=True)
+    pipe.close()
+    assert [g[0] for g in got] == [1156888] * n_proofs
+    assert got[0][1] == want[0][1] and got[1][1] == want[1][1]
+    assert [g[1] for g in got] == [g[1] for g in again]
+    assert len({g[1] for g in got}) == n_proofs

@@ -56,6 +56,7 @@ PROTOTYPES = {
     "zkb_merkle_build": (ctypes.c_int, [vp, vp, sz, ctypes.POINTER(vp)]),
     "zkb_merkle_root": (ctypes.c_int, [vp, c_u8p]),
     "zkb_merkle_open": (ctypes.c_int, [vp, c_u64p, sz, c_u8p]),
+    "zkb_merkle_open_ps": (ctypes.c_int, [vp, c_u64p, sz, vp]),
     "zkb_merkle_free": (None, [vp]),
     "zkb_merkle_verify": (ctypes.c_int, [c_u8p, u64, c_u8p, sz, c_u8p]),
     "zkb_blake2b512": (None, [c_u8p, sz, c_u8p]),

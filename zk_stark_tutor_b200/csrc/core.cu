@@ -1,5 +1,6 @@
 // core.cu - context lifecycle, scratch arena, power-table cache, host scalar helpers.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 #include "ctx.hpp"
 
@@ -59,6 +60,29 @@ bool is_device_ptr(const void* p) {
     cudaError_t e = cudaPointerGetAttributes(&a, p);
     if (e != cudaSuccess) { cudaGetLastError(); return false; }
     return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+// Pinned (page-locked, UVA-mapped) host memory can be read by a kernel in place over PCIe.
+// Returns the device alias of `p`, or nullptr if `p` is not such memory (ZKB_ZERO_COPY=0 disables).
+const void* pinned_device_alias(const void* p) {
+    static int on = -1;
+    if (on < 0) { const char* e = getenv("ZKB_ZERO_COPY"); on = e ? atoi(e) : 1; }
+    if (!on) return nullptr;
+    cudaPointerAttributes a;
+    cudaError_t e = cudaPointerGetAttributes(&a, p);
+    if (e != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return a.type == cudaMemoryTypeHost ? a.devicePointer : nullptr;
+}
+
+// For inputs the consuming kernel reads exactly ONCE (the coefficients of an LDE): pinned host
+// memory is handed to the kernel as is, so the PCIe transfer overlaps the first NTT pass instead
+// of preceding it; pageable memory is staged as usual.
+int stage_in_once(zkb_ctx* c, const void* p, size_t bytes, DevBuf& buf, const void** dev) {
+    if (bytes >= (1u << 20)) {
+        const void* alias = pinned_device_alias(p);
+        if (alias) { *dev = alias; return 0; }
+    }
+    return stage_in(c, p, bytes, buf, dev);
 }
 
 int stage_in(zkb_ctx* c, const void* p, size_t bytes, DevBuf& buf, const void** dev) {

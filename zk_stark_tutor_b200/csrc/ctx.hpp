@@ -113,6 +113,8 @@ struct DevBuf {
 // If `p` is a host pointer, stage it into `buf` (async on the ctx stream) and return the
 // device pointer; device pointers are passed through.
 int stage_in(zkb_ctx* c, const void* p, size_t bytes, DevBuf& buf, const void** dev);
+int stage_in_once(zkb_ctx* c, const void* p, size_t bytes, DevBuf& buf, const void** dev);   // pinned host memory is read in place
+const void* pinned_device_alias(const void* p);
 
 // ---- host-side field helpers (canonical values) built on the verified host path of
 // fe128.cuh

@@ -162,7 +162,7 @@ static int fri_commit_impl(zkb_ctx* c, const zkb_fri_params* p, const void* code
             if (e != cudaSuccess) return fail(set_err(c, ZKB_ERR_CUDA, "memset failed: %s", cudaGetErrorString(e)));
         } else {
             const void* d_coeffs = nullptr;
-            int rc = stage_in(c, coeffs, n_coeffs * sizeof(fe), staged_coeffs, &d_coeffs);
+            int rc = stage_in_once(c, coeffs, n_coeffs * sizeof(fe), staged_coeffs, &d_coeffs);
             if (rc) return fail(rc);
             NttOpts o;
             o.has_scale = true;

@@ -21,8 +21,10 @@
 //             walked with maximal parallelism per level instead of per-thread subtrees.
 #include <stdlib.h>
 #include <string.h>
+#include <vector>
 #include "merkle.cuh"
 #include "blake2b.cuh"
+#include "hosthash.hpp"
 
 namespace zkb {
 
@@ -356,6 +358,12 @@ __global__ void __launch_bounds__(128) k_open(OpenArgs a) {
     }
 }
 
+// values at k indices -> contiguous (for the Value objects of the Stark query phase)
+__global__ void k_gather_vals(const fe* __restrict__ vals, const uint64_t* __restrict__ idx, uint32_t k, fe* __restrict__ out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < k) fe_store(out + i, fe_ldg(vals + idx[i]));
+}
+
 static uint32_t tree_split_log() {   // trees of up to 2^this nodes are reduced by ONE CTA (ZKB_TREE_SPLIT_LOG)
     static int v = -1;
     if (v < 0) { const char* e = getenv("ZKB_TREE_SPLIT_LOG"); v = e ? atoi(e) : 8; if (v > 10) v = 10; if (v < 1) v = 1; }
@@ -427,9 +435,11 @@ int merkle_build_levels(zkb_ctx* c, const fe* vals, const FoldArgs* fold, uint64
         if (fold) fa = *fold; else memset(&fa, 0, sizeof(fa));
         {
             LaunchScope ls(c, K_LEAF1);
-            const unsigned blocks = (unsigned)((n + 255) / 256);
-            if (fold) k_leaf1<true><<<blocks, 256, 0, c->stream>>>(nullptr, fa, (uint32_t)n, nodes + L.level_off[0] * 64);
-            else k_leaf1<false><<<blocks, 256, 0, c->stream>>>(vals, fa, (uint32_t)n, nodes + L.level_off[0] * 64);
+            // latency-bound: small layers go out one warp per CTA so every warp gets a scheduler of its own
+            const unsigned threads = n <= (1u << 14) ? 32u : n <= (1u << 15) ? 64u : 256u;
+            const unsigned blocks = (unsigned)((n + threads - 1) / threads);
+            if (fold) k_leaf1<true><<<blocks, threads, 0, c->stream>>>(nullptr, fa, (uint32_t)n, nodes + L.level_off[0] * 64);
+            else k_leaf1<false><<<blocks, threads, 0, c->stream>>>(vals, fa, (uint32_t)n, nodes + L.level_off[0] * 64);
         }
         ZKB_CUDA(c, cudaGetLastError());
         if (n == 1) return 0;
@@ -575,6 +585,37 @@ int zkb_merkle_open(zkb_tree* t, const uint64_t* idx, size_t k, uint8_t* paths_o
     ZKB_TRY(merkle_open_device(c, t->vals, t->layout, t->nodes, d_idx, k, d_out));
     ZKB_CUDA(c, cudaMemcpyAsync(paths_out, d_out, k * path_bytes, cudaMemcpyDeviceToHost, c->stream));
     ZKB_CUDA(c, cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+// stark.rs:546-560: for every opened index push Value(codeword[i]) then Path(open(i)); one batched
+// opening + one D2H instead of k tree rebuilds.
+int zkb_merkle_open_ps(zkb_tree* t, const uint64_t* idx, size_t k, zkb_ps* ps) {
+    if (!t || !ps || (k && !idx)) return ZKB_ERR_ARG;
+    zkb_ctx* c = t->ctx;
+    if (t->n < 2) return set_err(c, ZKB_ERR_INDEX, "open on a 1-leaf tree (the reference recurses forever)");
+    for (size_t i = 0; i < k; i++)
+        if (idx[i] >= t->n) return set_err(c, ZKB_ERR_INDEX, "cannot open invalid index %llu", (unsigned long long)idx[i]);
+    if (k == 0) return 0;
+    ZKB_CUDA(c, cudaSetDevice(c->device));
+    const size_t depth = t->layout.log_n, path_bytes = depth * 64;
+    DevBuf buf;
+    const size_t idx_bytes = (k * 8 + 63) & ~(size_t)63, val_bytes = (k * 16 + 63) & ~(size_t)63;
+    ZKB_TRY(buf.alloc(c, idx_bytes + val_bytes + k * path_bytes));
+    uint64_t* d_idx = (uint64_t*)buf.p;
+    fe* d_vals = (fe*)((uint8_t*)buf.p + idx_bytes);
+    uint8_t* d_paths = (uint8_t*)buf.p + idx_bytes + val_bytes;
+    ZKB_CUDA(c, cudaMemcpyAsync(d_idx, idx, k * 8, cudaMemcpyHostToDevice, c->stream));
+    { LaunchScope ls(c, K_GATHER); k_gather_vals<<<(unsigned)((k + 127) / 128), 128, 0, c->stream>>>(t->vals, d_idx, (uint32_t)k, d_vals); }
+    ZKB_CUDA(c, cudaGetLastError());
+    ZKB_TRY(merkle_open_device(c, t->vals, t->layout, t->nodes, d_idx, k, d_paths));
+    std::vector<uint8_t> host(val_bytes + k * path_bytes);
+    ZKB_CUDA(c, cudaMemcpyAsync(host.data(), d_vals, host.size(), cudaMemcpyDeviceToHost, c->stream));
+    ZKB_CUDA(c, cudaStreamSynchronize(c->stream));
+    for (size_t i = 0; i < k; i++) {
+        zkb_ps_push_value(ps, host.data() + 16 * i);
+        zkb_ps_push_path(ps, host.data() + val_bytes + i * path_bytes, depth);
+    }
     return 0;
 }
 

@@ -617,14 +617,14 @@ int zkb_coset_lde_batch(zkb_ctx* c, const uint8_t omega[16], uint64_t order, con
         if (!coeffs) return ZKB_ERR_ARG;
         const void* d_in = nullptr;
         size_t in_elems = batch > 1 ? in_stride * (batch - 1) + n_coeffs : n_coeffs;
-        ZKB_TRY(stage_in(c, coeffs, in_elems * sizeof(fe), bin, &d_in));
+        ZKB_TRY(stage_in_once(c, coeffs, in_elems * sizeof(fe), bin, &d_in));   // read once, by the first pass
         NttOpts o;
         o.has_scale = true;
         o.scale_base = h_load(offset);
         ZKB_TRY(ntt_exec(c, h_load(omega), (const fe*)d_in, n_coeffs, in_stride, d_out, out_stride, batch, ilog2_u64(order), o));
     }
     if (!out_dev) ZKB_CUDA(c, cudaMemcpyAsync(out, d_out, out_elems * sizeof(fe), cudaMemcpyDeviceToHost, c->stream));
-    if (!out_dev || bin.p) ZKB_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (!out_dev || (coeffs && !is_device_ptr(coeffs))) ZKB_CUDA(c, cudaStreamSynchronize(c->stream));
     return 0;
 }
 

@@ -38,6 +38,14 @@ class MerkleTree:
     def open(self, index):
         return self.open_many([index])[0]
 
+    def open_into(self, indices, proof_stream):
+        """The opening loop of Stark::prove (stark.rs:546-560): for i in indices push Value(leaf i)
+        then Path(open(i)) onto the library's proof stream, one batched opening."""
+        k = len(indices)
+        idx = (ctypes.c_uint64 * max(k, 1))(*indices)
+        self.ctx.check(self.ctx.lib.zkb_merkle_open_ps(self.h, idx, k, proof_stream.h))
+        proof_stream.objects = None
+
     def close(self):
         if self.h is not None and self.h.value:
             self.ctx.lib.zkb_merkle_free(self.h)
