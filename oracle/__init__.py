@@ -17,6 +17,10 @@ and there is no rustc/cargo in this image, so it cannot be compiled or imported)
                              src/rescue_prime/proof_stream.rs, src/utils/digest.rs,
                              src/crypto/shake256.rs
 * ``oracle.fri``          <- src/fri.rs
+* ``oracle.mpoly``        <- src/m_polynomial.rs, src/utils/matrix.rs, src/utils/bit_iter.rs
+* ``oracle.rescue_prime`` <- src/rescue_prime/rescue_prime.rs
+* ``oracle.stark``        <- src/stark/stark.rs (prove AND verify), src/rpsss.rs: the CALLERS of the
+                             hot path, restated so the real prover can be run with either backend
 * ``oracle/zkoracle.c``   <- the same semantics in C (unsigned __int128) for sizes
                              where Python is too slow, plus a faithful-algorithm
                              (bit-serial mul_mod, per-element pow / xgcd) variant
@@ -26,7 +30,10 @@ Pinning: every known-answer test the reference holds for this path
 (src/fft/ntt.rs:78-130, src/merkle_root.rs:107-244, src/fri.rs:426-448,
 src/field/field.rs:186-241, src/field/field_element.rs:151-299,
 src/crypto/blake2b512.rs:22-30, src/proof_stream.rs:129-145, the 1,156,888-byte
-proof size of src/rpsss.rs:89) is asserted in tests/test_oracle_kat.py.
+proof size of src/rpsss.rs:89) is asserted in tests/test_oracle_kat.py; the callers' known
+answers (src/rescue_prime/rescue_prime.rs:298-423, src/m_polynomial.rs:330-560,
+src/utils/matrix.rs:110-183, the sign/verify round trip of src/rpsss.rs:103-135) in
+tests/test_oracle_stark.py.
 Third-party hashes the reference takes from crates.io (blake2 0.10.6 Blake2b512,
 sha3 0.10.8 Shake256, both pinned in Cargo.lock) are the standard RFC 7693 /
 FIPS 202 functions; here they come from ``hashlib`` and are pinned by the same KATs.

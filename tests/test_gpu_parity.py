@@ -679,3 +679,67 @@ def test_rpsss_shaped_proof_batch(ctx):
     assert got[0][1] == want[0][1] and got[1][1] == want[1][1]
     assert [g[1] for g in got] == [g[1] for g in again]
     assert len({g[1] for g in got}) == n_proofs
+
+
+# ---------------------------------------------------------------- the real callers ----------
+def _gpu_backend(ctx):
+    """The hot-path functions Stark / RPSSS call (oracle.stark.Backend), served by the CUDA path
+    through the mirror of the reference's API."""
+    class GpuBackend:
+        name = "gpu"
+        fast_zerofier = staticmethod(lambda root, order, domain: zk.fast_zerofier(root, order, domain, ctx))
+        fast_interpolate_domain = staticmethod(lambda root, order, dom, vals: zk.fast_interpolate_domain(root, order, dom, vals, ctx))
+        fast_coset_divide = staticmethod(lambda root, order, off, a, b: zk.fast_coset_divide(root, order, off, a, b, ctx))
+        fast_coset_evaluate = staticmethod(lambda w, n, off, p: zk.fast_coset_evaluate(w, n, off, p, ctx))
+        fast_multiply = staticmethod(lambda root, order, a, b: zk.fast_multiply(root, order, a, b, ctx))
+        commit = staticmethod(lambda cw: zk.MerkleRoot.commit(cw, ctx))
+
+        @staticmethod
+        def open_many(cw, idxs):
+            t = zk.MerkleTree(cw, ctx)
+            try:
+                return t.open_many(idxs)
+            finally:
+                t.close()
+
+        @staticmethod
+        def fri(offset, omega, n, ef, ncc):
+            return zk.FRI(offset, omega, n, ef, ncc, ctx=ctx)
+    return GpuBackend
+
+
+def test_rpsss_signature_gpu_backend(ctx):
+    """BASELINE configs[0] / configs[4]: the Rescue-Prime STARK signature (src/rpsss.rs:70-87 ->
+    Stark::prove, stark.rs:276-563) with every hot-path call - interpolation, zerofiers, coset
+    division, the products inside the AIR evaluation, LDEs, Merkle commits and openings, FRI::prove -
+    served by the CUDA path: the 1,156,888-byte signature is byte-identical to the oracle-backed one
+    and the restated Stark::verify (stark.rs:565-770) accepts it for the right document only."""
+    from oracle.stark import RPSSS, deterministic_rng
+    cpu = RPSSS(4, 64, 128, 3)
+    gpu = RPSSS(4, 64, 128, 3, backend=_gpu_backend(ctx))
+    assert [t.dictionary for t in gpu.transition_constraints()] == [t.dictionary for t in cpu.transition_constraints()]
+    sk, pk = cpu.keygen(deterministic_rng(b"k"))
+    doc = b"Hello, World!"
+    want = cpu.sign(sk, doc, deterministic_rng(b"r"))
+    got = gpu.sign(sk, doc, deterministic_rng(b"r"), make_stream=zk.SignatureProofStream)
+    assert len(got) == 1156888
+    assert got == want
+    assert cpu.verify(pk, doc, got) is None
+    assert cpu.verify(pk, b"Malicious document", got) is not None
+
+
+def test_stark_prove_gpu_backend_independent_stream(ctx):
+    """Stark::prove on a Rescue-Prime hash trace over an IndependentProofStream (stark.rs:810-880), GPU-backed."""
+    from oracle.rescue_prime import RescuePrime
+    from oracle.stark import Stark, deterministic_rng
+    B = _gpu_backend(ctx)
+    rp = RescuePrime(2, 1, 128, 27, interpolate=B.fast_interpolate_domain)
+    x = 0xFEEDFACE12345
+    out = rp.hash(x)
+    got_stark = Stark(4, 64, 128, rp.m, rp.N + 1, 3, backend=B)
+    ref_stark = Stark(4, 64, 128, rp.m, rp.N + 1, 3)
+    tcs = rp.transition_constraints(ref_stark.omicron, ref_stark.omicron_domain_length)
+    got = got_stark.prove(rp.trace(x), tcs, rp.boundary_constraints(out), zk.IndependentProofStream(), deterministic_rng(b"z"))
+    want = ref_stark.prove(rp.trace(x), tcs, rp.boundary_constraints(out), PS.IndependentProofStream(), deterministic_rng(b"z"))
+    assert got == want
+    assert ref_stark.verify(tcs, rp.boundary_constraints(out), PS.IndependentProofStream(PS.parse(got))) is None
