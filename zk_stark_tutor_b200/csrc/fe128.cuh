@@ -13,9 +13,9 @@
 // p > 2^127, so a+b can exceed 2^128: add/sub carry a real carry-out and do one
 // conditional correction; no lazy [0,2p) representation fits in four limbs.
 //
-// Montgomery reduction exploits p = 1 (mod 2^96): -p^-1 = -1 (mod 2^96), so
-// m = -T mod 2^96 cancels three limbs at once with three products m_i * 0xCB800000,
-// then one more 32-bit step; 16 + 4 = 20 32x32 products per field multiplication.
+// Montgomery reduction exploits p = 1 + c*2^119: p^-1 = 1 - c*2^119 (mod 2^128), so the
+// multiplier m = -T_lo * p^-1 is a negation plus one 32-bit multiply-add, and m*p costs four
+// products m_i * 0xCB800000; 16 + 4 (+1 low) 32x32 products per field multiplication.
 #pragma once
 #include <stdint.h>
 
@@ -140,8 +140,10 @@ ZKB_HD fe fe_half(const fe& a) {
 // ("even" holds a_i*b_j with i+j even at limb i+j, "odd" those with i+j odd) so that every
 // 32x32->64 product lands on a fixed, aligned register pair and maps to one IMAD.WIDE with
 // carry-out, rows chained by carry; the two are merged with one 7-limb add.  The reduction
-// uses p = 1 (mod 2^96): m = -T mod 2^96 clears three limbs with three products m_i*P3, a
-// fourth clears limb 3; one conditional subtraction makes the result canonical.
+// uses the shape of p = 1 + c*2^119: p^-1 mod 2^128 = 1 - c*2^119, so the full Montgomery
+// multiplier m = -T_lo/p is a 128-bit negation plus ONE 32-bit multiply-add on limb 3, and
+// m*p = m + (m*P3 << 96) needs four products m_i*P3 accumulated straight onto T[4..7];
+// one conditional subtraction makes the result canonical.  36 ALU-pipe + 20 IMAD.WIDE.
 __device__ __forceinline__ fe fe_montmul_ptx(const fe& a, const fe& b) {
     fe r;
     asm("{\n\t"
@@ -180,22 +182,25 @@ __device__ __forceinline__ fe fe_montmul_ptx(const fe& a, const fe& b) {
         "add.cc.u32 t1, e1, o0;\n\t"  "addc.cc.u32 t2, e2, o1;\n\t" "addc.cc.u32 t3, e3, o2;\n\t"
         "addc.cc.u32 t4, e4, o3;\n\t" "addc.cc.u32 t5, e5, o4;\n\t" "addc.cc.u32 t6, e6, o5;\n\t"
         "addc.u32 t7, e7, o6;\n\t"
-        // ---- m = -T mod 2^96 ; nz = (T mod 2^96 != 0)
+        // ---- m = -T_lo * p^-1 mod 2^128.  p = 1 + c*2^119 so p^-1 = 1 - c*2^119 (mod 2^128) and
+        //      m = -T_lo + ((c*T_lo mod 2^9) << 119) = -T_lo + (lo32(P3*t0) << 96): one 128-bit negation
+        //      (nz = borrow = T_lo != 0) and one 32-bit add on limb 3 (carry-out co is discarded mod 2^128)
         "sub.cc.u32 m0, 0, e0;\n\t" "subc.cc.u32 m1, 0, t1;\n\t" "subc.cc.u32 m2, 0, t2;\n\t"
-        "subc.u32 nz, 0, 0;\n\t"    "and.b32 nz, nz, 1;\n\t"
-        "mul.wide.u32 w0, m0, 0xCB800000;\n\t" "mov.b64 {q0l,q0h}, w0;\n\t"
-        "mul.wide.u32 w1, m1, 0xCB800000;\n\t" "mov.b64 {q1l,q1h}, w1;\n\t"
-        "mul.wide.u32 w2, m2, 0xCB800000;\n\t" "mov.b64 {q2l,q2h}, w2;\n\t"
-        // U = T[3..7] + nz + (m * P3) : two carry chains
-        "add.cc.u32 u3, t3, q0l;\n\t"  "addc.cc.u32 u4, t4, q0h;\n\t" "addc.cc.u32 u5, t5, q1h;\n\t"
-        "addc.cc.u32 u6, t6, q2h;\n\t" "addc.cc.u32 u7, t7, 0;\n\t"   "addc.u32 u8, 0, 0;\n\t"
-        "add.cc.u32 u3, u3, nz;\n\t"   "addc.cc.u32 u4, u4, q1l;\n\t" "addc.cc.u32 u5, u5, q2l;\n\t"
-        "addc.cc.u32 u6, u6, 0;\n\t"   "addc.cc.u32 u7, u7, 0;\n\t"   "addc.u32 u8, u8, 0;\n\t"
-        // ---- clear limb 3: m3 = -u3, carry c3 = (u3 != 0), m3*P3 lands on limbs 6,7
-        "sub.cc.u32 m3, 0, u3;\n\t" "subc.u32 c3, 0, 0;\n\t" "and.b32 c3, c3, 1;\n\t"
-        "mul.wide.u32 w3, m3, 0xCB800000;\n\t" "mov.b64 {q3l,q3h}, w3;\n\t"
-        "add.cc.u32 r0, u4, c3;\n\t"  "addc.cc.u32 r1, u5, 0;\n\t" "addc.cc.u32 r2, u6, q3l;\n\t"
-        "addc.cc.u32 r3, u7, q3h;\n\t" "addc.u32 top, u8, 0;\n\t"
+        "subc.cc.u32 m3, 0, t3;\n\t" "subc.u32 nz, 0, 0;\n\t"
+        "mul.lo.u32 d0, e0, 0xCB800000;\n\t"
+        "add.cc.u32 m3, m3, d0;\n\t" "addc.u32 c3, 0, 0;\n\t"
+        // T_lo + m = (d0 << 96) + k*2^128 with k = nz - co
+        "and.b32 nz, nz, 1;\n\t" "sub.u32 k, nz, c3;\n\t"
+        // (T + m*p) >> 128 = T[4..7] + k + ((d0 + m0*P3) >> 32) + m1*P3 + (m2*P3 << 32) + (m3*P3 << 64):
+        // limb 3 cancels inside the first wide multiply-add (addend {d0, k}); the other three products
+        // are accumulated straight onto T[4..7] in two carry chains
+        "mov.b64 w1, {d0, k};\n\t" "mad.wide.u32 w0, m0, 0xCB800000, w1;\n\t" "mov.b64 {q0l,q0h}, w0;\n\t"
+        "mad.lo.cc.u32 r0, m1, 0xCB800000, t4;\n\t"  "madc.hi.cc.u32 r1, m1, 0xCB800000, t5;\n\t"
+        "madc.lo.cc.u32 r2, m3, 0xCB800000, t6;\n\t" "madc.hi.cc.u32 r3, m3, 0xCB800000, t7;\n\t"
+        "addc.u32 top, 0, 0;\n\t"
+        "add.cc.u32 r0, r0, q0h;\n\t"
+        "madc.lo.cc.u32 r1, m2, 0xCB800000, r1;\n\t" "madc.hi.cc.u32 r2, m2, 0xCB800000, r2;\n\t"
+        "addc.cc.u32 r3, r3, 0;\n\t" "addc.u32 top, top, 0;\n\t"
         // ---- conditional subtraction of p = {1, 0, 0, P3}: keep r iff (top:r) < p
         "sub.cc.u32 d0, r0, 1;\n\t" "subc.cc.u32 d1, r1, 0;\n\t" "subc.cc.u32 d2, r2, 0;\n\t"
         "subc.cc.u32 d3, r3, 0xCB800000;\n\t" "subc.u32 k, top, 0;\n\t"

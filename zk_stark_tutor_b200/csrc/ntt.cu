@@ -170,28 +170,65 @@ __global__ void __launch_bounds__(ZKB_NTT_THREADS) k_ntt_pass(const PassParams p
 // multiplication sites; inlined that is 190 KB of SASS and the pass stalls on instruction
 // fetch (ncu: no_instruction is the top stall) - as calls it fits the instruction cache.
 __device__ __noinline__ fe mm(fe a, fe b) { return fe_montmul(a, b); }
+// Two independent products per call: the two carry chains interleave (ILP 2) and the call overhead halves.
+struct fe2 { fe a, b; };
+__device__ __noinline__ fe2 mm2(fe a0, fe b0, fe a1, fe b1) {
+    fe2 r;
+    r.a = fe_montmul(a0, b0);
+    r.b = fe_montmul(a1, b1);
+    return r;
+}
 
 __device__ __forceinline__ fe pow2lvl_c(const DevPow& t, uint64_t e) {
     fe lo = fe_ldg(t.lo + (e & ((1ull << t.lo_bits) - 1)));
     fe hi = fe_ldg(t.hi + (e >> t.lo_bits));
     return mm(hi, lo);
 }
+// position (in x[]) of the k-th butterfly of stage lh that needs a multiplication (j != 0), and its twiddle index
+template <int LOGR, int LH> __host__ __device__ constexpr int mul_bfly(int k) {
+    // butterflies i = 0 .. R/2-1 with j = i & (h-1) != 0, in order
+    int seen = 0;
+    for (int i = 0; i < (1 << (LOGR - 1)); i++) {
+        if ((i & ((1 << LH) - 1)) == 0) continue;
+        if (seen == k) return i;
+        seen++;
+    }
+    return -1;
+}
+template <int LOGR, int LH>
+__device__ __forceinline__ void dft_stage(fe (&x)[1 << LOGR], const fe* __restrict__ tw, uint32_t tw_stride) {
+    constexpr int R = 1 << LOGR, h = 1 << LH;
+#pragma unroll
+    for (int i = 0; i < R / 2; i++) {
+        const int j = i & (h - 1);
+        const int s0 = ((i >> LH) << (LH + 1)) | j;
+        fe u = x[s0], v = x[s0 + h];
+        x[s0] = fe_add(u, v);
+        x[s0 + h] = fe_sub(u, v);
+    }
+    constexpr int NM = R / 2 - R / (2 * h);                  // butterflies with j != 0
+#pragma unroll
+    for (int k = 0; k + 1 < NM; k += 2) {
+        constexpr int dummy = 0; (void)dummy;
+        const int i0 = mul_bfly<LOGR, LH>(k), i1 = mul_bfly<LOGR, LH>(k + 1);
+        const int j0 = i0 & (h - 1), j1 = i1 & (h - 1);
+        const int p0 = (((i0 >> LH) << (LH + 1)) | j0) + h, p1 = (((i1 >> LH) << (LH + 1)) | j1) + h;
+        fe2 r = mm2(x[p0], tw[(uint32_t)(j0 << (LOGR - 1 - LH)) * tw_stride], x[p1], tw[(uint32_t)(j1 << (LOGR - 1 - LH)) * tw_stride]);
+        x[p0] = r.a; x[p1] = r.b;
+    }
+    if (NM & 1) {
+        const int i0 = mul_bfly<LOGR, LH>(NM - 1);
+        const int j0 = i0 & (h - 1);
+        const int p0 = (((i0 >> LH) << (LH + 1)) | j0) + h;
+        x[p0] = mm(x[p0], tw[(uint32_t)(j0 << (LOGR - 1 - LH)) * tw_stride]);
+    }
+}
 template <int LOGR>
 __device__ __forceinline__ void dft_dif(fe (&x)[1 << LOGR], const fe* __restrict__ tw, uint32_t tw_stride) {
-    constexpr int R = 1 << LOGR;
-#pragma unroll
-    for (int lh = LOGR - 1; lh >= 0; lh--) {
-        const int h = 1 << lh;
-#pragma unroll
-        for (int i = 0; i < R / 2; i++) {
-            const int j = i & (h - 1);
-            const int s0 = ((i >> lh) << (lh + 1)) | j;
-            fe u = x[s0], v = x[s0 + h];
-            x[s0] = fe_add(u, v);
-            fe d = fe_sub(u, v);
-            x[s0 + h] = (j == 0) ? d : mm(d, tw[(uint32_t)(j << (LOGR - 1 - lh)) * tw_stride]);
-        }
-    }
+    if constexpr (LOGR >= 4) dft_stage<LOGR, 3>(x, tw, tw_stride);
+    if constexpr (LOGR >= 3) dft_stage<LOGR, 2>(x, tw, tw_stride);
+    if constexpr (LOGR >= 2) dft_stage<LOGR, 1>(x, tw, tw_stride);
+    dft_stage<LOGR, 0>(x, tw, tw_stride);
 }
 template <int LOGR> __host__ __device__ constexpr int brev_c(int i) {
     int r = 0;
@@ -255,8 +292,8 @@ __global__ void __launch_bounds__(ZKB_NTT_THREADS, 2) k_ntt_rr(const PassParams 
         for (uint32_t kb = 0; kb < R2; kb++) {
             fe y = x[brev_c<LR2>(kb)];
             if (p.has_tw) {
-                y = mm(y, t);
-                if (kb + 1 < R2) t = mm(t, step);
+                if (kb + 1 < R2) { fe2 r = mm2(y, t, t, step); y = r.a; t = r.b; }
+                else y = mm(y, t);
             }
             if (p.has_post) y = mm(y, p.post);
             fe_store(out + (uint64_t)(ka + R1 * kb) * p.st_k + (uint64_t)b * p.st_b, y);
