@@ -59,6 +59,11 @@ const char* zkb_last_error(const zkb_ctx* ctx);
 int zkb_ctx_sync(zkb_ctx* ctx);                       /* cudaStreamSynchronize             */
 uint64_t zkb_ctx_launches(const zkb_ctx* ctx);        /* kernels launched so far           */
 const char* zkb_version(void);
+/* Pinned (page-locked) host coefficients handed to zkb_coset_lde* / zkb_lde_fri_commit* are by default
+ * read in place by the first NTT pass (the PCIe transfer overlaps that pass).  A caller that keeps several
+ * contexts busy on one GPU (column / proof pipelines) gets better overlap from staged copies on the copy
+ * engines: enable = 0 restores the explicit H2D copy for this context. */
+int zkb_ctx_zero_copy_inputs(zkb_ctx* ctx, int enable);
 /* Per-kernel-class device timing (CUDA events on the context's stream around every launch;
  * this is what bench.py's roofline.achieved is computed from).  enable: 0 = off, 1 = on,
  * 2 = on + reset the accumulators.  zkb_kernel_name(id) is NULL past the last class. */

@@ -39,6 +39,8 @@ class ColumnPipeline:
         import zk_stark_tutor_b200 as zk
         self.zk = zk
         self.ctxs = [zk.Context(device, stream="own") for _ in range(lanes)]
+        for c in self.ctxs:      # with several lanes the copy engines overlap a staged H2D with the other lanes' kernels
+            c.check(c.lib.zkb_ctx_zero_copy_inputs(c.h, 0))
         offset, omega, n, ef, ncc = fri_params
         self.fris = [zk.FRI(offset, omega, n, ef, ncc, c) for c in self.ctxs]
 

@@ -78,7 +78,7 @@ const void* pinned_device_alias(const void* p) {
 // memory is handed to the kernel as is, so the PCIe transfer overlaps the first NTT pass instead
 // of preceding it; pageable memory is staged as usual.
 int stage_in_once(zkb_ctx* c, const void* p, size_t bytes, DevBuf& buf, const void** dev) {
-    if (bytes >= (1u << 20)) {
+    if (c->zero_copy_inputs && bytes >= (1u << 20)) {
         const void* alias = pinned_device_alias(p);
         if (alias) { *dev = alias; return 0; }
     }
@@ -239,6 +239,11 @@ int zkb_ctx_profile_read(zkb_ctx* c, int kernel_id, double* total_ms, uint64_t* 
     ZKB_TRY(prof_collect(c));
     if (total_ms) *total_ms = c->prof_ms[kernel_id];
     if (count) *count = c->prof_count[kernel_id];
+    return 0;
+}
+int zkb_ctx_zero_copy_inputs(zkb_ctx* c, int enable) {
+    if (!c) return ZKB_ERR_ARG;
+    c->zero_copy_inputs = enable != 0;
     return 0;
 }
 const char* zkb_kernel_name(int kernel_id) {

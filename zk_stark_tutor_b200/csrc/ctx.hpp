@@ -49,6 +49,7 @@ struct zkb_ctx {
     size_t pinned_bytes = 0;
     std::vector<std::unique_ptr<zkb::PowTable>> pow_tables;
     uint64_t clock = 0;
+    bool zero_copy_inputs = true;    // pinned host LDE inputs are read in place by the first NTT pass (zkb_ctx_zero_copy_inputs)
     uint32_t* tree_bars = nullptr;   // k_tree's arrival counter (device; zero between launches)
     uint32_t root_seq = 0;   // sequence number of the last root signalled through pinned memory
     uint64_t launches = 0;   // kernels launched through this context (bench "gpu_launches")
