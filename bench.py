@@ -60,7 +60,8 @@ def parse():
                          "round-robin to the ranks (strong scaling); ntt: configs[1], forward + inverse NTT of 2^log_n per rank; "
                          "ntt4step: configs[4], ONE 2^log_n NTT (default 2^26) across all ranks, NCCL all-to-all; "
                          "proofs: configs[4], a batch of --proofs RPSSS-shaped signature proofs (4096-point FRI domain) dealt round-robin to the ranks")
-    ap.add_argument("--proofs", type=int, default=256)
+    ap.add_argument("--proofs", type=int, default=1024)
+    ap.add_argument("--proof-batch", type=int, default=64, help="proofs workload: proofs that advance in lockstep per launch (0: one proof per call sequence)")
     ap.add_argument("--columns", type=int, default=64)
     ap.add_argument("--lanes", type=int, default=4, help="columns in flight per GPU in the columns workload (streams + host threads)")
     return ap.parse_args()
@@ -436,14 +437,23 @@ def proofs_arm(args, ctx, stream, rank, world, local, barrier):
     field = zk.Field()
     omega = field.primitive_nth_root(shape.fri_len)
     mine = pm.partition(args.proofs, world, rank)
-    lanes = max(1, args.lanes if args.lanes != 4 else 8)
+    pb = max(0, args.proof_batch)
+    lanes = max(1, args.lanes if args.lanes != 4 else (4 if pb else 8))
     pipe = pm.ProofPipeline(local, shape, GENERATOR, omega, lanes=lanes)
     lens = shape.column_lengths()
 
     def pinned(seed, n):
         return torch.from_numpy(synth.elements(seed, n).view(np.int64)).pin_memory()
     host_in = [([pinned(SEED + 16 * p + k, ln) for k, ln in enumerate(lens)], pinned(SEED + 16 * p + 15, shape.comb_len)) for p in mine]
-    dev_in = [([c.cuda() for c in cols], comb.cuda()) for cols, comb in host_in]
+    if pb:     # lockstep batches: one packed (K + 1, B, comb_len, 2) coefficient array per batch, pinned on the host
+        groups = [host_in[i:i + pb] for i in range(0, len(host_in), pb)]
+        host_in = [torch.from_numpy(pm.pack_batch(shape, [([c.numpy() for c in cols], comb.numpy()) for cols, comb in g]).view(np.int64)).pin_memory()
+                   for g in groups]
+        dev_in = [h.cuda() for h in host_in]
+        run = pipe.run_batched
+    else:
+        dev_in = [([c.cuda() for c in cols], comb.cuda()) for cols, comb in host_in]
+        run = pipe.run
     make_stream = lambda: zk.SignatureProofStream(b"bench")      # noqa: E731
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 
@@ -459,7 +469,7 @@ def proofs_arm(args, ctx, stream, rank, world, local, barrier):
             flush.fill_(1)
             a.record(stream)
             stream.synchronize()
-            sizes = pipe.run(inputs, make_stream)            # host-synchronous
+            sizes = run(inputs, make_stream)                 # host-synchronous
             b.record(stream)
         barrier()
         launches = sum(cx.launches for cx in pipe.ctxs) - l0
@@ -477,13 +487,13 @@ def proofs_arm(args, ctx, stream, rank, world, local, barrier):
         return float(t.item()), launches, prof, sizes
 
     for _ in range(max(args.warmup, 3)):
-        pipe.run(dev_in, make_stream)
+        run(dev_in, make_stream)
     sampler = ClockSampler(local) if rank == 0 else None
     total_ms, launches, _, sizes = timed(dev_in, args.steps, False)
     clocks = sampler.stop() if sampler else None
     _, _, prof, _ = timed(dev_in, 1, True)                       # per-kernel device time: a separate, profiled step
     for _ in range(2):
-        pipe.run(host_in, make_stream)
+        run(host_in, make_stream)
     e2e_steps = max(3, args.steps // 2)
     e2e_ms, _, _, _ = timed(host_in, e2e_steps, False)
     if rank == 0:
@@ -502,12 +512,12 @@ def proofs_arm(args, ctx, stream, rank, world, local, barrier):
                                    "polynomials (2 boundary quotients of 282 coefficients + randomizer of 1024) LDE'd to the 4096-point coset and "
                                    "Merkle-committed, the 1024-coefficient combination LDE'd + FRI::prove (4 rounds, 64 colinearity tests), "
                                    "3 x 256 Value+Path openings; %s-byte proof" % (args.proofs, world, proof_bytes),
-                       "proofs": args.proofs, "fri_domain": shape.fri_len, "lanes_per_gpu": lanes,
+                       "proofs": args.proofs, "fri_domain": shape.fri_len, "lanes_per_gpu": lanes, "proofs_in_lockstep_per_launch": pb,
                        "l2": "flushed between steps (256 MiB write, untimed)",
-                       "parallelism": "independent proofs per rank, no data-path collective; %d proofs in flight per GPU (streams + host threads)" % lanes},
+                       "parallelism": "independent proofs per rank, no data-path collective; " + (("batches of %d proofs advance in lockstep (every launch carries the whole batch), %d batches in flight per GPU" % (pb, lanes)) if pb else ("%d proofs in flight per GPU (streams + host threads)" % lanes))},
             "e2e": {"value": args.proofs / (e2e_ms / e2e_steps * 1e-3), "unit": "proofs/s", "h2d_bytes_per_step": len(mine) * in_bytes,
                     "d2h_bytes_per_step": len(mine) * (proof_bytes or 0), "ms_per_step": e2e_ms / e2e_steps,
-                    "api": "zkb_coset_lde / zkb_merkle_build / zkb_fri_prove / zkb_merkle_open_ps with pinned host coefficients; the proof bytes end in host memory in both arms"},
+                    "api": ("zkb_coset_lde_batch / zkb_merkle_build_batch / zkb_fri_prove_batch / zkb_merkle_open_ps_batch" if pb else "zkb_coset_lde / zkb_merkle_build / zkb_fri_prove / zkb_merkle_open_ps") + " with pinned host coefficients; the proof bytes end in host memory in both arms"},
             "gpu_launches": launches, "kernels": kern, "dominant_kernel": dom,
             "roofline": {"kernel": dom, "bound": "hbm", "achieved": None, "peak": None, "unit": "GB/s", "frac": None, "traffic": None,
                          "note": "latency-bound workload: every kernel works on 4096 elements (64 KiB); throughput comes from proofs in flight, "

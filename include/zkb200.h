@@ -221,6 +221,22 @@ int zkb_fri_prove(zkb_ctx* ctx, const zkb_fri_params* p, const void* codeword, s
  * the retained tree (the reference rebuilds the tree per index), objects appended to `ps` in index order. */
 int zkb_merkle_open_ps(zkb_tree* tree, const uint64_t* idx, size_t k, zkb_ps* ps);
 
+/* ---- batches of small independent instances (RPSSS-shaped proofs) ---------------------
+ * One proof at a 4096-point FRI domain cannot fill a GPU; independent proofs advance in lockstep instead:
+ * every launch carries all instances.  Per instance the results are byte-identical to the single-instance
+ * entry points above.  Limits: device pointers, n <= 2^17, batch <= 4096. */
+/* MerkleRoot::commit (stark.rs:373-381, 431-436) over `batch` codewords, instance b at vals + b*stride
+ * elements; trees[b] are retained trees sharing one arena - tree 0 owns it: free it LAST. */
+int zkb_merkle_build_batch(zkb_ctx* ctx, const void* vals, size_t n, size_t stride, size_t batch, zkb_tree** trees,
+                           zkb_ps* const* ps /* NULL, or per tree a stream (or NULL) that receives Root(root), in tree order */);
+/* FRI::prove (fri.rs:210-248) for `batch` codewords (instance b at codewords + b*stride elements) against
+ * `batch` proof streams; top_indices_out receives batch x num_colinearity_tests indices. */
+int zkb_fri_prove_batch(zkb_ctx* ctx, const zkb_fri_params* p, const void* codewords, size_t n, size_t stride, size_t batch,
+                        zkb_ps* const* ps, uint64_t* top_indices_out);
+/* zkb_merkle_open_ps for `count` trees of one zkb_merkle_build_batch (in batch order): tree i is opened at
+ * idx[i*k .. i*k+k) and appends to ps[i]; trees that share a proof stream append in increasing tree order. */
+int zkb_merkle_open_ps_batch(zkb_tree* const* trees, size_t count, const uint64_t* idx, size_t k, zkb_ps* const* ps);
+
 #ifdef __cplusplus
 }
 #endif

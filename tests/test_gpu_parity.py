@@ -743,3 +743,35 @@ def test_stark_prove_gpu_backend_independent_stream(ctx):
     want = ref_stark.prove(rp.trace(x), tcs, rp.boundary_constraints(out), PS.IndependentProofStream(), deterministic_rng(b"z"))
     assert got == want
     assert ref_stark.verify(tcs, rp.boundary_constraints(out), PS.IndependentProofStream(PS.parse(got))) is None
+
+
+def test_rpsss_shaped_proofs_in_lockstep(ctx):
+    """csrc/batch.cu: B proofs advance together (every launch carries all instances); each proof's bytes are
+    identical to the one-at-a-time sequence and to the oracle."""
+    from zk_stark_tutor_b200 import proofs
+    shape = proofs.ProofShape()
+    B = 7
+    inputs = []
+    for p in range(B):
+        cols = [C.synth(0x5EED0005 + 16 * p + k, ln) for k, ln in enumerate(shape.column_lengths())]
+        inputs.append((cols, C.synth(0x5EED0005 + 16 * p + 15, shape.comb_len)))
+    w = F.primitive_nth_root(shape.fri_len)
+    fri = zk.FRI(F.GENERATOR, w, shape.fri_len, shape.ef, shape.ncc, ctx)
+    one_by_one = []
+    for cols, comb in inputs:
+        ps = zk.SignatureProofStream(b"a document")
+        top = proofs.prove_hot_path(ctx, fri, shape, cols, comb, ps)
+        one_by_one.append((top, ps.digest()))
+    ops = PS.SignatureProofStream(b"a document")
+    _oracle_hot_path(shape, inputs[0][0], inputs[0][1], ops)
+    assert one_by_one[0][1] == ops.digest()
+    packed = proofs.pack_batch(shape, inputs)
+    for src in (packed, cuda(packed.reshape(-1, 2)).reshape(packed.shape)):
+        streams = [zk.SignatureProofStream(b"a document") for _ in range(B)]
+        tops = proofs.prove_hot_path_batch(ctx, fri, shape, src, streams)
+        assert tops == [t for t, _ in one_by_one]
+        assert [s.digest() for s in streams] == [d for _, d in one_by_one]
+    # a batch of one, and batched trees / openings against the single-tree calls on ragged sizes
+    streams = [zk.SignatureProofStream(b"a document")]
+    assert proofs.prove_hot_path_batch(ctx, fri, shape, proofs.pack_batch(shape, inputs[:1]), streams) == [one_by_one[0][0]]
+    assert streams[0].digest() == one_by_one[0][1]

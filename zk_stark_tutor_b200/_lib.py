@@ -58,6 +58,9 @@ PROTOTYPES = {
     "zkb_merkle_root": (ctypes.c_int, [vp, c_u8p]),
     "zkb_merkle_open": (ctypes.c_int, [vp, c_u64p, sz, c_u8p]),
     "zkb_merkle_open_ps": (ctypes.c_int, [vp, c_u64p, sz, vp]),
+    "zkb_merkle_build_batch": (ctypes.c_int, [vp, vp, sz, sz, sz, ctypes.POINTER(vp), ctypes.POINTER(vp)]),
+    "zkb_fri_prove_batch": (ctypes.c_int, [vp, ctypes.POINTER(FriParams), vp, sz, sz, sz, ctypes.POINTER(vp), c_u64p]),
+    "zkb_merkle_open_ps_batch": (ctypes.c_int, [ctypes.POINTER(vp), sz, c_u64p, sz, ctypes.POINTER(vp)]),
     "zkb_merkle_free": (None, [vp]),
     "zkb_merkle_verify": (ctypes.c_int, [c_u8p, u64, c_u8p, sz, c_u8p]),
     "zkb_blake2b512": (None, [c_u8p, sz, c_u8p]),

@@ -108,6 +108,21 @@ int scratch_reserve(zkb_ctx* c, size_t bytes, void** out) {
     return 0;
 }
 
+int host_scratch_reserve(zkb_ctx* c, int slot, size_t bytes, uint8_t** out) {
+    if (slot < 0 || slot >= 3) return set_err(c, ZKB_ERR_ARG, "internal: host scratch slot");
+    if (bytes > c->host_scratch_bytes[slot]) {
+        ZKB_CUDA(c, cudaStreamSynchronize(c->stream));            // a queued copy may still target the old buffer
+        if (c->host_scratch[slot]) cudaFreeHost(c->host_scratch[slot]);
+        c->host_scratch[slot] = nullptr;
+        c->host_scratch_bytes[slot] = 0;
+        const size_t want = bytes + (bytes >> 2);
+        ZKB_CUDA(c, cudaHostAlloc(&c->host_scratch[slot], want, cudaHostAllocDefault));
+        c->host_scratch_bytes[slot] = want;
+    }
+    *out = (uint8_t*)c->host_scratch[slot];
+    return 0;
+}
+
 fe h_inv(const fe& a) {
     if (fe_is_zero(a)) return fe_zero();
     // a^(p-2), p-2 = 0xCB7FFFFF_FFFFFFFF_FFFFFFFF_FFFFFFFF
@@ -212,6 +227,7 @@ void zkb_ctx_destroy(zkb_ctx* c) {
     for (auto e : c->prof_pool) cudaEventDestroy(e);
     if (c->scratch) cudaFree(c->scratch);
     if (c->tree_bars) cudaFree(c->tree_bars);
+    for (int i = 0; i < 3; i++) if (c->host_scratch[i]) cudaFreeHost(c->host_scratch[i]);
     if (c->pinned) cudaFreeHost(c->pinned);
     if (c->own_stream) cudaStreamDestroy(c->stream);
     delete c;

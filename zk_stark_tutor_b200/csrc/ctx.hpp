@@ -49,6 +49,8 @@ struct zkb_ctx {
     size_t pinned_bytes = 0;
     std::vector<std::unique_ptr<zkb::PowTable>> pow_tables;
     uint64_t clock = 0;
+    void* host_scratch[3] = {nullptr, nullptr, nullptr};   // grow-only pinned buffers for large D2H results (batch paths)
+    size_t host_scratch_bytes[3] = {0, 0, 0};
     bool zero_copy_inputs = true;    // pinned host LDE inputs are read in place by the first NTT pass (zkb_ctx_zero_copy_inputs)
     uint32_t* tree_bars = nullptr;   // k_tree's arrival counter (device; zero between launches)
     uint32_t root_seq = 0;   // sequence number of the last root signalled through pinned memory
@@ -93,6 +95,9 @@ struct LaunchScope {
 int prof_collect(zkb_ctx* c);
 
 int scratch_reserve(zkb_ctx* c, size_t bytes, void** out);
+// pinned host buffer `slot` of at least `bytes` (grow-only, owned by the context): D2H copies into pageable memory
+// are staged and synchronous (~8 GB/s); into pinned memory they run at PCIe rate
+int host_scratch_reserve(zkb_ctx* c, int slot, size_t bytes, uint8_t** out);
 int get_pow_table(zkb_ctx* c, const fe& base, uint32_t log_n, DevPow* out);
 bool is_device_ptr(const void* p);
 

@@ -9,6 +9,7 @@
 //   MerkleRoot::verify    src/merkle_root.rs:69-95
 // These stay on the host by design: they are tiny, serial, and sit between FRI rounds.
 #include <string.h>
+#include <algorithm>
 #include "hosthash.hpp"
 #include "fe128.cuh"
 #include "../../include/zkb200.h"
@@ -189,13 +190,18 @@ int zkb_ps_push_codeword(zkb_ps* ps, const void* vals_host, size_t n) {
 }
 int zkb_ps_push_path(zkb_ps* ps, const uint8_t* nodes, size_t count) {
     if (!ps || (!nodes && count)) return ZKB_ERR_ARG;
-    std::vector<uint8_t> p;
-    p.reserve(count * 72);
-    for (size_t i = 0; i < count; i++) {      // each node: len u64_be (= 64) || bytes
-        put_be64(p, 64);
-        p.insert(p.end(), nodes + 64 * i, nodes + 64 * i + 64);
+    // code || len || count x (u64_be(64) || 64 bytes), written in place (a proof holds ~1,350 paths)
+    std::vector<uint8_t>& v = ps->body;
+    const size_t payload = count * 72, at = v.size();
+    if (v.capacity() < at + 9 + payload) v.reserve(std::max(v.capacity() * 2, at + 9 + payload));
+    v.resize(at + 9 + payload);
+    uint8_t* o = v.data() + at;
+    *o++ = 2;
+    for (int i = 7; i >= 0; i--) *o++ = (uint8_t)((uint64_t)payload >> (8 * i));
+    for (size_t i = 0; i < count; i++) {
+        memset(o, 0, 7); o[7] = 64; o += 8;
+        memcpy(o, nodes + 64 * i, 64); o += 64;
     }
-    ps->push(2, p.data(), p.size());
     return 0;
 }
 int zkb_ps_push_leafs(zkb_ps* ps, const uint8_t a[16], const uint8_t b[16], const uint8_t c[16]) {

@@ -192,7 +192,8 @@ struct TopArgs {
     uint32_t count;
     uint32_t chunk_log;      // nodes per CTA = 2^chunk_log (== count: a single CTA does everything)
     uint8_t* level_out[26];  // global destination of relative level r >= 1
-    uint32_t* bar;           // arrival counter (zero between launches: the last CTA resets it)
+    uint64_t batch_stride;   // bytes between the node arenas of the instances of a batch (blockIdx.y); 0 for one tree
+    uint32_t* bar;           // arrival counter per instance (zero between launches: the last CTA resets it)
     uint8_t* host_root;      // mapped pinned host memory (or nullptr)
     volatile uint32_t* host_flag;
     uint32_t seq;
@@ -200,12 +201,18 @@ struct TopArgs {
 
 // One thread per leaf -> level-0 digests (the input of k_tree for small layers).
 template <bool FOLD>
-__global__ void __launch_bounds__(256, 2) k_leaf1(const fe* __restrict__ vals, FoldArgs f, uint32_t n, uint8_t* __restrict__ out0) {
+__global__ void __launch_bounds__(256, 2) k_leaf1(const fe* __restrict__ vals, FoldArgs f, uint32_t n, uint8_t* __restrict__ out0, BatchArgs b) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
+    const uint32_t inst = blockIdx.y;                      // instance of a batch (0 for a single tree)
+    vals += (uint64_t)inst * b.vals_stride;
+    out0 += (uint64_t)inst * b.nodes_stride;
     fe v;
     if (FOLD) {
-        fe k_m = fe_montmul(f.kk_m, pow2lvl_m(f.winv, (uint64_t)i * f.exp_mul));
+        f.cw += (uint64_t)inst * b.vals_stride;
+        f.next += (uint64_t)inst * b.next_stride;
+        const fe kk = b.kk_m ? fe_ldg(b.kk_m + inst) : f.kk_m;
+        fe k_m = fe_montmul(kk, pow2lvl_m(f.winv, (uint64_t)i * f.exp_mul));
         v = fold_one(f, i, k_m);
     } else {
         v = fe_ldg(vals + i);
@@ -222,7 +229,7 @@ static size_t dig_words_host(size_t i) { return i * 8 + (i >> 1); }
 // reduction (k = 0, 1, ...) produces relative level first_level + k, written to
 // out[first_level + k] at node offset (base >> (k + 1)) + j; `base` = global index of the first
 // input digest at its level.
-__device__ __forceinline__ void reduce_in_smem(uint64_t* cur, uint64_t* nxt, uint32_t n_in, uint8_t* const* out, uint32_t first_level,
+__device__ __forceinline__ void reduce_in_smem(uint64_t* cur, uint64_t* nxt, uint32_t n_in, uint8_t* const* out, uint64_t boff, uint32_t first_level,
                                                uint64_t base, const TopArgs& a, bool is_root_chunk) {
     const uint32_t tid = threadIdx.x, lane = tid & 31u, q = lane & 3u;
     const uint32_t quad = tid >> 2, quads = blockDim.x >> 2, warp_quad0 = (tid >> 5) << 3;
@@ -238,7 +245,7 @@ __device__ __forceinline__ void reduce_in_smem(uint64_t* cur, uint64_t* nxt, uin
             if (live) {
                 uint64_t* s = nxt + dig_word(j);
                 s[q] = h_lo; s[4 + q] = h_hi;
-                unsigned long long* g = reinterpret_cast<unsigned long long*>(out[level] + (base + j) * 64);
+                unsigned long long* g = reinterpret_cast<unsigned long long*>(out[level] + boff + (base + j) * 64);
                 g[q] = h_lo; g[4 + q] = h_hi;
                 if (cnt == 1 && is_root_chunk && a.host_root) {   // the root: hand it to the polling host
                     unsigned long long* hr = reinterpret_cast<unsigned long long*>(a.host_root);
@@ -264,27 +271,29 @@ __global__ void __launch_bounds__(512, 1) k_tree(TopArgs a) {
     __shared__ uint32_t s_last;
     const uint32_t chunk = 1u << a.chunk_log, chunks = a.count >> a.chunk_log;
     const uint32_t nmax = chunk > chunks ? chunk : chunks;
+    const uint64_t boff = (uint64_t)blockIdx.y * a.batch_stride;   // instance blockIdx.y of a batch: every buffer shifts by boff
+    uint32_t* const bar = a.bar + blockIdx.y;
     uint64_t* bufA = tree_smem;
     uint64_t* bufB = tree_smem + dig_word(nmax) + 8;
     // stage 0: this CTA's chunk; stage 1 (last CTA to arrive only): the chunk roots
-    const uint8_t* src = a.nodes_in + (size_t)blockIdx.x * chunk * 64;
+    const uint8_t* src = a.nodes_in + boff + (size_t)blockIdx.x * chunk * 64;
     uint32_t n_in = chunk, first_level = 1;
     uint64_t base = (uint64_t)blockIdx.x * chunk;
     bool last_stage = chunks == 1;
 #pragma unroll 1
     for (;;) {
         load_chunk(bufA, src, n_in, first_level != 1);
-        reduce_in_smem(bufA, bufB, n_in, a.level_out, first_level, base, a, last_stage);
+        reduce_in_smem(bufA, bufB, n_in, a.level_out, boff, first_level, base, a, last_stage);
         if (last_stage) return;
         if (threadIdx.x == 0) {                // (the __syncthreads closing the reduction ordered the CTA's stores before this)
             __threadfence();
-            const uint32_t arrived = atomicAdd(a.bar, 1u);
+            const uint32_t arrived = atomicAdd(bar, 1u);
             s_last = arrived == gridDim.x - 1;
-            if (s_last) { *a.bar = 0; __threadfence(); }
+            if (s_last) { *bar = 0; __threadfence(); }
         }
         __syncthreads();
         if (!s_last) return;
-        src = a.level_out[a.chunk_log];
+        src = a.level_out[a.chunk_log] + boff;
         n_in = chunks; first_level = a.chunk_log + 1; base = 0; last_stage = true;
     }
 }
@@ -299,10 +308,15 @@ struct OpenArgs {
     const uint64_t* idx;
     uint32_t k;
     uint8_t* out;            // k * log_n * 64 bytes
+    uint64_t vals_stride, nodes_stride;   // batch (blockIdx.y): elements / bytes between instances; idx and out are dense (k per instance)
 };
 __global__ void __launch_bounds__(128) k_open(OpenArgs a) {
     __shared__ uint64_t dig[4][14][8];          // per warp: 8 + 4 + 2 digests
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    a.vals += (uint64_t)blockIdx.y * a.vals_stride;
+    a.nodes += (uint64_t)blockIdx.y * a.nodes_stride;
+    a.idx += (uint64_t)blockIdx.y * a.k;
+    a.out += (uint64_t)blockIdx.y * a.k * a.layout.log_n * 64;
     const uint32_t q = blockIdx.x * 4 + warp;
     if (q >= a.k) return;
     const uint64_t idx = a.idx[q];
@@ -374,7 +388,7 @@ static uint32_t tree_chunks_log() {  // larger ones are cut into 2^this chunks (
     if (v < 0) { const char* e = getenv("ZKB_TREE_CHUNKS_LOG"); v = e ? atoi(e) : 7; if (v > 10) v = 10; if (v < 1) v = 1; }
     return (uint32_t)v;
 }
-static int launch_top(zkb_ctx* c, const TopArgs& a) {
+static int launch_top(zkb_ctx* c, const TopArgs& a, uint32_t batch = 1) {
     static bool attr_set = false;
     const size_t max_smem = (size_t)(dig_words_host(ZKB_TREE_MAX_CHUNK) + 8 + dig_words_host(ZKB_TREE_MAX_CHUNK / 2) + 8) * sizeof(uint64_t);
     if (!attr_set) {
@@ -395,14 +409,15 @@ static int launch_top(zkb_ctx* c, const TopArgs& a) {
     if (threads < 128) threads = 128;
     if (threads > 512) threads = 512;
     const size_t smem = (size_t)(dig_words_host(nmax) + 8 + dig_words_host(nmax / 2) + 8) * sizeof(uint64_t);
+    if (batch < 1 || batch > ZKB_MAX_BATCH) return set_err(c, ZKB_ERR_ARG, "internal: tree batch %u out of range", batch);
     if (!c->tree_bars) {
-        ZKB_CUDA(c, cudaMalloc(&c->tree_bars, 64));
-        ZKB_CUDA(c, cudaMemsetAsync(c->tree_bars, 0, 64, c->stream));
+        ZKB_CUDA(c, cudaMalloc(&c->tree_bars, ZKB_MAX_BATCH * sizeof(uint32_t)));
+        ZKB_CUDA(c, cudaMemsetAsync(c->tree_bars, 0, ZKB_MAX_BATCH * sizeof(uint32_t), c->stream));
     }
     b.bar = c->tree_bars;
     {
         LaunchScope ls(c, K_MERKLE_SMALL);
-        k_tree<<<chunks, threads, smem, c->stream>>>(b);
+        k_tree<<<dim3(chunks, batch), threads, smem, c->stream>>>(b);
     }
     ZKB_CUDA(c, cudaGetLastError());
     return 0;
@@ -438,8 +453,8 @@ int merkle_build_levels(zkb_ctx* c, const fe* vals, const FoldArgs* fold, uint64
             // latency-bound: small layers go out one warp per CTA so every warp gets a scheduler of its own
             const unsigned threads = n <= (1u << 14) ? 32u : n <= (1u << 15) ? 64u : 256u;
             const unsigned blocks = (unsigned)((n + threads - 1) / threads);
-            if (fold) k_leaf1<true><<<blocks, threads, 0, c->stream>>>(nullptr, fa, (uint32_t)n, nodes + L.level_off[0] * 64);
-            else k_leaf1<false><<<blocks, threads, 0, c->stream>>>(vals, fa, (uint32_t)n, nodes + L.level_off[0] * 64);
+            if (fold) k_leaf1<true><<<blocks, threads, 0, c->stream>>>(nullptr, fa, (uint32_t)n, nodes + L.level_off[0] * 64, BatchArgs());
+            else k_leaf1<false><<<blocks, threads, 0, c->stream>>>(vals, fa, (uint32_t)n, nodes + L.level_off[0] * 64, BatchArgs());
         }
         ZKB_CUDA(c, cudaGetLastError());
         if (n == 1) return 0;
@@ -487,12 +502,56 @@ int merkle_build_levels(zkb_ctx* c, const fe* vals, const FoldArgs* fold, uint64
     return 0;
 }
 
+int merkle_build_levels_batch(zkb_ctx* c, const fe* vals, const FoldArgs* fold, uint64_t n,
+                              const TreeLayout& L, uint8_t* nodes, const BatchArgs& b) {
+    if (L.top != 0) return set_err(c, ZKB_ERR_ARG, "internal: batched trees are limited to 2^%u leaves", tree_leaf_log());
+    if (b.batch < 1 || b.batch > ZKB_MAX_BATCH) return set_err(c, ZKB_ERR_ARG, "batch of %u trees not supported (max %u)", b.batch, ZKB_MAX_BATCH);
+    FoldArgs fa;
+    if (fold) fa = *fold; else memset(&fa, 0, sizeof(fa));
+    {
+        LaunchScope ls(c, K_LEAF1);
+        const unsigned threads = n * b.batch <= (1u << 14) ? 32u : n * b.batch <= (1u << 15) ? 64u : 256u;
+        const dim3 grid((unsigned)((n + threads - 1) / threads), b.batch);
+        if (fold) k_leaf1<true><<<grid, threads, 0, c->stream>>>(nullptr, fa, (uint32_t)n, nodes + L.level_off[0] * 64, b);
+        else k_leaf1<false><<<grid, threads, 0, c->stream>>>(vals, fa, (uint32_t)n, nodes + L.level_off[0] * 64, b);
+    }
+    ZKB_CUDA(c, cudaGetLastError());
+    if (n == 1) return 0;
+    TopArgs a;
+    memset(&a, 0, sizeof(a));
+    a.nodes_in = nodes + L.level_off[0] * 64;
+    a.count = (uint32_t)n;
+    a.batch_stride = b.nodes_stride;
+    for (uint32_t l = 1; l <= L.log_n; l++) a.level_out[l] = nodes + L.level_off[l] * 64;
+    return launch_top(c, a, b.batch);
+}
+
+int merkle_batch_roots(zkb_ctx* c, const TreeLayout& L, const uint8_t* nodes, const BatchArgs& b, uint8_t* roots_host) {
+    ZKB_CUDA(c, cudaMemcpy2DAsync(roots_host, 64, nodes + L.level_off[L.log_n] * 64, b.nodes_stride ? b.nodes_stride : 64, 64, b.batch,
+                                  cudaMemcpyDeviceToHost, c->stream));
+    ZKB_CUDA(c, cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
 int merkle_open_device(zkb_ctx* c, const fe* vals, const TreeLayout& layout, const uint8_t* nodes,
                        const uint64_t* d_idx, size_t k, uint8_t* d_out) {
     if (k == 0) return 0;
     OpenArgs a;
     a.vals = vals; a.nodes = nodes; a.layout = layout; a.idx = d_idx; a.k = (uint32_t)k; a.out = d_out;
+    a.vals_stride = 0; a.nodes_stride = 0;
     { LaunchScope ls(c, K_OPEN); k_open<<<(unsigned)((k + 3) / 4), 128, 0, c->stream>>>(a); }
+    ZKB_CUDA(c, cudaGetLastError());
+    return 0;
+}
+
+int merkle_open_device_batch(zkb_ctx* c, const fe* vals, const TreeLayout& layout, const uint8_t* nodes,
+                             const uint64_t* d_idx, size_t k, uint8_t* d_out, uint32_t batch,
+                             uint64_t vals_stride, uint64_t nodes_stride) {
+    if (k == 0 || batch == 0) return 0;
+    OpenArgs a;
+    a.vals = vals; a.nodes = nodes; a.layout = layout; a.idx = d_idx; a.k = (uint32_t)k; a.out = d_out;
+    a.vals_stride = vals_stride; a.nodes_stride = nodes_stride;
+    { LaunchScope ls(c, K_OPEN); k_open<<<dim3((unsigned)((k + 3) / 4), batch), 128, 0, c->stream>>>(a); }
     ZKB_CUDA(c, cudaGetLastError());
     return 0;
 }

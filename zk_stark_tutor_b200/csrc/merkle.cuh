@@ -46,12 +46,33 @@ struct RootSignal {
 };
 int merkle_build_levels(zkb_ctx* c, const fe* vals, const FoldArgs* fold, uint64_t n,
                         const TreeLayout& layout, uint8_t* nodes, const RootSignal* signal = nullptr);
+
+// Batched small trees (n <= 2^ZKB_TREE_LEAF_LOG, i.e. layout.top == 0): `batch` independent instances with
+// identical layouts, instance b = blockIdx.y working on buffers offset by b * stride.  One leaf launch and one
+// tree launch for the whole batch: at RPSSS sizes (4096-point domain) a single instance cannot fill the GPU.
+#define ZKB_MAX_BATCH 4096
+struct BatchArgs {
+    uint32_t batch = 1;
+    uint64_t vals_stride = 0;    // elements between the instances' inputs (vals, or fold->cw)
+    uint64_t next_stride = 0;    // elements between the instances' folded outputs (fold->next)
+    uint64_t nodes_stride = 0;   // bytes between the instances' node arenas
+    const fe* kk_m = nullptr;    // per-instance alpha / offset_r in Montgomery form (overrides FoldArgs::kk_m)
+};
+int merkle_build_levels_batch(zkb_ctx* c, const fe* vals, const FoldArgs* fold, uint64_t n,
+                              const TreeLayout& layout, uint8_t* nodes, const BatchArgs& b);
+// roots of a batch -> host (batch x 64 bytes), one strided copy; synchronises the stream
+int merkle_batch_roots(zkb_ctx* c, const TreeLayout& layout, const uint8_t* nodes, const BatchArgs& b, uint8_t* roots_host);
 // Spin until *signal->host_flag == signal->seq (falls back to a stream sync on a CUDA error).
 int wait_root(zkb_ctx* c, const RootSignal& signal, uint8_t root_out[64]);
 
 // Authentication paths for k indices: out[k][log_n][64] (device), leaf sibling first.
 int merkle_open_device(zkb_ctx* c, const fe* vals, const TreeLayout& layout, const uint8_t* nodes,
                        const uint64_t* d_idx, size_t k, uint8_t* d_out);
+// The same for `batch` instances: instance b reads vals + b*vals_stride, nodes + b*nodes_stride, indices
+// d_idx + b*k and writes d_out + b*k*log_n*64.
+int merkle_open_device_batch(zkb_ctx* c, const fe* vals, const TreeLayout& layout, const uint8_t* nodes,
+                             const uint64_t* d_idx, size_t k, uint8_t* d_out, uint32_t batch,
+                             uint64_t vals_stride, uint64_t nodes_stride);
 
 }  // namespace zkb
 

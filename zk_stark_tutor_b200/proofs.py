@@ -85,6 +85,59 @@ def prove_hot_path(ctx, fri, shape, columns, combination, proof_stream):
             lib.zkb_merkle_free(h)
 
 
+def pack_batch(shape, proofs):
+    """The coefficient vectors of a batch in the layout prove_hot_path_batch takes: a (K + 1, B, comb_len, 2)
+    uint64 array, zero padded - plane t < K holds committed polynomial t of every proof, plane K the combinations.
+    (Zero padding does not change an LDE: the extra coefficients are zero.)"""
+    K, B = len(shape.column_lengths()), len(proofs)
+    out = np.zeros((K + 1, B, shape.comb_len, 2), dtype=np.uint64)
+    for b, (cols, comb) in enumerate(proofs):
+        for t, col in enumerate(cols):
+            a = np.ascontiguousarray(col).view(np.uint64).reshape(-1, 2)
+            out[t, b, :a.shape[0]] = a
+        a = np.ascontiguousarray(comb).view(np.uint64).reshape(-1, 2)
+        out[K, b, :a.shape[0]] = a
+    return out
+
+
+def prove_hot_path_batch(ctx, fri, shape, packed, proof_streams):
+    """prove_hot_path for B proofs in lockstep (csrc/batch.cu): every launch carries all B instances.
+    packed: pack_batch(...) as a numpy array / pinned or CUDA tensor of shape (K + 1, B, comb_len, 2);
+    proof_streams: B library proof streams.  Returns the B lists of top-level FRI indices.  The bytes each
+    stream ends up with are identical to prove_hot_path's."""
+    import torch
+    lib = ctx.lib
+    n, K, B, nc = shape.fri_len, len(shape.column_lengths()), len(proof_streams), shape.comb_len
+    ptr = packed.data_ptr() if hasattr(packed, "data_ptr") else np.ascontiguousarray(packed).ctypes.data
+    assert tuple(packed.shape) == (K + 1, B, nc, 2)
+    dev = torch.device("cuda", ctx.device)
+    cws = torch.empty(((K + 1) * B, n, 2), dtype=torch.int64, device=dev)       # plane-major like `packed`
+    omega, offset = le16(fri.omega), le16(fri.offset)
+    ctx.check(lib.zkb_coset_lde_batch(ctx.h, omega, n, offset, ptr, nc, nc, cws.data_ptr(), n, (K + 1) * B))   # stark.rs:373-381, 431-436, 520-522
+    trees = (ctypes.c_void_p * (K * B))()
+    handles = [p.h.value for p in proof_streams]
+    ps_arr = (ctypes.c_void_p * B)(*handles)
+    ps_of_tree = (ctypes.c_void_p * (K * B))(*(handles * K))                    # tree t*B + b belongs to proof b
+    ctx.check(lib.zkb_merkle_build_batch(ctx.h, cws.data_ptr(), n, n, K * B, trees, ps_of_tree))   # commits + Root pushes, tree order
+    try:
+        top = np.empty((B, shape.ncc), dtype=np.uint64)
+        ctx.check(lib.zkb_fri_prove_batch(ctx.h, ctypes.byref(fri.params), cws[K * B].data_ptr(), n, n, B, ps_arr,
+                                          top.ctypes.data_as(ctypes.POINTER(ctypes.c_uint64))))               # stark.rs:520-531
+        nn, ef = np.uint64(n), np.uint64(shape.ef)
+        dup = np.concatenate([top, (top + ef) % nn], axis=1)                     # stark.rs:534-542, all proofs at once
+        quad = np.sort(np.concatenate([dup, (dup + nn // np.uint64(2)) % nn], axis=1), axis=1)
+        k = quad.shape[1]
+        idx = np.ascontiguousarray(np.broadcast_to(quad[None, :, :], (K, B, k)))
+        ctx.check(lib.zkb_merkle_open_ps_batch(trees, K * B, idx.ctypes.data_as(ctypes.POINTER(ctypes.c_uint64)), k, ps_of_tree))   # stark.rs:546-560
+        for p in proof_streams:
+            p.objects = None
+        return top.tolist()
+    finally:
+        for i in range(K * B - 1, -1, -1):           # tree 0 owns the shared arena: free it last
+            if trees[i]:
+                lib.zkb_merkle_free(trees[i])
+
+
 def _vec(x):
     """(pointer, n) of a (n, 2) 64-bit numpy array or torch tensor (host or device)."""
     if hasattr(x, "data_ptr"):
@@ -129,6 +182,36 @@ class ProofPipeline:
         if errors:
             raise errors[0]
         return results
+
+    def run_batched(self, batches, make_stream, keep_digest=False):
+        """batches: list of pack_batch(...) arrays / tensors, each a group of proofs that advances in lockstep
+        (prove_hot_path_batch); the lanes take batches round-robin, so one lane's host-side proof assembly
+        overlaps another lane's kernels.  Returns per proof (proof bytes length, digest or None), batch-major."""
+        results = [None] * len(batches)
+        errors = []
+
+        def worker(lane):
+            try:
+                ctx, fri = self.ctxs[lane], self.fris[lane]
+                for i in range(lane, len(batches), len(self.ctxs)):
+                    streams = [make_stream() for _ in range(batches[i].shape[1])]
+                    prove_hot_path_batch(ctx, fri, self.shape, batches[i], streams)
+                    results[i] = [(int(ctx.lib.zkb_ps_digest(ps.h, None, 0)), ps.digest() if keep_digest else None) for ps in streams]
+                    for ps in streams:
+                        ps.close()
+            except Exception as e:       # noqa: BLE001 - re-raised in the caller's thread
+                errors.append(e)
+
+        threads = [threading.Thread(target=worker, args=(k,)) for k in range(len(self.ctxs))]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+        for c in self.ctxs:
+            c.sync()
+        if errors:
+            raise errors[0]
+        return [r for batch in results for r in batch]
 
     def close(self):
         for c in self.ctxs:
