@@ -26,3 +26,6 @@ done
 for np in 4 8; do
     [ $np -le $N ] && run ntt4step_n$np $np --workload ntt4step --log-n 26 --steps 5 --warmup 3 --no-cpu-baseline
 done
+for np in 1 2 4 8; do
+    [ $np -le $N ] && run proofs_n$np $np --workload proofs --proofs 8192 --proof-batch 64 --lanes 4 --steps 3 --warmup 3 --no-cpu-baseline
+done
