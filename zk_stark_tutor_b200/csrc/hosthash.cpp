@@ -10,6 +10,7 @@
 // These stay on the host by design: they are tiny, serial, and sit between FRI rounds.
 #include <string.h>
 #include <algorithm>
+#include <mutex>
 #include "hosthash.hpp"
 #include "fe128.cuh"
 #include "../../include/zkb200.h"
@@ -161,9 +162,21 @@ extern "C" {
 void zkb_blake2b512(const uint8_t* msg, size_t len, uint8_t out[64]) { host_blake2b512(msg, len, out); }
 void zkb_shake256(const uint8_t* msg, size_t len, uint8_t* out, size_t out_len) { host_shake256(msg, len, out, out_len); }
 
+// Transcript buffers are recycled: a proof is ~1.2 MB, which malloc serves with a fresh mmap (page faults on
+// every first touch, munmap on free) - measured 2.7 ms of 2.8 ms per assembled proof.  A small free list of
+// bodies that keep their capacity removes that (0.3 ms per proof).
+static std::mutex g_pool_mu;
+static std::vector<std::vector<uint8_t>> g_body_pool;
+static const size_t kPoolMax = 256, kPoolKeepBytes = 8u << 20;
+
 int zkb_ps_create(const uint8_t* document, size_t document_len, int is_signature, zkb_ps** out) {
     if (!out) return ZKB_ERR_ARG;
     zkb_ps* ps = new zkb_ps();
+    {
+        std::lock_guard<std::mutex> lk(g_pool_mu);
+        if (!g_body_pool.empty()) { ps->body.swap(g_body_pool.back()); g_body_pool.pop_back(); }
+    }
+    ps->body.clear();
     if (is_signature) {
         uint8_t h[64];
         host_blake2b512(document, document_len, h);       // rescue_prime/proof_stream.rs:15-22
@@ -173,7 +186,14 @@ int zkb_ps_create(const uint8_t* document, size_t document_len, int is_signature
     *out = ps;
     return 0;
 }
-void zkb_ps_free(zkb_ps* ps) { delete ps; }
+void zkb_ps_free(zkb_ps* ps) {
+    if (!ps) return;
+    if (ps->body.capacity() >= (64u << 10) && ps->body.capacity() <= kPoolKeepBytes) {
+        std::lock_guard<std::mutex> lk(g_pool_mu);
+        if (g_body_pool.size() < kPoolMax) { g_body_pool.emplace_back(); g_body_pool.back().swap(ps->body); }
+    }
+    delete ps;
+}
 
 int zkb_ps_push_root(zkb_ps* ps, const uint8_t* root, size_t len) {
     if (!ps || (!root && len)) return ZKB_ERR_ARG;

@@ -403,6 +403,13 @@ static int launch_top(zkb_ctx* c, const TopArgs& a, uint32_t batch = 1) {
         b.chunk_log = log_c > tree_chunks_log() + 1 ? log_c - tree_chunks_log() : 1;
         if (b.chunk_log > 10) b.chunk_log = 10;
     }
+    if (batch > 1) {
+        // a batch is a throughput problem: the fattest chunks that still give >= 128 CTAs over the whole batch
+        // (fewer waves of CTAs, fewer latency-bound finishing stages)
+        uint32_t cl = log_c < 10 ? log_c : 10;
+        while (cl > b.chunk_log && (uint64_t)batch * (a.count >> cl) < 128) cl--;
+        b.chunk_log = cl;
+    }
     const uint32_t chunk = 1u << b.chunk_log, chunks = a.count >> b.chunk_log;
     const uint32_t nmax = chunk > chunks ? chunk : chunks;
     uint32_t threads = 2 * nmax;                          // one quad per node of the widest level computed
