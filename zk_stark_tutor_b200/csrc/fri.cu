@@ -10,10 +10,9 @@
 // is evaluated as  half(c[i] + c[i+n/2] + k_i (c[i] - c[i+n/2])),  k_i = (alpha/offset) omega^-i
 // - the same field element (exact arithmetic), 2.25 multiplications per output instead of the
 // reference's pow + xgcd inverse + 5 products.  omega^-i comes from one two-level power
-// table of omega_0^-1 shared by all rounds (round r uses exponent i*2^r).  For layers of
-// more than 1024 values the fold runs inside the leaf-hash kernel of the NEXT layer
-// (merkle.cu k_leaf8<true> / k_top): the folded value is written once to HBM and hashed while
-// still in registers.  Every layer (codeword + pruned tree) stays on the device for the
+// table of omega_0^-1 shared by all rounds (round r uses exponent i*2^r).  The fold runs inside
+// the leaf-hash kernel of the NEXT layer (merkle.cu k_leaf8<true> / k_leaf1<true>): the folded
+// value is written once to HBM and hashed while still in registers.  Every layer (codeword + pruned tree) stays on the device for the
 // query phase; only the 64-byte root goes to the host each round, where the Fiat-Shamir
 // callback turns it into alpha (SHAKE256 over a transcript of < 1.5 KB).
 #include <string.h>

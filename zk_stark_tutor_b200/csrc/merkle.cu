@@ -14,11 +14,12 @@
 //             of the previous layer and written out as the next codeword ("fold fused with
 //             the next round's leaf hashing").
 //   k_node8   the same over 8 stored nodes: 7 compressions -> the node three levels up.
-//   k_tree    everything above a level of <= 2^15 nodes, and whole trees of <= 2^17 leaves:
-//             level by level, one compression per thread per level, grid-wide barrier between
-//             levels (cooperative launch), every level stored.  These phases are bound by the
-//             latency of a chain of log2(n) compressions, not by throughput, so the tree is
-//             walked with maximal parallelism per level instead of per-thread subtrees.
+//   k_leaf1   one thread per leaf, for layers of <= 2^17 leaves (latency-bound: a warp per CTA when small).
+//   k_tree    everything above a level of <= 2^17 nodes, and (after k_leaf1) whole trees of <= 2^17
+//             leaves: the latency-mode tree - chunks reduced inside one SM's shared memory with one
+//             compression spread over FOUR lanes, the last CTA to arrive finishes (see below).  These
+//             phases are bound by the latency of a chain of log2(n) compressions, not by throughput.
+//             blockIdx.y = instance of a batch of identical small trees (batch.cu).
 #include <stdlib.h>
 #include <string.h>
 #include <vector>
@@ -45,7 +46,7 @@ void TreeLayout::init(uint32_t log_n_) {
     uint64_t off = 0;
     for (uint32_t l = 0; l <= 40; l++) { level_off[l] = 0; stored[l] = 0; }
     if (log_n <= tree_leaf_log()) {
-        top = 0;                                   // the level-by-level kernel takes the leaves directly
+        top = 0;                                   // small layer: k_leaf1, then the latency-mode tree
     } else {
         top = 3;
         while (log_n - top > tree_node_log()) top += 3;

@@ -7,15 +7,15 @@ namespace zkb {
 // Layout of a retained tree.  Levels are counted from the leaves: level 0 = leaf hashes
 // (n nodes), level log_n = the root.  Trees of <= 2^17 leaves store every level.  Larger
 // trees store level 3, 6, 9, ... (what the per-thread 8-ary subtree kernels emit) down to the
-// first level `top` with <= 2^15 nodes, and every level above `top` (<= 9.2n bytes + 4 MiB
+// first level `top` with <= 2^17 nodes, and every level above `top` (<= 9.2n bytes + 4 MiB
 // instead of 128n).  The two unstored levels inside each group of three - and the leaf hashes - of an
 // authentication path are recomputed at opening time from the 8 group inputs, which the tree
 // can always reach (it references the committed values).
-#define ZKB_TREE_LEAF_LOG 17     // trees up to 2^17 leaves: level-by-level kernel from the leaves
+#define ZKB_TREE_LEAF_LOG 17     // trees up to 2^17 leaves: k_leaf1 + the latency-mode tree from the leaf level
 #define ZKB_TREE_NODE_LOG 17     // larger trees: 8-ary subtree kernels down to <= 2^17 nodes, then the latency-mode tree
 struct TreeLayout {
     uint32_t log_n = 0;
-    uint32_t top = 0;            // first level handled by the level-by-level kernel (0: it starts from the leaves)
+    uint32_t top = 0;            // first level handled by the latency-mode tree k_tree (0: it starts from the leaf hashes)
     uint8_t stored[41];
     uint64_t level_off[41];      // node index (64-byte units) of level l inside `nodes` (stored levels only)
     uint64_t total_nodes = 0;
