@@ -201,6 +201,9 @@ int zkb_ps_push_codeword(zkb_ps* ps, const void* vals_host, size_t n);
 int zkb_ps_push_path(zkb_ps* ps, const uint8_t* nodes, size_t count);       /* count x 64 bytes */
 int zkb_ps_push_leafs(zkb_ps* ps, const uint8_t a[16], const uint8_t b[16], const uint8_t c[16]);
 int zkb_ps_push_value(zkb_ps* ps, const uint8_t v[16]);
+/* StarkProofStreamEnum::to_bytes proof_stream_enum.rs:67-127 for an object the caller serialised itself
+ * (code 0..4, payload in wire order: big-endian values, length-prefixed path nodes of any size). */
+int zkb_ps_push_object(zkb_ps* ps, uint8_t code, const uint8_t* payload, size_t len);
 /* ProofStream::digest (the wire bytes): returns the length; copies min(len, cap) bytes */
 size_t zkb_ps_digest(const zkb_ps* ps, uint8_t* out, size_t cap);
 /* fiat_shamir_prover(num_bytes) proof_stream.rs:36-40 */

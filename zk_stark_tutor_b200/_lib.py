@@ -86,6 +86,7 @@ PROTOTYPES = {
     "zkb_ps_push_path": (ctypes.c_int, [vp, c_u8p, sz]),
     "zkb_ps_push_leafs": (ctypes.c_int, [vp, c_u8p, c_u8p, c_u8p]),
     "zkb_ps_push_value": (ctypes.c_int, [vp, c_u8p]),
+    "zkb_ps_push_object": (ctypes.c_int, [vp, ctypes.c_uint8, c_u8p, sz]),
     "zkb_ps_digest": (sz, [vp, c_u8p, sz]),
     "zkb_ps_fiat_shamir": (ctypes.c_int, [vp, sz, c_u8p]),
     "zkb_fri_prove": (ctypes.c_int, [vp, ctypes.POINTER(FriParams), vp, sz, vp, c_u64p]),

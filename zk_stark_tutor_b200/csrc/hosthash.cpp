@@ -240,6 +240,12 @@ int zkb_ps_push_value(zkb_ps* ps, const uint8_t v[16]) {
     ps->has_field = true;
     return 0;
 }
+int zkb_ps_push_object(zkb_ps* ps, uint8_t code, const uint8_t* payload, size_t len) {
+    if (!ps || (!payload && len) || code > 4) return ZKB_ERR_ARG;
+    ps->push(code, payload, len);
+    if (code == 3 || code == 4 || (code == 1 && len)) ps->has_field = true;   // proof_stream_enum.rs:76-125
+    return 0;
+}
 size_t zkb_ps_digest(const zkb_ps* ps, uint8_t* out, size_t cap) {
     if (!ps) return 0;
     size_t total = 16 + ps->body.size();
