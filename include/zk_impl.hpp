@@ -392,11 +392,12 @@ inline size_t next_power_of_two(size_t n) { size_t p = 1; while (p < n) p <<= 1;
 
 // ntt(root, inputs) ntt.rs:7-49: zero-pads to the next power of two, natural order in and out
 inline std::vector<FieldElement> ntt(const FieldElement& root, const std::vector<FieldElement>& inputs) {
+    if (inputs.empty()) throw Panic("index out of bounds: the len is 0 but the index is 0", ZKB_ERR_EMPTY);    // ntt.rs:11
     const Field* f = field_of(inputs, root.field);
-    std::vector<u128> in = pack_values(inputs), out(next_power_of_two(std::max<size_t>(inputs.size(), 1)));
+    std::vector<u128> in = pack_values(inputs), out(next_power_of_two(inputs.size()));
     uint8_t r[16];
     to_le16(root.value, r);
-    Device::check(zkb_ntt(Device::ctx(), r, in.data(), in.size(), out.data()));     // empty input: ZKB_ERR_EMPTY (ntt.rs:11 panics)
+    Device::check(zkb_ntt(Device::ctx(), r, in.data(), in.size(), out.data()));
     return attach_field(f, out, out.size());
 }
 // intt(root, input) ntt.rs:51-68
@@ -512,6 +513,7 @@ inline Polynomial fast_interpolate_domain(const FieldElement& root, u128 root_or
 // ---- merkle_root.rs (T = FieldElement, the only T the crate uses on this path) -------------------
 struct MerkleRoot {
     static Bytes commit(const std::vector<FieldElement>& leafs) {                       // merkle_root.rs:21-32
+        if (leafs.empty()) throw Panic("length must be power of two", ZKB_ERR_NOT_POW2);  // merkle_root.rs:9 (0 is not a power of two)
         field_of(leafs);
         std::vector<u128> v = pack_values(leafs);
         Bytes root = Bytes::zeroed(64);
@@ -521,6 +523,7 @@ struct MerkleRoot {
     // merkle_root.rs:55-66.  The reference rebuilds the tree per call; open_many opens any number of indices from one build.
     static std::vector<Bytes> open(size_t index, const std::vector<FieldElement>& leafs) { return open_many({(uint64_t)index}, leafs)[0]; }
     static std::vector<std::vector<Bytes>> open_many(const std::vector<uint64_t>& indices, const std::vector<FieldElement>& leafs) {
+        if (leafs.empty()) throw Panic("length must be power of two", ZKB_ERR_NOT_POW2);  // merkle_root.rs:36
         field_of(leafs);
         std::vector<u128> v = pack_values(leafs);
         zkb_tree* t = nullptr;

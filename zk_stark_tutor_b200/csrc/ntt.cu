@@ -533,8 +533,9 @@ extern "C" {
 
 int zkb_ntt_batch(zkb_ctx* c, const uint8_t root[16], int inverse, const void* in, size_t n_in,
                   size_t in_stride, void* out, size_t out_stride, size_t batch) {
-    if (!c || !root || !in || !out) return ZKB_ERR_ARG;
-    if (n_in == 0) return set_err(c, ZKB_ERR_EMPTY, "ntt: empty input");
+    if (!c || !root) return ZKB_ERR_ARG;
+    if (n_in == 0) return set_err(c, ZKB_ERR_EMPTY, "ntt: empty input (ntt.rs:11 indexes inputs[0])");   // an empty Vec's pointer may be null
+    if (!in || !out) return set_err(c, ZKB_ERR_ARG, "ntt: null data pointer");
     if (batch == 0) return 0;
     ZKB_CUDA(c, cudaSetDevice(c->device));
     const uint64_t n = next_pow2_u64(n_in);
