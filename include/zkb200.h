@@ -224,6 +224,40 @@ int zkb_fri_prove(zkb_ctx* ctx, const zkb_fri_params* p, const void* codeword, s
  * the retained tree (the reference rebuilds the tree per index), objects appended to `ps` in index order. */
 int zkb_merkle_open_ps(zkb_tree* tree, const uint64_t* idx, size_t k, zkb_ps* ps);
 
+/* ---- evaluation-form quotients and combination : src/stark/stark.rs:388-519 ---------------------------------
+ * The middle of Stark::prove between the committed codewords and FRI::prove.  The reference evaluates the
+ * transition constraints SYMBOLICALLY (MPolynomial::evaluate_symbolic m_polynomial.rs:128-142, schoolbook
+ * polynomial products), divides by the transition zerofier (fast_coset_divide stark.rs:405-416), forms the
+ * x^shift products (fast_multiply stark.rs:480, 493), the weighted sum (stark.rs:500-512) and LDEs the result
+ * (stark.rs:514-519).  All of that is a polynomial identity, so the same codeword is computed here pointwise on
+ * the FRI coset from the codewords that are already committed - the formula the reference's verifier applies per
+ * index (stark.rs:679-769) - bit-identical, and nothing leaves HBM.  Variables of a constraint, in order:
+ * x, the registers at this row, the registers at the next row (stark.rs:389-399). */
+typedef struct zkb_air_desc {
+    uint8_t offset[16];                  /* FRI domain: x_i = offset * omega^i                                   */
+    uint8_t omega[16];
+    uint64_t domain_length;
+    uint64_t expansion_factor;           /* omicron = omega^expansion_factor: the next row is that many indices on */
+    uint32_t num_registers;
+    uint32_t num_constraints;
+    const uint32_t* term_counts;         /* per constraint: number of dictionary entries                          */
+    const uint8_t* coefs;                /* all terms, 16 bytes each                                              */
+    const uint32_t* exps;                /* all terms, (1 + 2*num_registers) exponents each (short keys zero padded) */
+    const void* const* boundary_zerofiers;      /* per register: coefficient vector (host), stark.rs:196-213     */
+    const size_t* boundary_zerofier_lens;
+    const void* const* boundary_interpolants;   /* per register, stark.rs:215-243                                */
+    const size_t* boundary_interpolant_lens;
+    const void* transition_zerofier;            /* stark.rs:186-194                                               */
+    size_t transition_zerofier_len;
+    const uint8_t* weights;              /* (1 + 2*num_constraints + 2*num_registers) x 16 bytes, stark.rs:447-450 */
+    const uint64_t* shifts;              /* num_constraints + num_registers exponents of x, stark.rs:476, 489      */
+} zkb_air_desc;
+/* bq_codewords: the boundary-quotient codewords (DEVICE, register s at + s*bq_stride elements); randomizer_codeword,
+ * combined_out: DEVICE, domain_length values; tq_out: NULL or DEVICE num_constraints x domain_length values that
+ * receive the transition-quotient codewords (for the degree check of stark.rs:451-464). */
+int zkb_air_combination(zkb_ctx* ctx, const zkb_air_desc* desc, const void* bq_codewords, size_t bq_stride,
+                        const void* randomizer_codeword, void* combined_out, void* tq_out);
+
 /* ---- batches of small independent instances (RPSSS-shaped proofs) ---------------------
  * One proof at a 4096-point FRI domain cannot fill a GPU; independent proofs advance in lockstep instead:
  * every launch carries all instances.  Per instance the results are byte-identical to the single-instance

@@ -1,0 +1,101 @@
+"""SURVEY.md 8f.3 / 8f.4 on the B200: the transition quotients, x^shift products and the weighted combination of
+Stark::prove (stark.rs:388-519) in evaluation form (zkb_air_combination) against the oracle's coefficient-form
+route, and the whole Stark::prove / RPSSS signature through zk.Stark - proof bytes identical to the oracle's."""
+import numpy as np
+import pytest
+
+import zk_stark_tutor_b200 as zk
+from air_common import prover_intermediates
+from oracle import cbind as C, ntt as N, proof_stream as PS
+from oracle.stark import RPSSS, deterministic_rng
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = zk.Context(0)
+    yield c
+    c.close()
+
+
+def cuda(arr):
+    import torch
+    return torch.from_numpy(np.ascontiguousarray(arr).view(np.int64)).cuda()
+
+
+def host(t):
+    return C.from_arr(t.cpu().numpy().view(np.uint64))
+
+
+def test_air_combination_equals_coefficient_form_prover(ctx):
+    m = prover_intermediates()
+    st, nr, nc, n = m["stark"], m["nr"], m["nc"], m["n"]
+    bq = cuda(np.stack([C.to_arr(cw) for cw in m["bq_cws"]]))
+    rnd = cuda(C.to_arr(m["rnd_cw"]))
+    before = ctx.launches
+    comb, tq = zk.air_combination(st.generator, st.omega, n, st.expansion_factor, m["tcs"], m["zerofiers"], m["interpolants"], m["tz"],
+                                  m["weights"], m["shifts"], bq, rnd, want_quotients=True, ctx=ctx)
+    assert ctx.launches > before
+    assert host(comb) == m["combined"], "evaluation-form combination differs from LDE(weighted sum of terms)"
+    for j in range(nc):
+        assert host(tq[j]) == N.fast_coset_evaluate(st.omega, n, st.generator, m["tq_polys"][j]), "transition quotient %d" % j
+    # without the quotient output
+    comb2 = zk.air_combination(st.generator, st.omega, n, st.expansion_factor, m["tcs"], m["zerofiers"], m["interpolants"], m["tz"],
+                               m["weights"], m["shifts"], bq, rnd, ctx=ctx)
+    assert host(comb2) == m["combined"]
+
+
+def test_air_combination_rejects_host_codewords_and_zero_divisor(ctx):
+    import ctypes
+    from zk_stark_tutor_b200 import _lib
+    m = prover_intermediates()
+    st, nr, n = m["stark"], m["nr"], m["n"]
+    bq = cuda(np.stack([C.to_arr(cw) for cw in m["bq_cws"]]))
+    rnd = cuda(C.to_arr(m["rnd_cw"]))
+    # a transition zerofier with a root ON the coset: x - generator  ->  the reference's division panics
+    bad_tz = [(-st.generator) % zk.P, 1]
+    with pytest.raises(zk.ZkbError) as e:
+        zk.air_combination(st.generator, st.omega, n, st.expansion_factor, m["tcs"], m["zerofiers"], m["interpolants"], bad_tz,
+                           m["weights"], m["shifts"], bq, rnd, ctx=ctx)
+    assert e.value.code == -7
+    d = _lib.AirDesc()
+    assert ctx.lib.zkb_air_combination(ctx.h, ctypes.byref(d), None, 0, None, None, None) == -2
+
+
+def test_rpsss_signature_through_device_stark(ctx):
+    """Stark::prove on the Rescue-Prime trace at the tutorial's signature parameters with the evaluation-form middle:
+    the 1,156,888-byte signature equals the oracle's (coefficient-form) one and the restated verifier accepts it."""
+    cpu = RPSSS(4, 64, 128, 3)
+    sk, pk = cpu.keygen(deterministic_rng(b"k2"))
+    doc = b"evaluation form"
+    want = cpu.sign(sk, doc, deterministic_rng(b"r2"))
+    stark = zk.Stark(4, 64, 128, cpu.rp.m, cpu.rp.N + 1, 3, ctx=ctx)
+    assert (stark.omicron_domain_length, stark.fri_domain_length) == (1024, 4096)
+    tcs = [tc.dictionary for tc in cpu.transition_constraints()]
+    got = stark.prove(cpu.rp.trace(sk), tcs, cpu.rp.boundary_constraints(pk), zk.SignatureProofStream(doc), deterministic_rng(b"r2"))
+    assert len(got) == 1156888
+    assert got == want
+    assert cpu.verify(pk, doc, got) is None
+    assert cpu.verify(pk, b"another document", got) is not None
+    # a trace that violates the AIR is caught by the degree check (stark.rs:451-464)
+    bad = [list(r) for r in cpu.rp.trace(sk)]
+    bad[5][1] = (bad[5][1] + 1) % zk.P
+    with pytest.raises(ValueError):
+        stark.prove(bad, tcs, cpu.rp.boundary_constraints(pk), zk.SignatureProofStream(doc), deterministic_rng(b"r2"))
+
+
+def test_stark_prove_independent_stream_through_device_stark(ctx):
+    """stark.rs:810-880: hash-trace proof over an IndependentProofStream (BASELINE configs[0]), device prover == oracle."""
+    from oracle.rescue_prime import RescuePrime
+    from oracle.stark import Stark
+    rp = RescuePrime(2, 1, 128, 27)
+    ref = Stark(4, 64, 128, rp.m, rp.N + 1, 3)
+    x = 0xC0FFEE1234
+    out = rp.hash(x)
+    tcs = rp.transition_constraints(ref.omicron, ref.omicron_domain_length)
+    want = ref.prove(rp.trace(x), tcs, rp.boundary_constraints(out), PS.IndependentProofStream(), deterministic_rng(b"q"))
+    dev = zk.Stark(4, 64, 128, rp.m, rp.N + 1, 3, ctx=ctx)
+    got = dev.prove(rp.trace(x), tcs, rp.boundary_constraints(out), zk.IndependentProofStream(), deterministic_rng(b"q"), check_degrees=False)
+    assert got == want
+    assert ref.verify(tcs, rp.boundary_constraints(out), PS.IndependentProofStream(PS.parse(got))) is None

@@ -11,3 +11,5 @@ from .fft import (ntt, intt, ntt_batch, scale, fast_coset_evaluate, coset_lde_ba
 from .merkle_root import MerkleRoot, MerkleTree                                  # noqa: F401
 from .proof_stream import IndependentProofStream, SignatureProofStream           # noqa: F401
 from .fri import FRI, FriLayers                                                  # noqa: F401
+from .air import air_combination                                                 # noqa: F401
+from .stark import Stark                                                         # noqa: F401

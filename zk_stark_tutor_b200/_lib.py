@@ -21,6 +21,17 @@ class FriParams(ctypes.Structure):
                 ("domain_length", u64), ("expansion_factor", u64), ("num_colinearity_tests", u64)]
 
 
+class AirDesc(ctypes.Structure):
+    _fields_ = [("offset", ctypes.c_uint8 * 16), ("omega", ctypes.c_uint8 * 16),
+                ("domain_length", u64), ("expansion_factor", u64),
+                ("num_registers", ctypes.c_uint32), ("num_constraints", ctypes.c_uint32),
+                ("term_counts", ctypes.POINTER(ctypes.c_uint32)), ("coefs", c_u8p), ("exps", ctypes.POINTER(ctypes.c_uint32)),
+                ("boundary_zerofiers", ctypes.POINTER(vp)), ("boundary_zerofier_lens", ctypes.POINTER(sz)),
+                ("boundary_interpolants", ctypes.POINTER(vp)), ("boundary_interpolant_lens", ctypes.POINTER(sz)),
+                ("transition_zerofier", vp), ("transition_zerofier_len", sz),
+                ("weights", c_u8p), ("shifts", c_u64p)]
+
+
 FS_CALLBACK = ctypes.CFUNCTYPE(ctypes.c_int, vp, ctypes.c_uint32, c_u8p, ctypes.c_int, c_u8p)
 
 # name -> (restype, argtypes); mirrors include/zkb200.h one to one
@@ -90,6 +101,7 @@ PROTOTYPES = {
     "zkb_ps_digest": (sz, [vp, c_u8p, sz]),
     "zkb_ps_fiat_shamir": (ctypes.c_int, [vp, sz, c_u8p]),
     "zkb_fri_prove": (ctypes.c_int, [vp, ctypes.POINTER(FriParams), vp, sz, vp, c_u64p]),
+    "zkb_air_combination": (ctypes.c_int, [vp, ctypes.POINTER(AirDesc), vp, sz, vp, vp, vp]),
 }
 
 

@@ -1,0 +1,188 @@
+"""Stark::prove (src/stark/stark.rs:276-563) with the hot path AND its evaluation-form middle on the B200:
+
+    trace interpolation            fast_interpolate_domain            (stark.rs:303-326)   GPU NTT products
+    boundary quotients             fast_coset_divide                  (stark.rs:331-360)   GPU
+    LDE + Merkle commit            fast_coset_evaluate, commit        (stark.rs:366-386, 424-445)   GPU, codewords + trees stay in HBM
+    transition quotients, x^shift products, weighted combination, LDE of the combination
+                                   (stark.rs:388-519)                 ONE pointwise kernel over the committed codewords
+                                                                      (zkb_air_combination, csrc/air.cu) instead of symbolic
+                                                                      polynomial arithmetic + another LDE
+    FRI::prove                     (stark.rs:522)                     GPU, from the device codeword
+    openings                       (stark.rs:546-560)                 one batched opening per committed tree
+
+The transcript, Fiat-Shamir hops and proof bytes are those of the reference for the same randomness: the
+evaluation-form route computes the same polynomials' values (exact field arithmetic).  The degree bookkeeping
+(stark.rs:115-258) is integer logic on the host, restated here because the prover needs the shifts.
+Rescue-Prime / RPSSS themselves (the AIR's author) are out of scope: the caller hands in the trace,
+the constraint dictionaries and the boundary conditions.  The reference draws randomizers from thread_rng
+(stark.rs:283, 428); here `rng(n) -> n bytes` is a parameter so proofs are reproducible."""
+import numpy as np
+
+from . import fft
+from .air import air_combination
+from .context import P, default_context, unpack
+from .field import Field
+from .fri import FRI
+from .merkle_root import MerkleTree
+from .proof_stream import PROOF_BYTES, ROOT
+
+
+def _bit_count(v):
+    """BitIter::from(v).count() (utils/bit_iter.rs): bits from the highest set bit down; 0 counts one."""
+    return max(v.bit_length(), 1)
+
+
+def _degree(p):
+    d = None
+    for i, c in enumerate(p):
+        if c:
+            d = i
+    return d
+
+
+class Stark:
+    def __init__(self, expansion_factor, num_collinearity_checks, security_level, num_registers, num_cycles,
+                 transition_constraints_degree, ctx=None):
+        """Stark::new stark.rs:71-113"""
+        assert _bit_count(P) >= security_level
+        assert expansion_factor & (expansion_factor - 1) == 0, "expansion_factor must be a power of 2"
+        assert expansion_factor >= 4, "expansion_factor must be at least 4"
+        assert num_collinearity_checks * 2 >= security_level
+        self.ctx = ctx or default_context()
+        self.field = Field()
+        self.expansion_factor = expansion_factor
+        self.num_registers = num_registers
+        self.original_trace_length = num_cycles
+        self.num_randomizers = 4 * num_collinearity_checks
+        randomized_trace_length = num_cycles + self.num_randomizers
+        self.omicron_domain_length = 1 << _bit_count(randomized_trace_length * transition_constraints_degree)
+        self.fri_domain_length = self.omicron_domain_length * expansion_factor
+        self.generator = self.field.generator()
+        self.omega = self.field.primitive_nth_root(self.fri_domain_length)
+        self.omicron = self.field.primitive_nth_root(self.omicron_domain_length)
+        self.fri = FRI(self.generator, self.omega, self.fri_domain_length, expansion_factor, num_collinearity_checks, ctx=self.ctx)
+
+    # ---- degree bookkeeping: walks dictionary KEYS, zero coefficients included (stark.rs:115-184) ----
+    def transition_degree_bounds(self, transition_constraints):
+        points_degree = [1] + [self.original_trace_length + self.num_randomizers - 1] * (2 * self.num_registers)
+        res = []
+        for a in transition_constraints:
+            d = getattr(a, "dictionary", a)
+            assert d, "cannot calculate max on empty vec a"
+            res.append(max(sum(r * l for r, l in zip(points_degree, k)) for k in d))
+        return res
+
+    def transition_quotient_degree_bounds(self, transition_constraints):
+        return [d - (self.original_trace_length - 1) for d in self.transition_degree_bounds(transition_constraints)]
+
+    def max_degree(self, transition_constraints):
+        return (1 << _bit_count(max(self.transition_degree_bounds(transition_constraints)))) - 1
+
+    def _omicron_pow(self, e):
+        return pow(self.omicron, e, P)
+
+    def transition_zerofier(self):                                        # stark.rs:186-194
+        return fft.fast_zerofier(self.omicron, self.omicron_domain_length,
+                                 [self._omicron_pow(i) for i in range(self.original_trace_length - 1)], self.ctx)
+
+    def boundary_zerofiers(self, boundary):                               # stark.rs:196-213
+        return [fft.fast_zerofier(self.omicron, self.omicron_domain_length,
+                                  [self._omicron_pow(c) for c, r, _ in boundary if r == s], self.ctx)
+                for s in range(self.num_registers)]
+
+    def boundary_interpolants(self, boundary):                            # stark.rs:215-243
+        return [fft.fast_interpolate_domain(self.omicron, self.omicron_domain_length,
+                                            [self._omicron_pow(c) for c, r, _ in boundary if r == s],
+                                            [v for _, r, v in boundary if r == s], self.ctx)
+                for s in range(self.num_registers)]
+
+    def sample_weights(self, number, randomness):                         # stark.rs:260-274 (all weights equal: SURVEY.md A.6)
+        return [self.field.sample(bytes(i) + randomness) for i in range(number)]
+
+    def prove(self, trace, transition_constraints, boundary, proof_stream, rng, check_degrees=True):
+        """Returns the proof bytes (proof_stream.digest()).  proof_stream: the library's IndependentProofStream /
+        SignatureProofStream."""
+        import torch
+        ctx, n, nr = self.ctx, self.fri_domain_length, self.num_registers
+        dev = torch.device("cuda", ctx.device)
+        trace = [list(row) for row in trace]
+        for _ in range(self.num_randomizers):                                         # stark.rs:286-301
+            trace.append([self.field.sample(rng(17)) for _ in range(nr)])
+        trace_domain = [self._omicron_pow(i) for i in range(len(trace))]
+        trace_polynomials = [fft.fast_interpolate_domain(self.omicron, self.omicron_domain_length, trace_domain,
+                                                         [row[s] for row in trace], ctx) for s in range(nr)]
+        interpolants = self.boundary_interpolants(boundary)
+        zerofiers = self.boundary_zerofiers(boundary)
+        boundary_quotients = []
+        for s in range(nr):                                                           # stark.rs:331-360
+            num = _psub(trace_polynomials[s], interpolants[s])
+            boundary_quotients.append(fft.fast_coset_divide(self.omicron, self.omicron_domain_length, self.generator, num, zerofiers[s], ctx))
+        # committed codewords live in ONE device buffer: the registers' boundary quotients, then the randomizer
+        cws = torch.empty((nr + 1, n, 2), dtype=torch.int64, device=dev)
+        trees = []
+        try:
+            for s in range(nr):                                                       # stark.rs:366-386
+                self._lde_into(boundary_quotients[s], cws[s])
+                trees.append(MerkleTree(cws[s], ctx))
+                proof_stream.push((ROOT, trees[-1].root()))
+            tz = self.transition_zerofier()
+            tcd = self.max_degree(transition_constraints)
+            randomizer_polynomial = [self.field.sample(rng(17)) for _ in range(tcd + 1)]   # stark.rs:424-432
+            self._lde_into(randomizer_polynomial, cws[nr])
+            trees.append(MerkleTree(cws[nr], ctx))
+            proof_stream.push((ROOT, trees[-1].root()))                               # stark.rs:441-445
+            nc = len(transition_constraints)
+            weights = self.sample_weights(1 + 2 * nc + 2 * nr, proof_stream.fiat_shamir_prover(PROOF_BYTES))
+            tq_bounds = self.transition_quotient_degree_bounds(transition_constraints)
+            bq_bounds = [len(trace) - 1 - _degree(bz) for bz in zerofiers]            # stark.rs:245-258
+            shifts = [tcd - b for b in tq_bounds] + [tcd - b for b in bq_bounds]
+            # stark.rs:388-519 in evaluation form: quotients, x^shift products, weighted sum - one kernel, one codeword out
+            res = air_combination(self.generator, self.omega, n, self.expansion_factor, transition_constraints, zerofiers, interpolants,
+                                  tz, weights, shifts, cws[:nr], cws[nr], want_quotients=check_degrees, ctx=ctx)
+            if check_degrees:                                                         # stark.rs:451-464
+                combined, tq_cws = res
+                for j in range(nc):
+                    deg = self._coset_degree(tq_cws[j])
+                    if deg is None:
+                        raise ValueError("Failed to get degree of transition quotient")
+                    if deg != tq_bounds[j]:
+                        raise ValueError("transition quotient degrees do not match with expectation")
+            else:
+                combined = res
+            indices = self.fri.prove(combined, proof_stream)                          # stark.rs:522
+            dup = list(indices) + [(i + self.expansion_factor) % n for i in indices]  # stark.rs:524-543
+            quad = sorted(dup + [(i + n // 2) % n for i in dup])
+            for t in trees:                                                           # stark.rs:546-560
+                t.open_into(quad, proof_stream)
+            return proof_stream.digest()
+        finally:
+            for t in trees:
+                t.close()
+
+    def _lde_into(self, coefficients, out):
+        ctx = self.ctx
+        from .context import Vec, le16
+        v = Vec(list(coefficients))
+        ctx.check(ctx.lib.zkb_coset_lde(ctx.h, le16(self.omega), self.fri_domain_length, le16(self.generator),
+                                        v.ptr if v.n else None, v.n, out.data_ptr()))
+
+    def _coset_degree(self, codeword):
+        """degree of the polynomial whose values on offset*<omega> are `codeword` (iNTT, then un-scale)"""
+        coeffs = fft.intt(self.omega, codeword, self.ctx)            # values of p(offset * x) -> coefficients c_i * offset^i
+        host = unpack(coeffs.cpu().numpy().view(np.uint64))          # offset != 0, so the degree is unchanged by the scale
+        return _degree(host)
+
+
+def _psub(a, b):
+    """Polynomial - (polynomial.rs:252-288): a + (-b) with the reference's early returns for zero operands"""
+    nb = [(-c) % P for c in b]
+    if _degree(a) is None:
+        return nb
+    if _degree(nb) is None:
+        return list(a)
+    out = [0] * max(len(a), len(nb))
+    for i, c in enumerate(a):
+        out[i] = (out[i] + c) % P
+    for i, c in enumerate(nb):
+        out[i] = (out[i] + c) % P
+    return out
