@@ -1,0 +1,59 @@
+"""Host-side algorithms of zk_stark_tutor_b200/stark.py (the device Stark prover) on the CPU, with the oracle's
+NTT products injected where the product code calls the GPU: the subgroup-prefix interpolation that replaces the
+reference's divide-and-conquer fast_interpolate_domain for trace columns (stark.rs:305-326), the small Lagrange
+interpolation of boundary conditions, and the degree bookkeeping (stark.rs:115-258) against the oracle's."""
+import random
+
+import pytest
+
+from oracle import field as F, ntt as N, poly as PL
+from oracle.stark import RPSSS
+from zk_stark_tutor_b200 import stark as S
+
+P = F.P
+
+
+@pytest.mark.parametrize("L,Nn", [(284, 1024), (1, 4), (2, 4), (5, 8), (7, 8), (8, 8), (100, 128), (129, 256)])
+def test_prefix_interpolator_equals_fast_interpolate_domain(L, Nn):
+    rnd = random.Random(L * 1000 + Nn)
+    w, big = F.primitive_nth_root(Nn), F.primitive_nth_root(4 * Nn)
+    dom = [F.fpow(w, i) for i in range(L)]
+    Z = PL.fast_zerofier(w, Nn, dom) if 1 < L < Nn else [(-1) % P, 1]
+    it = S.PrefixInterpolator(L, Nn, Z, mul=lambda a, b: N.fast_multiply(big, 4 * Nn, a, b), intt=lambda v: N.intt(w, v))
+    for vals in ([rnd.randrange(P) for _ in range(L)], [0] * L, [7] * L, [P - 1] + [0] * (L - 1)):
+        got = it(vals)
+        assert len(got) <= max(L, Nn if L == Nn else L)
+        assert [PL.evaluate(got, x) for x in dom] == [v % P for v in vals]
+        assert (PL.degree(got) or 0) < L
+        if L > 1:
+            want = PL.fast_interpolate_domain(w, Nn, dom, vals)
+            d = PL.degree(want)
+            assert PL.degree(got) == d and (d is None or got[:d + 1] == want[:d + 1])
+
+
+def test_lagrange_interpolate_small_domains():
+    rnd = random.Random(3)
+    w = F.primitive_nth_root(1024)
+    for k in (1, 2, 3, 8):
+        dom = [F.fpow(w, rnd.randrange(1024)) for _ in range(k)]
+        if len(set(dom)) < k:
+            continue
+        vals = [rnd.randrange(P) for _ in range(k)]
+        got = S.lagrange_interpolate(dom, vals)
+        assert [PL.evaluate(got, x) for x in dom] == vals
+        if k > 1:
+            want = PL.fast_interpolate_domain(w, 1024, dom, vals)
+            d = PL.degree(want)
+            assert PL.degree(got) == d and got[:d + 1] == want[:d + 1]
+
+
+def test_degree_bookkeeping_equals_oracle():
+    """stark.rs:115-258 restated in the product prover == the oracle's restatement, on the Rescue-Prime AIR"""
+    r = RPSSS(4, 64, 128, 3)
+    tcs = r.transition_constraints()
+    dev = S.Stark.__new__(S.Stark)                       # the bookkeeping needs no device
+    dev.original_trace_length, dev.num_randomizers, dev.num_registers = r.stark.original_trace_length, r.stark.num_randomizers, r.stark.num_registers
+    assert dev.transition_degree_bounds(tcs) == r.stark.transition_degree_bounds(tcs)
+    assert dev.transition_quotient_degree_bounds([t.dictionary for t in tcs]) == r.stark.transition_quotient_degree_bounds(tcs)
+    assert dev.max_degree(tcs) == r.stark.max_degree(tcs) == 1023
+    assert S._bit_count(0) == 1 and S._bit_count(1) == 1 and S._bit_count(852) == 10

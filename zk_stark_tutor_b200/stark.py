@@ -16,15 +16,74 @@ evaluation-form route computes the same polynomials' values (exact field arithme
 Rescue-Prime / RPSSS themselves (the AIR's author) are out of scope: the caller hands in the trace,
 the constraint dictionaries and the boundary conditions.  The reference draws randomizers from thread_rng
 (stark.rs:283, 428); here `rng(n) -> n bytes` is a parameter so proofs are reproducible."""
-import numpy as np
-
 from . import fft
 from .air import air_combination
-from .context import P, default_context, unpack
+from .context import P, default_context
 from .field import Field
 from .fri import FRI
 from .merkle_root import MerkleTree
 from .proof_stream import PROOF_BYTES, ROOT
+
+
+class PrefixInterpolator:
+    """The polynomial of degree < L through (root^i, values[i]), i < L, where the points are a PREFIX of the order-N
+    subgroup <root> - the shape of Stark's trace domain (stark.rs:305-326: omicron^0 .. omicron^(trace_len-1)).
+
+    The reference interpolates with a divide-and-conquer over arbitrary points (fast_interpolate_domain,
+    ntt_arithmetics.rs:172-237: O(L log^2 L) products plus schoolbook remainders).  On a subgroup prefix the same - unique -
+    polynomial is the remainder of ANY degree < N polynomial that takes the values on the prefix, modulo the prefix's
+    zerofier Z:   p = iNTT(values || 0...) mod Z.   Z and the power-series inverse of its reversal depend only on (L, N) and
+    are computed once; per column that leaves one iNTT and two NTT products (fast division), all on the GPU.
+    `mul(a, b)`, `intt(values)` are injected so the algorithm can be checked on the CPU against the oracle."""
+
+    def __init__(self, L, N, zerofier, mul, intt):
+        assert 0 < L <= N
+        self.L, self.N, self.mul, self.intt = L, N, mul, intt
+        self.m = N - L                                    # number of quotient coefficients for a dividend of degree < N
+        if self.m:                                        # (L == N: the prefix is the whole subgroup, the iNTT is the answer)
+            assert len(zerofier) >= L + 1 and zerofier[L] == 1 and not any(zerofier[L + 1:]), "Z must be monic of degree L"
+            self.Z = list(zerofier[:L + 1])
+            f = self.Z[::-1][:self.m]                      # rev(Z) mod x^m; f[0] = 1
+            f += [0] * (self.m - len(f))
+            g = [1]
+            while len(g) < self.m:                         # Newton: g <- g * (2 - f*g) mod x^(2 len g)
+                k = min(2 * len(g), self.m)
+                t = [(-c) % P for c in self._mul_trunc(f[:k], g, k)]
+                t[0] = (t[0] + 2) % P
+                g = self._mul_trunc(g, t, k)
+            self.inv_rev_Z = g
+
+    def _mul_trunc(self, a, b, k):
+        out = list(self.mul(list(a), list(b)))[:k]
+        return out + [0] * (k - len(out))
+
+    def __call__(self, values):
+        L, N, m = self.L, self.N, self.m
+        assert len(values) == L
+        if L == 1:
+            return [values[0] % P]
+        pt = list(self.intt(list(values) + [0] * (N - L)))     # degree < N, right on the prefix (and zero on the rest)
+        if m == 0:
+            return pt
+        q_rev = self._mul_trunc(pt[::-1][:m], self.inv_rev_Z, m)   # rev(quotient) = rev(pt) * rev(Z)^-1 mod x^m
+        zq = self._mul_trunc(self.Z, q_rev[::-1], N)
+        return [(pt[i] - zq[i]) % P for i in range(L)]
+
+
+def lagrange_interpolate(domain, values):
+    """Polynomial::interpolate_domain (polynomial.rs:123-148) for a handful of points (the boundary conditions):
+    exact host arithmetic; the interpolant is unique, so it is the polynomial fast_interpolate_domain returns."""
+    acc = [0] * len(domain)
+    for i, xi in enumerate(domain):
+        num, den = [values[i] % P], 1
+        for j, xj in enumerate(domain):
+            if i != j:
+                num = [(a - xj * b) % P for a, b in zip([0] + num, num + [0])]        # num * (x - xj)
+                den = den * (xi - xj) % P
+        inv = pow(den, P - 2, P)
+        for k, c in enumerate(num):
+            acc[k] = (acc[k] + c * inv) % P
+    return acc
 
 
 def _bit_count(v):
@@ -61,6 +120,7 @@ class Stark:
         self.omega = self.field.primitive_nth_root(self.fri_domain_length)
         self.omicron = self.field.primitive_nth_root(self.omicron_domain_length)
         self.fri = FRI(self.generator, self.omega, self.fri_domain_length, expansion_factor, num_collinearity_checks, ctx=self.ctx)
+        self._cache = {}          # what depends on the AIR's shape only: zerofiers, the trace-domain interpolator
 
     # ---- degree bookkeeping: walks dictionary KEYS, zero coefficients included (stark.rs:115-184) ----
     def transition_degree_bounds(self, transition_constraints):
@@ -81,20 +141,46 @@ class Stark:
     def _omicron_pow(self, e):
         return pow(self.omicron, e, P)
 
+    def _prefix_zerofier(self, length):
+        """zerofier of omicron^0 .. omicron^(length-1) (fast_zerofier, ntt_arithmetics.rs:66-108); depends on the shape only"""
+        key = ("zerofier", length)
+        if key not in self._cache:
+            self._cache[key] = fft.fast_zerofier(self.omicron, self.omicron_domain_length, [self._omicron_pow(i) for i in range(length)], self.ctx)
+        return self._cache[key]
+
     def transition_zerofier(self):                                        # stark.rs:186-194
-        return fft.fast_zerofier(self.omicron, self.omicron_domain_length,
-                                 [self._omicron_pow(i) for i in range(self.original_trace_length - 1)], self.ctx)
+        return self._prefix_zerofier(self.original_trace_length - 1)
 
     def boundary_zerofiers(self, boundary):                               # stark.rs:196-213
-        return [fft.fast_zerofier(self.omicron, self.omicron_domain_length,
-                                  [self._omicron_pow(c) for c, r, _ in boundary if r == s], self.ctx)
-                for s in range(self.num_registers)]
+        out = []
+        for s in range(self.num_registers):
+            key = ("boundary_zerofier",) + tuple(c for c, r, _ in boundary if r == s)
+            if key not in self._cache:
+                self._cache[key] = fft.fast_zerofier(self.omicron, self.omicron_domain_length, [self._omicron_pow(c) for c in key[1:]], self.ctx)
+            out.append(self._cache[key])
+        return out
 
     def boundary_interpolants(self, boundary):                            # stark.rs:215-243
-        return [fft.fast_interpolate_domain(self.omicron, self.omicron_domain_length,
-                                            [self._omicron_pow(c) for c, r, _ in boundary if r == s],
-                                            [v for _, r, v in boundary if r == s], self.ctx)
-                for s in range(self.num_registers)]
+        out = []
+        for s in range(self.num_registers):
+            domain = [self._omicron_pow(c) for c, r, _ in boundary if r == s]
+            values = [v for _, r, v in boundary if r == s]
+            if len(domain) <= 8:
+                out.append(lagrange_interpolate(domain, values))
+            else:
+                out.append(fft.fast_interpolate_domain(self.omicron, self.omicron_domain_length, domain, values, self.ctx))
+        return out
+
+    def trace_interpolator(self, length):
+        """stark.rs:305-326 for every column of a trace of `length` rows (see PrefixInterpolator)"""
+        key = ("interpolator", length)
+        if key not in self._cache:
+            ctx, n = self.ctx, self.fri_domain_length
+            self._cache[key] = PrefixInterpolator(
+                length, self.omicron_domain_length, self._prefix_zerofier(length),
+                mul=lambda a, b: fft.fast_multiply(self.omega, n, a, b, ctx),        # products of degree < 2*omicron_domain_length <= n
+                intt=lambda v: fft.intt(self.omicron, v, ctx))
+        return self._cache[key]
 
     def sample_weights(self, number, randomness):                         # stark.rs:260-274 (all weights equal: SURVEY.md A.6)
         return [self.field.sample(bytes(i) + randomness) for i in range(number)]
@@ -108,9 +194,8 @@ class Stark:
         trace = [list(row) for row in trace]
         for _ in range(self.num_randomizers):                                         # stark.rs:286-301
             trace.append([self.field.sample(rng(17)) for _ in range(nr)])
-        trace_domain = [self._omicron_pow(i) for i in range(len(trace))]
-        trace_polynomials = [fft.fast_interpolate_domain(self.omicron, self.omicron_domain_length, trace_domain,
-                                                         [row[s] for row in trace], ctx) for s in range(nr)]
+        interpolate = self.trace_interpolator(len(trace))                            # stark.rs:303-326
+        trace_polynomials = [interpolate([row[s] for row in trace]) for s in range(nr)]
         interpolants = self.boundary_interpolants(boundary)
         zerofiers = self.boundary_zerofiers(boundary)
         boundary_quotients = []
@@ -167,10 +252,11 @@ class Stark:
                                         v.ptr if v.n else None, v.n, out.data_ptr()))
 
     def _coset_degree(self, codeword):
-        """degree of the polynomial whose values on offset*<omega> are `codeword` (iNTT, then un-scale)"""
-        coeffs = fft.intt(self.omega, codeword, self.ctx)            # values of p(offset * x) -> coefficients c_i * offset^i
-        host = unpack(coeffs.cpu().numpy().view(np.uint64))          # offset != 0, so the degree is unchanged by the scale
-        return _degree(host)
+        """degree of the polynomial whose values on offset*<omega> are `codeword`: iNTT gives c_i * offset^i, and
+        offset != 0, so the last non-zero entry is the degree (no un-scaling needed)"""
+        coeffs = fft.intt(self.omega, codeword, self.ctx)
+        nz = (coeffs != 0).any(dim=1).nonzero()
+        return int(nz[-1]) if nz.numel() else None
 
 
 def _psub(a, b):
