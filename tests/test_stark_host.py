@@ -31,6 +31,28 @@ def test_prefix_interpolator_equals_fast_interpolate_domain(L, Nn):
             assert PL.degree(got) == d and (d is None or got[:d + 1] == want[:d + 1])
 
 
+def test_prefix_interpolator_array_mode():
+    """the GPU path keeps coefficient vectors as (n, 2) uint64 arrays between library calls"""
+    from oracle import cbind as C
+    L, Nn = 284, 1024
+    rnd = random.Random(11)
+    w, big = F.primitive_nth_root(Nn), F.primitive_nth_root(4 * Nn)
+    dom = [F.fpow(w, i) for i in range(L)]
+    mul = lambda a, b: N.fast_multiply(big, 4 * Nn, a, b)                                     # noqa: E731
+    amul = lambda a, b: C.to_arr(N.fast_multiply(big, 4 * Nn, C.from_arr(a), C.from_arr(b)))  # noqa: E731
+    aintt = lambda v: C.to_arr(N.intt(w, C.from_arr(v)))                                      # noqa: E731
+    it = S.PrefixInterpolator(L, Nn, PL.fast_zerofier(w, Nn, dom), mul, lambda v: N.intt(w, v))
+    vals = [rnd.randrange(P) for _ in range(L)]
+    want = it(vals)
+    assert it.use_arrays(amul, aintt)(vals) == want
+    assert [PL.evaluate(want, x) for x in dom[:7]] == vals[:7]
+
+
+def test_sample_is_field_sample():
+    for data in (bytes.fromhex("6c9c4992"), bytes.fromhex("ac4cd3be"), bytes(range(17)), b"\xff" * 40, b""):
+        assert S.Stark.sample(data) == F.sample(data)
+
+
 def test_lagrange_interpolate_small_domains():
     rnd = random.Random(3)
     w = F.primitive_nth_root(1024)

@@ -37,7 +37,8 @@ def air_combination(offset, omega, domain_length, expansion_factor, constraints,
     nr, n = bq_codewords.shape[0], domain_length
     assert tuple(bq_codewords.shape) == (nr, n, 2) and bq_codewords.is_cuda and bq_codewords.is_contiguous()
     assert tuple(randomizer_codeword.shape) == (n, 2) and randomizer_codeword.is_cuda and randomizer_codeword.is_contiguous()
-    counts, coefs, exps = flatten_constraints(constraints, nr)
+    # a (term_counts, coefs, exps) tuple is taken as already flattened (a prover flattens its AIR once, not per proof)
+    counts, coefs, exps = constraints if isinstance(constraints, tuple) else flatten_constraints(constraints, nr)
     nc = len(counts)
     assert len(weights) == 1 + 2 * nc + 2 * nr and len(shifts) == nc + nr
     d = _lib.AirDesc()

@@ -16,9 +16,11 @@ evaluation-form route computes the same polynomials' values (exact field arithme
 Rescue-Prime / RPSSS themselves (the AIR's author) are out of scope: the caller hands in the trace,
 the constraint dictionaries and the boundary conditions.  The reference draws randomizers from thread_rng
 (stark.rs:283, 428); here `rng(n) -> n bytes` is a parameter so proofs are reproducible."""
+import numpy as np
+
 from . import fft
 from .air import air_combination
-from .context import P, default_context
+from .context import P, default_context, pack, unpack
 from .field import Field
 from .fri import FRI
 from .merkle_root import MerkleTree
@@ -38,7 +40,8 @@ class PrefixInterpolator:
 
     def __init__(self, L, N, zerofier, mul, intt):
         assert 0 < L <= N
-        self.L, self.N, self.mul, self.intt = L, N, mul, intt
+        self.L, self.N, self.array_mode = L, N, False
+        self.mul, self.intt = mul, intt
         self.m = N - L                                    # number of quotient coefficients for a dividend of degree < N
         if self.m:                                        # (L == N: the prefix is the whole subgroup, the iNTT is the answer)
             assert len(zerofier) >= L + 1 and zerofier[L] == 1 and not any(zerofier[L + 1:]), "Z must be monic of degree L"
@@ -52,22 +55,50 @@ class PrefixInterpolator:
                 t[0] = (t[0] + 2) % P
                 g = self._mul_trunc(g, t, k)
             self.inv_rev_Z = g
+            self.Z_arr, self.inv_arr = pack(self.Z), pack(g)
+
+    def use_arrays(self, mul, intt):
+        """switch to (n, 2) uint64 arrays end to end (mul / intt then take and return arrays)"""
+        self.mul, self.intt, self.array_mode = mul, intt, True
+        return self
+
+    # coefficient vectors are lists of ints (CPU tests, oracle products) or (n, 2) uint64 arrays (the GPU path: no per-element
+    # packing on the way to the library); only structural operations happen here, plus one subtraction on the L results
+    @staticmethod
+    def _zeros(like, k):
+        return np.zeros((k, 2), dtype=np.uint64) if isinstance(like, np.ndarray) else [0] * k
+
+    @classmethod
+    def _fit(cls, a, k):
+        a = a[:k]
+        if len(a) == k:
+            return a
+        pad = cls._zeros(a, k - len(a))
+        return np.concatenate([a.reshape(-1, 2), pad]) if isinstance(a, np.ndarray) else list(a) + pad
+
+    @staticmethod
+    def _rev(a):
+        return np.ascontiguousarray(a[::-1]) if isinstance(a, np.ndarray) else a[::-1]
 
     def _mul_trunc(self, a, b, k):
-        out = list(self.mul(list(a), list(b)))[:k]
-        return out + [0] * (k - len(out))
+        return self._fit(self.mul(a, b), k)
 
     def __call__(self, values):
         L, N, m = self.L, self.N, self.m
         assert len(values) == L
         if L == 1:
-            return [values[0] % P]
-        pt = list(self.intt(list(values) + [0] * (N - L)))     # degree < N, right on the prefix (and zero on the rest)
+            return [int(values[0]) % P]
+        as_array = self.array_mode
+        v = pack([int(x) for x in values]) if as_array else list(values)
+        pt = self.intt(self._fit(v, N))                        # degree < N, right on the prefix (and zero on the rest)
         if m == 0:
-            return pt
-        q_rev = self._mul_trunc(pt[::-1][:m], self.inv_rev_Z, m)   # rev(quotient) = rev(pt) * rev(Z)^-1 mod x^m
-        zq = self._mul_trunc(self.Z, q_rev[::-1], N)
-        return [(pt[i] - zq[i]) % P for i in range(L)]
+            return unpack(pt) if as_array else list(pt)
+        Z = self.Z_arr if as_array else self.Z
+        g = self.inv_arr if as_array else self.inv_rev_Z
+        q_rev = self._mul_trunc(self._fit(self._rev(pt), m), g, m)   # rev(quotient) = rev(pt) * rev(Z)^-1 mod x^m
+        zq = self._mul_trunc(Z, self._rev(q_rev), N)
+        a, b = (unpack(pt[:L]), unpack(zq[:L])) if as_array else (pt[:L], zq[:L])
+        return [(x - y) % P for x, y in zip(a, b)]
 
 
 def lagrange_interpolate(domain, values):
@@ -176,14 +207,18 @@ class Stark:
         key = ("interpolator", length)
         if key not in self._cache:
             ctx, n = self.ctx, self.fri_domain_length
-            self._cache[key] = PrefixInterpolator(
-                length, self.omicron_domain_length, self._prefix_zerofier(length),
-                mul=lambda a, b: fft.fast_multiply(self.omega, n, a, b, ctx),        # products of degree < 2*omicron_domain_length <= n
-                intt=lambda v: fft.intt(self.omicron, v, ctx))
+            mul = lambda a, b: fft.fast_multiply(self.omega, n, a, b, ctx)           # noqa: E731  products of degree < 2*omicron_domain_length <= n
+            intt = lambda v: fft.intt(self.omicron, v, ctx)                           # noqa: E731
+            self._cache[key] = PrefixInterpolator(length, self.omicron_domain_length, self._prefix_zerofier(length), mul, intt).use_arrays(mul, intt)
         return self._cache[key]
 
+    @staticmethod
+    def sample(data):
+        """Field::sample field.rs:87-99: the wrapping shift-xor fold keeps the big-endian value of the LAST 16 bytes; then % p"""
+        return int.from_bytes(bytes(data)[-16:], "big") % P
+
     def sample_weights(self, number, randomness):                         # stark.rs:260-274 (all weights equal: SURVEY.md A.6)
-        return [self.field.sample(bytes(i) + randomness) for i in range(number)]
+        return [self.sample(bytes(i) + randomness) for i in range(number)]
 
     def prove(self, trace, transition_constraints, boundary, proof_stream, rng, check_degrees=True):
         """Returns the proof bytes (proof_stream.digest()).  proof_stream: the library's IndependentProofStream /
@@ -193,7 +228,7 @@ class Stark:
         dev = torch.device("cuda", ctx.device)
         trace = [list(row) for row in trace]
         for _ in range(self.num_randomizers):                                         # stark.rs:286-301
-            trace.append([self.field.sample(rng(17)) for _ in range(nr)])
+            trace.append([self.sample(rng(17)) for _ in range(nr)])
         interpolate = self.trace_interpolator(len(trace))                            # stark.rs:303-326
         trace_polynomials = [interpolate([row[s] for row in trace]) for s in range(nr)]
         interpolants = self.boundary_interpolants(boundary)
@@ -211,18 +246,18 @@ class Stark:
                 trees.append(MerkleTree(cws[s], ctx))
                 proof_stream.push((ROOT, trees[-1].root()))
             tz = self.transition_zerofier()
-            tcd = self.max_degree(transition_constraints)
-            randomizer_polynomial = [self.field.sample(rng(17)) for _ in range(tcd + 1)]   # stark.rs:424-432
+            tcd = self._air_shape(transition_constraints)[0]
+            randomizer_polynomial = [self.sample(rng(17)) for _ in range(tcd + 1)]   # stark.rs:424-432
             self._lde_into(randomizer_polynomial, cws[nr])
             trees.append(MerkleTree(cws[nr], ctx))
             proof_stream.push((ROOT, trees[-1].root()))                               # stark.rs:441-445
             nc = len(transition_constraints)
             weights = self.sample_weights(1 + 2 * nc + 2 * nr, proof_stream.fiat_shamir_prover(PROOF_BYTES))
-            tq_bounds = self.transition_quotient_degree_bounds(transition_constraints)
+            tcd, tq_bounds, flat = self._air_shape(transition_constraints)
             bq_bounds = [len(trace) - 1 - _degree(bz) for bz in zerofiers]            # stark.rs:245-258
             shifts = [tcd - b for b in tq_bounds] + [tcd - b for b in bq_bounds]
             # stark.rs:388-519 in evaluation form: quotients, x^shift products, weighted sum - one kernel, one codeword out
-            res = air_combination(self.generator, self.omega, n, self.expansion_factor, transition_constraints, zerofiers, interpolants,
+            res = air_combination(self.generator, self.omega, n, self.expansion_factor, flat, zerofiers, interpolants,
                                   tz, weights, shifts, cws[:nr], cws[nr], want_quotients=check_degrees, ctx=ctx)
             if check_degrees:                                                         # stark.rs:451-464
                 combined, tq_cws = res
@@ -243,6 +278,16 @@ class Stark:
         finally:
             for t in trees:
                 t.close()
+
+    def _air_shape(self, transition_constraints):
+        """(max_degree, transition quotient degree bounds, flattened terms) of an AIR: computed once per constraint list
+        (the list is kept alive by the cache entry, so its id cannot be recycled)"""
+        key = ("air", id(transition_constraints))
+        if key not in self._cache:
+            from .air import flatten_constraints
+            self._cache[key] = (self.max_degree(transition_constraints), self.transition_quotient_degree_bounds(transition_constraints),
+                                flatten_constraints(transition_constraints, self.num_registers), transition_constraints)
+        return self._cache[key][:3]
 
     def _lde_into(self, coefficients, out):
         ctx = self.ctx
