@@ -99,3 +99,22 @@ def test_stark_prove_independent_stream_through_device_stark(ctx):
     got = dev.prove(rp.trace(x), tcs, rp.boundary_constraints(out), zk.IndependentProofStream(), deterministic_rng(b"q"), check_degrees=False)
     assert got == want
     assert ref.verify(tcs, rp.boundary_constraints(out), PS.IndependentProofStream(PS.parse(got))) is None
+
+
+def test_committed_rpsss_fixture_signatures(ctx):
+    """tests/golden/rpsss_air.json (AIR, traces, boundary conditions as data + the oracle prover's signature digests):
+    zk.Stark.prove reproduces every committed digest - the check bench.py's `signatures` workload repeats before timing."""
+    import hashlib
+    import json
+    import os
+    from zk_stark_tutor_b200.stark import deterministic_rng as drng
+    fx = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "rpsss_air.json")))
+    pr = fx["params"]
+    stark = zk.Stark(pr["expansion_factor"], pr["num_collinearity_checks"], pr["security_level"], pr["num_registers"], pr["num_cycles"],
+                     pr["transition_constraints_degree"], ctx=ctx)
+    tcs = [{tuple(k): int(v) for k, v in tc} for tc in fx["transition_constraints"]]
+    for c in fx["cases"]:
+        sig = stark.prove([[int(v) for v in row] for row in c["trace"]], tcs, [(cy, reg, int(v)) for cy, reg, v in c["boundary"]],
+                          zk.SignatureProofStream(c["document"].encode()), drng(c["rng_seed"].encode()))
+        assert len(sig) == c["signature_bytes"] == 1156888
+        assert hashlib.sha256(sig).hexdigest() == c["signature_sha256"]

@@ -117,6 +117,19 @@ def lagrange_interpolate(domain, values):
     return acc
 
 
+def deterministic_rng(seed: bytes):
+    """A reproducible stand-in for thread_rng().fill_bytes (stark.rs:283, 428): call k returns SHAKE256(seed || u64_be(k)).
+    Production callers pass os.urandom."""
+    import hashlib
+    state = {"n": 0}
+
+    def fill(n):
+        out = hashlib.shake_256(seed + state["n"].to_bytes(8, "big")).digest(n)
+        state["n"] += 1
+        return out
+    return fill
+
+
 def _bit_count(v):
     """BitIter::from(v).count() (utils/bit_iter.rs): bits from the highest set bit down; 0 counts one."""
     return max(v.bit_length(), 1)
