@@ -313,6 +313,7 @@ class Stark:
         """degree of the polynomial whose values on offset*<omega> are `codeword`: iNTT gives c_i * offset^i, and
         offset != 0, so the last non-zero entry is the degree (no un-scaling needed)"""
         coeffs = fft.intt(self.omega, codeword, self.ctx)
+        self.ctx.sync()                                   # the context may run on its own stream; torch reads on its current one
         nz = (coeffs != 0).any(dim=1).nonzero()
         return int(nz[-1]) if nz.numel() else None
 
