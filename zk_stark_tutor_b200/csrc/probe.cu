@@ -10,7 +10,7 @@
 // per second over the whole GPU (one SASS instruction = 32 lane-ops).
 #include <cuda_runtime.h>
 #include <stdint.h>
-#include "blake2b.cuh"
+#include "blake2b_variants.cuh"
 
 #define CH 8
 #define UNROLL 16
