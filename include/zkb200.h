@@ -258,6 +258,51 @@ typedef struct zkb_air_desc {
 int zkb_air_combination(zkb_ctx* ctx, const zkb_air_desc* desc, const void* bq_codewords, size_t bq_stride,
                         const void* randomizer_codeword, void* combined_out, void* tq_out);
 
+/* The same pipeline for batches of instances of ONE AIR, and with the boundary quotients in evaluation form as well
+ * (stark.rs:331-360 on the coset: bq = (t - I) / Z_B pointwise from the trace codewords).  What depends on the AIR's shape only
+ * - grouped constraint terms, zerofier codewords and their inverses - lives in a handle created once. */
+typedef struct zkb_air zkb_air;
+typedef struct zkb_air_shape {
+    uint8_t offset[16];
+    uint8_t omega[16];
+    uint64_t domain_length;
+    uint64_t expansion_factor;
+    uint32_t num_registers;
+    uint32_t num_constraints;
+    const uint32_t* term_counts;
+    const uint8_t* coefs;
+    const uint32_t* exps;
+    const void* const* boundary_zerofiers;
+    const size_t* boundary_zerofier_lens;
+    const void* transition_zerofier;
+    size_t transition_zerofier_len;
+    const uint64_t* shifts;
+} zkb_air_shape;
+int zkb_air_create(zkb_ctx* ctx, const zkb_air_shape* shape, zkb_air** out);
+void zkb_air_free(zkb_air* air);
+/* the instances' boundary interpolants (stark.rs:215-243): batch x num_registers coefficient vectors of interp_len values each
+ * (zero padded), instance-major; evaluated on the coset and kept in the handle for the two calls below */
+int zkb_air_set_interpolants(zkb_air* air, size_t batch, const void* interpolants, size_t interp_len);
+/* trace codewords -> boundary-quotient codewords; register s of instance b at + s*stride + b*inst elements (DEVICE) */
+int zkb_air_boundary_quotients(zkb_air* air, size_t batch, const void* trace_codewords, size_t trace_stride, size_t trace_inst,
+                               void* bq_out, size_t bq_stride, size_t bq_inst);
+/* weights: batch x (1 + 2*num_constraints + 2*num_registers) x 16 bytes (host); everything else DEVICE; tq_out may be NULL */
+int zkb_air_combine(zkb_air* air, size_t batch, const uint8_t* weights, const void* bq, size_t bq_stride, size_t bq_inst,
+                    const void* randomizer, size_t randomizer_inst, void* combined_out, size_t out_inst, void* tq_out, size_t tq_inst);
+
+/* Trace interpolation + evaluation on the FRI coset for `batch` columns (stark.rs:303-326, then ntt_arithmetics.rs:161-170):
+ * column c holds `length` values (host or device, at values + c*stride elements) on omicron^0 .. omicron^(length-1), a PREFIX
+ * of the order-omicron_order subgroup; out (DEVICE) receives `order` evaluations on offset*<omega> per column at + c*out_stride.
+ * The interpolant is iNTT(values || 0...) mod the prefix zerofier - the polynomial fast_interpolate_domain returns - computed with
+ * cached per-(length, omicron_order) tables.  coeffs_out: NULL, or DEVICE batch x length coefficients. */
+int zkb_trace_lde_batch(zkb_ctx* ctx, const uint8_t omicron[16], uint64_t omicron_order, uint64_t length, const uint8_t omega[16],
+                        uint64_t order, const uint8_t offset[16], const void* values, size_t stride, size_t batch, void* out,
+                        size_t out_stride, void* coeffs_out);
+/* Polynomial::degree (polynomial.rs:46-63) of the polynomials whose values on a coset offset*<omega> are the given DEVICE
+ * codewords (iNTT + scan); -1 for the zero polynomial.  Used for the degree check of stark.rs:451-464. */
+int zkb_coset_degree_batch(zkb_ctx* ctx, const uint8_t omega[16], const void* codewords, size_t n, size_t stride, size_t batch,
+                           int64_t* degrees_out);
+
 /* ---- batches of small independent instances (RPSSS-shaped proofs) ---------------------
  * One proof at a 4096-point FRI domain cannot fill a GPU; independent proofs advance in lockstep instead:
  * every launch carries all instances.  Per instance the results are byte-identical to the single-instance

@@ -44,7 +44,7 @@ def prover_intermediates(seed=b"air"):
     shifts = [tcd - b for b in st.transition_quotient_degree_bounds(tcs)] + [tcd - b for b in st.boundary_quotient_degree_bounds(trace_len, boundary)]
     return dict(stark=st, tcs=tcs, boundary=boundary, signature=sig, nr=nr, nc=nc, n=n,
                 bq_cws=log["lde"][:nr], rnd_cw=log["lde"][nr], combined=log["lde"][nr + 1],
-                tq_polys=log["div"][nr:nr + nc], weights=log["weights"], shifts=shifts,
+                bq_polys=log["div"][:nr], tq_polys=log["div"][nr:nr + nc], weights=log["weights"], shifts=shifts,
                 zerofiers=zerofiers, interpolants=st.boundary_interpolants(boundary), tz=st.transition_zerofier())
 
 

@@ -118,3 +118,67 @@ def test_committed_rpsss_fixture_signatures(ctx):
                           zk.SignatureProofStream(c["document"].encode()), drng(c["rng_seed"].encode()))
         assert len(sig) == c["signature_bytes"] == 1156888
         assert hashlib.sha256(sig).hexdigest() == c["signature_sha256"]
+
+
+def _fixture():
+    import json
+    import os
+    fx = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "rpsss_air.json")))
+    tcs = [{tuple(k): int(v) for k, v in tc} for tc in fx["transition_constraints"]]
+    cases = [dict(trace=[[int(v) for v in row] for row in c["trace"]], boundary=[(cy, reg, int(v)) for cy, reg, v in c["boundary"]],
+                  doc=c["document"].encode(), seed=c["rng_seed"].encode(), sha=c["signature_sha256"]) for c in fx["cases"]]
+    return fx["params"], tcs, cases
+
+
+def test_trace_lde_batch_equals_interpolate_then_lde(ctx):
+    """zkb_trace_lde_batch (iNTT mod the prefix zerofier, then coset LDE) == fast_interpolate_domain + fast_coset_evaluate (stark.rs:305-326, 373-378)"""
+    import ctypes
+    import random
+    import torch
+    from oracle import field as F, poly as PL
+    from zk_stark_tutor_b200.context import le16
+    rnd = random.Random(77)
+    for L, N_, n in ((284, 1024, 4096), (5, 8, 32), (8, 8, 16), (2, 4, 16), (100, 128, 512)):
+        omicron, omega = F.primitive_nth_root(N_), F.primitive_nth_root(n)
+        dom = [F.fpow(omicron, i) for i in range(L)]
+        cols = [[rnd.randrange(zk.P) for _ in range(L)] for _ in range(3)] + [[0] * L, [5] * L]
+        vals = np.stack([C.to_arr(c) for c in cols])
+        out = torch.empty((len(cols), n, 2), dtype=torch.int64, device="cuda")
+        coeffs = torch.empty((len(cols), L, 2), dtype=torch.int64, device="cuda")
+        ctx.check(ctx.lib.zkb_trace_lde_batch(ctx.h, le16(omicron), N_, L, le16(omega), n, le16(F.GENERATOR), vals.ctypes.data, L, len(cols),
+                                              out.data_ptr(), n, coeffs.data_ptr()))
+        for k, col in enumerate(cols):
+            want = PL.fast_interpolate_domain(omicron, N_, dom, col)
+            d = PL.degree(want)
+            got = host(coeffs[k])
+            assert PL.degree(got) == d and (d is None or got[:d + 1] == want[:d + 1]), (L, N_, k)
+            assert host(out[k]) == N.fast_coset_evaluate(omega, n, F.GENERATOR, got), (L, N_, k)
+        degs = (ctypes.c_int64 * len(cols))()
+        ctx.check(ctx.lib.zkb_coset_degree_batch(ctx.h, le16(omega), out.data_ptr(), n, n, len(cols), degs))
+        assert list(degs) == [(-1 if PL.degree(host(coeffs[k])) is None else PL.degree(host(coeffs[k]))) for k in range(len(cols))]
+
+
+def test_prove_batch_reproduces_committed_signatures(ctx):
+    """Stark.prove_batch: four different signatures (keys, documents, randomness) advancing in lockstep == the committed digests of
+    the oracle's one-at-a-time coefficient-form prover; a batch of one as well."""
+    import hashlib
+    from zk_stark_tutor_b200.stark import deterministic_rng as drng
+    pr, tcs, cases = _fixture()
+    stark = zk.Stark(pr["expansion_factor"], pr["num_collinearity_checks"], pr["security_level"], pr["num_registers"], pr["num_cycles"],
+                     pr["transition_constraints_degree"], ctx=ctx)
+    before = ctx.launches
+    sigs = stark.prove_batch([c["trace"] for c in cases], tcs, [c["boundary"] for c in cases], [zk.SignatureProofStream(c["doc"]) for c in cases],
+                             [drng(c["seed"]) for c in cases])
+    launches = ctx.launches - before
+    assert [len(x) for x in sigs] == [1156888] * len(cases)
+    assert [hashlib.sha256(x).hexdigest() for x in sigs] == [c["sha"] for c in cases]
+    c = cases[2]
+    one = stark.prove_batch([c["trace"]], tcs, [c["boundary"]], [zk.SignatureProofStream(c["doc"])], [drng(c["seed"])], check_degrees=False)
+    assert hashlib.sha256(one[0]).hexdigest() == c["sha"]
+    assert ctx.launches - before - launches <= launches              # the launch count does not grow with the batch
+    # a trace that violates the AIR is caught by the degree check (stark.rs:451-464)
+    bad = [list(r) for r in c["trace"]]
+    bad[7][0] = (bad[7][0] + 1) % zk.P
+    with pytest.raises(ValueError):
+        stark.prove_batch([c["trace"], bad], tcs, [c["boundary"]] * 2, [zk.SignatureProofStream(c["doc"]) for _ in range(2)], [drng(b"a"), drng(b"b")])
+    stark.close()

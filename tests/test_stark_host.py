@@ -79,3 +79,20 @@ def test_degree_bookkeeping_equals_oracle():
     assert dev.transition_quotient_degree_bounds([t.dictionary for t in tcs]) == r.stark.transition_quotient_degree_bounds(tcs)
     assert dev.max_degree(tcs) == r.stark.max_degree(tcs) == 1023
     assert S._bit_count(0) == 1 and S._bit_count(1) == 1 and S._bit_count(852) == 10
+
+
+def test_sample_many_and_zerofier_of(monkeypatch):
+    import os
+    from zk_stark_tutor_b200.context import unpack
+    buf = bytes([0]) + P.to_bytes(16, "big") + bytes([9]) + (P + 5).to_bytes(16, "big") + bytes([0]) + ((1 << 128) - 1).to_bytes(16, "big") \
+        + bytes([1]) + (P - 1).to_bytes(16, "big") + os.urandom(17 * 500)
+    monkeypatch.setattr(os, "urandom", lambda k: buf[:k])
+    want = [S.Stark.sample(buf[17 * i:17 * i + 17]) for i in range(504)]
+    assert want[:4] == [0, 5, (1 << 128) - 1 - P, P - 1]
+    assert unpack(S.sample_many(os.urandom, 504)) == want                     # one bulk draw, vectorised reduction
+    calls = iter(buf[17 * i:17 * i + 17] for i in range(504))
+    assert unpack(S.sample_many(lambda k: next(calls), 504)) == want          # any other byte source: element by element
+    w = F.primitive_nth_root(1024)
+    pts = [F.fpow(w, i) for i in range(27)]
+    assert S.zerofier_of(pts) == PL.fast_zerofier(w, 1024, pts)
+    assert S.zerofier_of([]) == [1]

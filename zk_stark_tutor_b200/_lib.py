@@ -32,6 +32,15 @@ class AirDesc(ctypes.Structure):
                 ("weights", c_u8p), ("shifts", c_u64p)]
 
 
+class AirShape(ctypes.Structure):
+    _fields_ = [("offset", ctypes.c_uint8 * 16), ("omega", ctypes.c_uint8 * 16),
+                ("domain_length", u64), ("expansion_factor", u64),
+                ("num_registers", ctypes.c_uint32), ("num_constraints", ctypes.c_uint32),
+                ("term_counts", ctypes.POINTER(ctypes.c_uint32)), ("coefs", c_u8p), ("exps", ctypes.POINTER(ctypes.c_uint32)),
+                ("boundary_zerofiers", ctypes.POINTER(vp)), ("boundary_zerofier_lens", ctypes.POINTER(sz)),
+                ("transition_zerofier", vp), ("transition_zerofier_len", sz), ("shifts", c_u64p)]
+
+
 FS_CALLBACK = ctypes.CFUNCTYPE(ctypes.c_int, vp, ctypes.c_uint32, c_u8p, ctypes.c_int, c_u8p)
 
 # name -> (restype, argtypes); mirrors include/zkb200.h one to one
@@ -102,6 +111,13 @@ PROTOTYPES = {
     "zkb_ps_fiat_shamir": (ctypes.c_int, [vp, sz, c_u8p]),
     "zkb_fri_prove": (ctypes.c_int, [vp, ctypes.POINTER(FriParams), vp, sz, vp, c_u64p]),
     "zkb_air_combination": (ctypes.c_int, [vp, ctypes.POINTER(AirDesc), vp, sz, vp, vp, vp]),
+    "zkb_air_create": (ctypes.c_int, [vp, ctypes.POINTER(AirShape), ctypes.POINTER(vp)]),
+    "zkb_air_free": (None, [vp]),
+    "zkb_air_set_interpolants": (ctypes.c_int, [vp, sz, vp, sz]),
+    "zkb_air_boundary_quotients": (ctypes.c_int, [vp, sz, vp, sz, sz, vp, sz, sz]),
+    "zkb_air_combine": (ctypes.c_int, [vp, sz, c_u8p, vp, sz, sz, vp, sz, vp, sz, vp, sz]),
+    "zkb_trace_lde_batch": (ctypes.c_int, [vp, c_u8p, u64, u64, c_u8p, u64, c_u8p, vp, sz, sz, vp, sz, vp]),
+    "zkb_coset_degree_batch": (ctypes.c_int, [vp, c_u8p, vp, sz, sz, sz, ctypes.POINTER(ctypes.c_int64)]),
 }
 
 

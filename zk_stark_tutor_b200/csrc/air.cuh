@@ -30,19 +30,23 @@ struct AirGroup {
     uint8_t e[AIR_MAX_STATE];
 };
 
+// Batched: instance b = blockIdx.y.  What depends on the AIR's shape only (zerofier codewords, grouped terms, shifts) is
+// shared; the committed codewords, the boundary interpolants (they carry the instance's public values) and the weights
+// (from the instance's transcript) have an instance stride.
 struct AirView {
     uint64_t n, rot;                   // domain length; index distance of the next trace row (= expansion factor)
     uint32_t nr, nc;                   // registers, constraints
-    const fe* bq; uint64_t bq_stride;  // boundary-quotient codewords, register s at bq + s*bq_stride
-    const fe* rnd;                     // randomizer codeword
-    const fe* zb; const fe* ib;        // boundary zerofier / interpolant codewords, register s at + s*n
-    const fe* tz;                      // transition zerofier codeword
+    const fe* bq; uint64_t bq_stride, bq_inst;   // boundary-quotient codewords: register s of instance b at bq + s*bq_stride + b*bq_inst
+    const fe* rnd; uint64_t rnd_inst;  // randomizer codewords
+    const fe* zb;                      // boundary zerofier codewords, register s at + s*n (shared)
+    const fe* ib; uint64_t ib_inst;    // boundary interpolant codewords, register s of instance b at + s*n + b*ib_inst
+    const fe* tz_inv_m;                // 1 / Z_T(x_i), Montgomery form (shared)
     const AirGroup* groups;            // all constraints' groups
     const uint32_t* group_begin;       // nc + 1 offsets into groups
     const fe* coefs;
-    const fe* weights;                 // 1 + 2*nc + 2*nr canonical values, stark.rs:447-450 order
+    const fe* weights; uint32_t nw;    // per instance 1 + 2*nc + 2*nr canonical values, stark.rs:447-450 order
     const uint32_t* shifts;            // nc + nr exponents of x (stark.rs:476, 489)
-    fe* tq_out;                        // nullptr, or nc codewords of n values: the transition quotients
+    fe* tq_out; uint64_t tq_inst;      // nullptr, or per instance nc codewords of n values: the transition quotients
 };
 
 #if defined(__CUDA_ARCH__)
@@ -62,22 +66,23 @@ ZKB_HD fe fe_mont_inv(const fe& a_m) {
     return acc;
 }
 
-// comb[i].  x_m = x_i * R.  *div_zero is set if Z_T(x_i) == 0 (the reference's division panics, field_element.rs:85).
-ZKB_HD fe air_point(const AirView& a, uint64_t i, const fe& x_m, bool* div_zero) {
+// t_s(x_i) = bq_s(x_i) * Z_B,s(x_i) + I_s(x_i)  (stark.rs:722-731) for instance b
+ZKB_HD fe air_trace_value(const AirView& a, uint32_t b, uint32_t s, uint64_t i) {
+    const fe q = ZKB_AIR_LD(a.bq + s * a.bq_stride + b * a.bq_inst + i);
+    return fe_add(fe_montmul(fe_to_mont(q), ZKB_AIR_LD(a.zb + s * a.n + i)), ZKB_AIR_LD(a.ib + s * a.n + b * a.ib_inst + i));
+}
+
+// comb[i] of instance b.  x_m = x_i * R.
+ZKB_HD fe air_point(const AirView& a, uint32_t b, uint64_t i, const fe& x_m) {
     const uint64_t i2 = (i + a.rot) % a.n;
     fe v[AIR_MAX_STATE];                                     // state variables, Montgomery form
     for (uint32_t s = 0; s < a.nr; s++) {
-        const fe* bq = a.bq + s * a.bq_stride;
-        // t_s(x) = bq_s(x) * Z_B,s(x) + I_s(x)  (stark.rs:722-731)
-        fe cur = fe_add(fe_montmul(fe_to_mont(ZKB_AIR_LD(bq + i)), ZKB_AIR_LD(a.zb + s * a.n + i)), ZKB_AIR_LD(a.ib + s * a.n + i));
-        fe nxt = fe_add(fe_montmul(fe_to_mont(ZKB_AIR_LD(bq + i2)), ZKB_AIR_LD(a.zb + s * a.n + i2)), ZKB_AIR_LD(a.ib + s * a.n + i2));
-        v[s] = fe_to_mont(cur);
-        v[a.nr + s] = fe_to_mont(nxt);
+        v[s] = fe_to_mont(air_trace_value(a, b, s, i));
+        v[a.nr + s] = fe_to_mont(air_trace_value(a, b, s, i2));
     }
-    const fe tz = ZKB_AIR_LD(a.tz + i);
-    if (fe_is_zero(tz)) *div_zero = true;
-    const fe tz_inv_m = fe_mont_inv(fe_to_mont(tz));
-    fe comb = fe_montmul(fe_to_mont(ZKB_AIR_LD(a.rnd + i)), ZKB_AIR_LD(a.weights));          // w0 * randomizer
+    const fe tz_inv_m = ZKB_AIR_LD(a.tz_inv_m + i);
+    const fe* w = a.weights + (uint64_t)b * a.nw;
+    fe comb = fe_montmul(fe_to_mont(ZKB_AIR_LD(a.rnd + b * a.rnd_inst + i)), ZKB_AIR_LD(w));      // w0 * randomizer
     for (uint32_t j = 0; j < a.nc; j++) {
         fe acc = fe_zero();                                                                    // tc_j(point) * R
         for (uint32_t g = a.group_begin[j]; g < a.group_begin[j + 1]; g++) {
@@ -95,18 +100,24 @@ ZKB_HD fe air_point(const AirView& a, uint64_t i, const fe& x_m, bool* div_zero)
             acc = fe_add(acc, h);
         }
         const fe q_m = fe_montmul(acc, tz_inv_m);                                              // transition quotient (stark.rs:744-746)
-        if (a.tq_out) a.tq_out[(uint64_t)j * a.n + i] = fe_from_mont(q_m);
+        if (a.tq_out) a.tq_out[b * a.tq_inst + (uint64_t)j * a.n + i] = fe_from_mont(q_m);
         const fe xs_m = fe_mont_pow(x_m, a.shifts[j]);
-        const fe cw = fe_add(ZKB_AIR_LD(a.weights + 1 + 2 * j), fe_montmul(xs_m, ZKB_AIR_LD(a.weights + 2 + 2 * j)));
+        const fe cw = fe_add(ZKB_AIR_LD(w + 1 + 2 * j), fe_montmul(xs_m, ZKB_AIR_LD(w + 2 + 2 * j)));
         comb = fe_add(comb, fe_montmul(q_m, cw));
     }
     for (uint32_t s = 0; s < a.nr; s++) {
         const fe xs_m = fe_mont_pow(x_m, a.shifts[a.nc + s]);
-        const uint32_t w = 1 + 2 * a.nc + 2 * s;
-        const fe cw = fe_add(ZKB_AIR_LD(a.weights + w), fe_montmul(xs_m, ZKB_AIR_LD(a.weights + w + 1)));
-        comb = fe_add(comb, fe_montmul(fe_to_mont(ZKB_AIR_LD(a.bq + s * a.bq_stride + i)), cw));
+        const uint32_t k = 1 + 2 * a.nc + 2 * s;
+        const fe cw = fe_add(ZKB_AIR_LD(w + k), fe_montmul(xs_m, ZKB_AIR_LD(w + k + 1)));
+        comb = fe_add(comb, fe_montmul(fe_to_mont(ZKB_AIR_LD(a.bq + s * a.bq_stride + b * a.bq_inst + i)), cw));
     }
     return comb;
+}
+
+// boundary quotient in evaluation form (stark.rs:331-360 on the coset): bq_s(x_i) = (t_s(x_i) - I_s(x_i)) / Z_B,s(x_i);
+// zb_inv_m = 1 / Z_B,s(x_i) in Montgomery form
+ZKB_HD fe air_boundary_quotient(const fe& t, const fe& interpolant, const fe& zb_inv_m) {
+    return fe_montmul(fe_sub(t, interpolant), zb_inv_m);
 }
 
 // ---- host: MPolynomial dictionaries (flattened) -> groups ----------------------------------------

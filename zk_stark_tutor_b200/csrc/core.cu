@@ -223,6 +223,7 @@ void zkb_ctx_destroy(zkb_ctx* c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     for (auto& t : c->pow_tables) cudaFree(t->lo);
+    for (auto& at : c->attachments) at.destroy(at.p);
     for (auto& r : c->prof_recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
     for (auto e : c->prof_pool) cudaEventDestroy(e);
     if (c->scratch) cudaFree(c->scratch);

@@ -62,6 +62,9 @@ struct zkb_ctx {
     std::vector<cudaEvent_t> prof_pool;
     double prof_ms[16] = {0};
     uint64_t prof_count[16] = {0};
+    // caches owned by other translation units (e.g. the prefix-interpolation tables of stark.cu): destroyed with the context
+    struct Attachment { void* p; void (*destroy)(void*); };
+    std::vector<Attachment> attachments;
 };
 
 namespace zkb {

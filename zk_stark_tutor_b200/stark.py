@@ -101,6 +101,33 @@ class PrefixInterpolator:
         return [(x - y) % P for x, y in zip(a, b)]
 
 
+def zerofier_of(points):
+    """prod (X - x) over a handful of points (boundary / transition zerofiers, stark.rs:186-213): exact host arithmetic, the
+    polynomial fast_zerofier returns"""
+    z = [1]
+    for x in points:
+        z = [(a - x * b) % P for a, b in zip([0] + z, z + [0])]
+    return z
+
+
+def sample_many(rng, count):
+    """count x Field::sample(rng(17)) (stark.rs:293-295, 428-430) as a (count, 2) uint64 array.  os.urandom is drawn in one call -
+    any split of OS entropy is as random as another; every other byte source is called once per element, so reproducible streams
+    give the same elements as the one-by-one loop of `prove`."""
+    import os
+    if rng is os.urandom:
+        raw = np.frombuffer(rng(17 * count), dtype=np.uint8).reshape(count, 17)[:, 1:]     # sample keeps the last 16 bytes, big-endian
+        hi = raw[:, :8].copy().view(">u8").reshape(count).astype(np.uint64)
+        lo = raw[:, 8:].copy().view(">u8").reshape(count).astype(np.uint64)
+        p_hi, p_lo = np.uint64(P >> 64), np.uint64(P & ((1 << 64) - 1))
+        ge = (hi > p_hi) | ((hi == p_hi) & (lo >= p_lo))                                   # value >= p: subtract p once (p > 2^127)
+        borrow = (lo < p_lo) & ge
+        lo = np.where(ge, lo - p_lo, lo)
+        hi = np.where(ge, hi - p_hi - borrow.astype(np.uint64), hi)
+        return np.stack([lo, hi], axis=1)
+    return pack([Stark.sample(rng(17)) for _ in range(count)])
+
+
 def lagrange_interpolate(domain, values):
     """Polynomial::interpolate_domain (polynomial.rs:123-148) for a handful of points (the boundary conditions):
     exact host arithmetic; the interpolant is unique, so it is the polynomial fast_interpolate_domain returns."""
@@ -291,6 +318,131 @@ class Stark:
         finally:
             for t in trees:
                 t.close()
+
+    # ---- batches of instances of one AIR in lockstep (csrc/stark.cu, csrc/air.cu, csrc/batch.cu) --------------------------
+    def prove_batch(self, traces, transition_constraints, boundaries, proof_streams, rngs, check_degrees=True):
+        """Stark::prove for B instances of the same AIR (same constraint list, same boundary POSITIONS; values, traces, documents and
+        randomness differ), every launch carrying all of them: trace interpolation + LDE (zkb_trace_lde_batch), boundary quotients in
+        evaluation form (zkb_air_boundary_quotients), commits (zkb_merkle_build_batch), the evaluation-form middle (zkb_air_combine),
+        FRI (zkb_fri_prove_batch) and the openings (zkb_merkle_open_ps_batch).  Per instance the proof bytes are those of `prove`.
+        rngs: one byte source per instance (os.urandom draws in bulk).  Returns the list of proofs."""
+        import ctypes
+        import torch
+        from . import _lib
+        from .context import le16
+        ctx, lib, n, nr, B = self.ctx, self.ctx.lib, self.fri_domain_length, self.num_registers, len(traces)
+        assert B == len(boundaries) == len(proof_streams) == len(rngs) and B >= 1
+        dev = torch.device("cuda", ctx.device)
+        L = len(traces[0]) + self.num_randomizers
+        positions = tuple((c, r) for c, r, _ in boundaries[0])
+        assert all(tuple((c, r) for c, r, _ in b) == positions for b in boundaries), "a batch shares the boundary positions"
+        tcd, tq_bounds, _ = self._air_shape(transition_constraints)
+        nc = len(transition_constraints)
+        air, bq_bounds = self._air_handle(transition_constraints, positions, L)
+        # randomized traces, register-major so that column s*B + b of the batched calls is plane s, instance b
+        values = np.zeros((nr, B, L, 2), dtype=np.uint64)
+        rnd_polys = np.zeros((B, tcd + 1, 2), dtype=np.uint64)
+        t0 = len(traces[0])
+        for b in range(B):
+            assert len(traces[b]) == t0
+            values[:, b, :t0] = pack([row[s] for s in range(nr) for row in traces[b]]).reshape(nr, t0, 2)
+            draws = sample_many(rngs[b], self.num_randomizers * nr)                   # stark.rs:286-301: row by row, register by register
+            values[:, b, t0:] = draws.reshape(self.num_randomizers, nr, 2).transpose(1, 0, 2)
+        tcw = torch.empty((nr, B, n, 2), dtype=torch.int64, device=dev)              # trace codewords
+        cws = torch.empty((nr + 2, B, n, 2), dtype=torch.int64, device=dev)          # planes: boundary quotients | randomizer | combination
+        ctx.check(lib.zkb_trace_lde_batch(ctx.h, le16(self.omicron), self.omicron_domain_length, L, le16(self.omega), n, le16(self.generator),
+                                          values.ctypes.data, L, nr * B, tcw.data_ptr(), n, None))          # stark.rs:303-326 + LDE
+        ilen = max(len([1 for _, r in positions if r == s]) for s in range(nr)) or 1
+        interp = np.zeros((B, nr, ilen, 2), dtype=np.uint64)
+        for b in range(B):                                                            # stark.rs:215-243 (a handful of points each)
+            for s in range(nr):
+                poly = lagrange_interpolate([self._omicron_pow(c) for c, r, _ in boundaries[b] if r == s], [v for _, r, v in boundaries[b] if r == s])
+                if poly:
+                    interp[b, s, :len(poly)] = pack(poly)
+        ctx.check(lib.zkb_air_set_interpolants(air, B, interp.ctypes.data, ilen))
+        ctx.check(lib.zkb_air_boundary_quotients(air, B, tcw.data_ptr(), B * n, n, cws.data_ptr(), B * n, n))   # stark.rs:331-360
+        for b in range(B):
+            rnd_polys[b] = sample_many(rngs[b], tcd + 1)                              # stark.rs:424-432
+        ctx.check(lib.zkb_coset_lde_batch(ctx.h, le16(self.omega), n, le16(self.generator), rnd_polys.ctypes.data, tcd + 1, tcd + 1,
+                                          cws[nr].data_ptr(), n, B))
+        K = nr + 1
+        trees = (ctypes.c_void_p * (K * B))()
+        handles = [p.h.value for p in proof_streams]
+        ps_arr = (ctypes.c_void_p * B)(*handles)
+        ps_of_tree = (ctypes.c_void_p * (K * B))(*(handles * K))                      # tree t*B + b belongs to proof b
+        ctx.check(lib.zkb_merkle_build_batch(ctx.h, cws.data_ptr(), n, n, K * B, trees, ps_of_tree))   # stark.rs:366-386, 441-445
+        try:
+            nw = 1 + 2 * nc + 2 * nr
+            weights = np.zeros((B, nw, 2), dtype=np.uint64)
+            for b, p in enumerate(proof_streams):                                     # stark.rs:447-450 (all weights of a proof are equal, A.6)
+                weights[b, :] = pack([self.sample(p.fiat_shamir_prover(PROOF_BYTES))])[0]
+            tq = torch.empty((B, nc, n, 2), dtype=torch.int64, device=dev) if check_degrees else None
+            ctx.check(lib.zkb_air_combine(air, B, weights.ctypes.data_as(_lib.c_u8p), cws.data_ptr(), B * n, n, cws[nr].data_ptr(), n,
+                                          cws[nr + 1].data_ptr(), n, tq.data_ptr() if check_degrees else None, nc * n))   # stark.rs:388-519
+            if check_degrees:                                                         # stark.rs:451-464
+                degs = (ctypes.c_int64 * (B * nc))()
+                ctx.check(lib.zkb_coset_degree_batch(ctx.h, le16(self.omega), tq.data_ptr(), n, n, B * nc, degs))
+                for b in range(B):
+                    got = list(degs[b * nc:(b + 1) * nc])
+                    if any(d < 0 for d in got):
+                        raise ValueError("Failed to get degree of transition quotient")
+                    if got != tq_bounds:
+                        raise ValueError("transition quotient degrees do not match with expectation")
+            top = np.empty((B, self.fri.num_colinearity_tests), dtype=np.uint64)
+            ctx.check(lib.zkb_fri_prove_batch(ctx.h, ctypes.byref(self.fri.params), cws[nr + 1].data_ptr(), n, n, B, ps_arr,
+                                              top.ctypes.data_as(ctypes.POINTER(ctypes.c_uint64))))               # stark.rs:522
+            nn, ef = np.uint64(n), np.uint64(self.expansion_factor)
+            dup = np.concatenate([top, (top + ef) % nn], axis=1)                      # stark.rs:524-543
+            quad = np.sort(np.concatenate([dup, (dup + nn // np.uint64(2)) % nn], axis=1), axis=1)
+            k = quad.shape[1]
+            idx = np.ascontiguousarray(np.broadcast_to(quad[None, :, :], (K, B, k)))
+            ctx.check(lib.zkb_merkle_open_ps_batch(trees, K * B, idx.ctypes.data_as(ctypes.POINTER(ctypes.c_uint64)), k, ps_of_tree))   # stark.rs:546-560
+            for p in proof_streams:
+                p.objects = None
+            return [p.digest() for p in proof_streams]
+        finally:
+            for i in range(K * B - 1, -1, -1):          # tree 0 owns the shared arena: free it last
+                if trees[i]:
+                    lib.zkb_merkle_free(trees[i])
+
+    def _air_handle(self, transition_constraints, positions, trace_length):
+        """zkb_air for (constraints, boundary positions): grouped terms + zerofier codewords, created once"""
+        import ctypes
+        from . import _lib
+        from .context import Vec, le16
+        key = ("air_handle", id(transition_constraints), positions, trace_length)
+        if key not in self._cache:
+            nr = self.num_registers
+            tcd, tq_bounds, (counts, coefs, exps) = self._air_shape(transition_constraints)
+            zerofiers = [zerofier_of([self._omicron_pow(c) for c, r in positions if r == s]) for s in range(nr)]
+            tz = zerofier_of([self._omicron_pow(i) for i in range(self.original_trace_length - 1)])
+            bq_bounds = [trace_length - 1 - _degree(z) for z in zerofiers]             # stark.rs:245-258
+            shifts = np.asarray([tcd - b for b in tq_bounds] + [tcd - b for b in bq_bounds], dtype=np.uint64)
+            d = _lib.AirShape()
+            d.offset[:] = list(int(self.generator).to_bytes(16, "little"))
+            d.omega[:] = list(int(self.omega).to_bytes(16, "little"))
+            d.domain_length, d.expansion_factor, d.num_registers, d.num_constraints = self.fri_domain_length, self.expansion_factor, nr, len(counts)
+            d.term_counts = counts.ctypes.data_as(ctypes.POINTER(ctypes.c_uint32))
+            d.coefs = coefs.ctypes.data_as(_lib.c_u8p)
+            d.exps = exps.ctypes.data_as(ctypes.POINTER(ctypes.c_uint32))
+            zv = [Vec(z) for z in zerofiers]
+            zp = (ctypes.c_void_p * nr)(*[v.ptr for v in zv])
+            zl = (ctypes.c_size_t * nr)(*[v.n for v in zv])
+            d.boundary_zerofiers, d.boundary_zerofier_lens = zp, zl
+            tzv = Vec(tz)
+            d.transition_zerofier, d.transition_zerofier_len = tzv.ptr, tzv.n
+            d.shifts = shifts.ctypes.data_as(_lib.c_u64p)
+            h = ctypes.c_void_p()
+            self.ctx.check(self.ctx.lib.zkb_air_create(self.ctx.h, ctypes.byref(d), ctypes.byref(h)))
+            self._cache[key] = (h, bq_bounds, transition_constraints)
+        return self._cache[key][:2]
+
+    def close(self):
+        """release the device tables of the cached AIR handles"""
+        for key, val in list(self._cache.items()):
+            if key[0] == "air_handle":
+                self.ctx.lib.zkb_air_free(val[0])
+                del self._cache[key]
 
     def _air_shape(self, transition_constraints):
         """(max_degree, transition quotient degree bounds, flattened terms) of an AIR: computed once per constraint list
