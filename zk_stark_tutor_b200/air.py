@@ -7,7 +7,7 @@ import ctypes
 import numpy as np
 
 from . import _lib
-from .context import Vec, default_context, le16, pack
+from .context import Vec, default_context, pack
 
 
 def flatten_constraints(constraints, num_registers):
