@@ -72,6 +72,8 @@ static Polynomial rand_poly(const Field& f, size_t max_degree) {
     return Polynomial(rand_domain(f, degree));
 }
 
+static int objs_kind(const std::vector<StarkProofStreamEnum>& o, size_t i) { return (int)o.at(i).kind; }
+
 // ------------------------------------------------------------------------------------------- host
 static void host_tests() {
     run("field::field::tests::mul", [] {                                  // field.rs:176-183 (through FieldElement)
@@ -428,6 +430,45 @@ static void gpu_tests() {
     };
     run("fri::tests::verify (library proof stream: one zkb_fri_prove call)", [&] { fri_verify(true); });
     run("fri::tests::verify (foreign ProofStream: Fiat-Shamir callback per round)", [&] { fri_verify(false); });
+    run("fri: verify rejects tampered proofs with the reference's messages", [] {     // fri.rs:279-281, 374-383, 392-408
+        Field field(FIELD_PRIME);
+        const size_t n = 256, ef = 4, ncc = 17;
+        FieldElement omega = field.primitive_nth_root(n);
+        FRI fri(field.generator(), omega, n, ef, ncc);
+        std::vector<FieldElement> coeffs, domain;
+        for (size_t i = 0; i < n / ef; i++) coeffs.push_back(fe(field, 3 * i + 1));
+        std::vector<FieldElement> codeword = fast_coset_evaluate(omega, n, field.one(), Polynomial(coeffs));
+        IndependentProofStream honest;
+        fri.prove(codeword, honest);
+        const size_t R = fri.num_rounds();
+        auto verdict = [&](const std::function<void(std::vector<StarkProofStreamEnum>&)>& tamper) {
+            std::vector<StarkProofStreamEnum> objs = honest.objects;
+            tamper(objs);
+            IndependentProofStream ps(objs);
+            std::vector<std::pair<size_t, FieldElement>> points;
+            Result r = fri.verify(ps, points);
+            return r.err ? *r.err : std::string("ok");
+        };
+        ASSERT_EQ(verdict([](std::vector<StarkProofStreamEnum>&) {}), std::string("ok"));
+        ASSERT_EQ(objs_kind(honest.objects, R), (int)StarkProofStreamEnum::Codeword);
+        // the last codeword no longer matches the last root
+        ASSERT_EQ(verdict([&](std::vector<StarkProofStreamEnum>& o) { o[R].codeword[3] = o[R].codeword[3] + field.one(); }),
+                  std::string("last codeword is not well formed"));
+        // a first-layer leaf changed: the challenges stay the same (Leafs come after every challenge), the colinearity test fails
+        ASSERT_EQ(verdict([&](std::vector<StarkProofStreamEnum>& o) { o[R + 1].leafs[2] = o[R + 1].leafs[2] + field.one(); }),
+                  std::string("colinearity check failure"));
+        // a path node changed: Merkle verification of the first opened leaf fails
+        ASSERT_EQ(verdict([&](std::vector<StarkProofStreamEnum>& o) { o[R + 1 + ncc].path[0].buf[5] ^= 1; }),
+                  std::string("Merkle auth path verification failed for aa"));
+        ASSERT_EQ(verdict([&](std::vector<StarkProofStreamEnum>& o) { o[R + 1 + ncc + 2].path[1].buf[0] ^= 0x80; }),
+                  std::string("Merkle auth path verification failed for cc"));
+        // a root changed: every later challenge changes, so the proof cannot verify (which check trips first depends on the challenge)
+        ASSERT_NE(verdict([&](std::vector<StarkProofStreamEnum>& o) { o[0].root.buf[0] ^= 1; }), std::string("ok"));
+        // an object of the wrong kind where a root is expected panics (expect_root, proof_stream_enum.rs:129-133)
+        bool panicked = false;
+        try { verdict([&](std::vector<StarkProofStreamEnum>& o) { o[1] = StarkProofStreamEnum::Value_(field.one()); }); } catch (const Panic&) { panicked = true; }
+        ASSERT(panicked, "expect_root on a Value must panic");
+    });
     run("fri: prove panics on a codeword of the wrong length", [] {        // fri.rs:215-219
         Field field(FIELD_PRIME);
         FRI fri(field.generator(), field.primitive_nth_root(256), 256, 4, 17);

@@ -71,12 +71,12 @@ def test_cpp_mirror_links_and_host_groups_pass(tmp_path):
 
 def test_cpp_mirror_host_logic_on_oracle_backend(tmp_path):
     out = _run(_build(tmp_path, True), "all")
-    assert "33 passed; 0 failed" in out
+    assert "34 passed; 0 failed" in out
     _check_proof(out)
 
 
 @pytest.mark.gpu
 def test_cpp_mirror_reference_tests_on_gpu(tmp_path):
     out = _run(_build(tmp_path, False), "all")
-    assert "33 passed; 0 failed" in out
+    assert "34 passed; 0 failed" in out
     _check_proof(out)
