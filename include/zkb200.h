@@ -64,6 +64,10 @@ const char* zkb_version(void);
  * contexts busy on one GPU (column / proof pipelines) gets better overlap from staged copies on the copy
  * engines: enable = 0 restores the explicit H2D copy for this context. */
 int zkb_ctx_zero_copy_inputs(zkb_ctx* ctx, int enable);
+/* The batched entry points (zkb_fri_prove_batch, zkb_merkle_open_ps_batch) assemble the instances' proof streams on up to
+ * `threads` host threads per call (default 16).  A caller that keeps several batches in flight on its own threads should lower it
+ * (8 batches in flight on a 16-core host: 1-4 threads beat 16 by 16 %). */
+int zkb_ctx_assembly_threads(zkb_ctx* ctx, int threads);
 /* Per-kernel-class device timing (CUDA events on the context's stream around every launch;
  * this is what bench.py's roofline.achieved is computed from).  enable: 0 = off, 1 = on,
  * 2 = on + reset the accumulators.  zkb_kernel_name(id) is NULL past the last class. */

@@ -244,6 +244,12 @@ int zkb_ctx_sync(zkb_ctx* c) {
 
 uint64_t zkb_ctx_launches(const zkb_ctx* c) { return c ? c->launches : 0; }
 
+int zkb_ctx_assembly_threads(zkb_ctx* c, int threads) {
+    if (!c || threads < 1) return ZKB_ERR_ARG;
+    c->assembly_threads = (size_t)threads;
+    return 0;
+}
+
 int zkb_ctx_profile(zkb_ctx* c, int enable) {
     if (!c) return ZKB_ERR_ARG;
     ZKB_TRY(prof_collect(c));

@@ -51,6 +51,7 @@ struct zkb_ctx {
     uint64_t clock = 0;
     void* host_scratch[3] = {nullptr, nullptr, nullptr};   // grow-only pinned buffers for large D2H results (batch paths)
     size_t host_scratch_bytes[3] = {0, 0, 0};
+    size_t assembly_threads = 16;    // host threads per batched call for proof-stream assembly (zkb_ctx_assembly_threads)
     bool zero_copy_inputs = true;    // pinned host LDE inputs are read in place by the first NTT pass (zkb_ctx_zero_copy_inputs)
     uint32_t* tree_bars = nullptr;   // k_tree's arrival counter (device; zero between launches)
     uint32_t root_seq = 0;   // sequence number of the last root signalled through pinned memory
