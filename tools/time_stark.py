@@ -48,3 +48,11 @@ for rep in range(3):
     for k, v in sorted(stages.items(), key=lambda kv: -kv[1]):
         print("    %-26s %8.2f ms" % (k, v * 1e3))
     print("    %-26s %8.2f ms" % ("(other host work)", (total - sum(stages.values())) * 1e3))
+
+# the same signature through the batched entry points with a batch of one (every stage a single device call)
+import time as _t                                                   # noqa: E402
+for rep in range(3):
+    ctx.sync()
+    t0 = _t.perf_counter()
+    out = st.prove_batch([trace], tcs, [boundary], [zk.SignatureProofStream(b"doc")], [deterministic_rng(b"r")])
+    print("prove_batch, batch of 1: %.2f ms, %d bytes, same bytes as prove: %s" % ((_t.perf_counter() - t0) * 1e3, len(out[0]), out[0] == sig))
