@@ -584,7 +584,8 @@ def signatures_arm(args, ctx, stream, rank, world, local, barrier):
     pr = fx["params"]
     from concurrent.futures import ThreadPoolExecutor
     # defaults (flags left at their shared defaults 64 / 4): batches of 32 signatures in lockstep, 8 batches in flight - measured on one B200
-    # (2048 signatures): 32x8 7,333/s, 32x4 6,997/s, 64x4 5,827/s, 16x8 5,686/s, 32x16 5,716/s, 64x1 2,877/s.
+    # (2048 signatures, 16 assembly threads per call): 32x8 7,333/s, 32x4 6,997/s, 64x4 5,827/s, 16x8 5,686/s, 32x16 5,716/s, 64x1 2,877/s;
+    # with 2 assembly threads per call (set below when lanes > 1): 32x8 8,824/s, 64x8 7,874/s, 32x12 7,627/s.
     # One-at-a-time mode (--proof-batch 0): 1 lane 207/s, 4 lanes 148/s, 8 lanes 126/s - there the per-signature host glue is Python (GIL);
     # lockstep batches spend their host time inside the library (GIL released), so several batches in flight do overlap.
     pb = max(0, args.proof_batch if args.proof_batch != 64 else 32)

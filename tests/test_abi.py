@@ -146,3 +146,41 @@ def test_proof_stream_bytes(L):
         L.zkb_ps_fiat_shamir(ps, 32, ch)
         assert bytes(ch) == ref.fiat_shamir_prover(32)
         L.zkb_ps_free(ps)
+
+
+def test_proof_stream_raw_objects(L):
+    """zkb_ps_push_object: objects the caller serialised itself (any path node size, stark.rs:785-808's test shape) give the oracle's
+    wire bytes and header rule (order only once a field-carrying object is present, proof_stream_enum.rs:161-190)."""
+    ps = ctypes.c_void_p()
+    assert L.zkb_ps_create(None, 0, 0, ctypes.byref(ps)) == 0
+    ref = ops.IndependentProofStream()
+
+    def both(code, payload, obj):
+        assert L.zkb_ps_push_object(ps, code, _buf(payload) if payload else None, len(payload)) == 0
+        ref.push(obj)
+        n = L.zkb_ps_digest(ps, None, 0)
+        buf = (ctypes.c_uint8 * n)()
+        L.zkb_ps_digest(ps, buf, n)
+        assert bytes(buf) == ref.digest()
+    both(0, bytes([0x49, 0x6e, 0x20, 0x74]), (ops.ROOT, bytes([0x49, 0x6e, 0x20, 0x74])))
+    nodes = [bytes([0x49, 0x6e, 0x20, 0x74]), bytes([0x01, 0x6b, 0xfe, 0x25, 0x99])]
+    both(2, b"".join(len(x).to_bytes(8, "big") + x for x in nodes), (ops.PATH, nodes))
+    both(1, b"", (ops.CODEWORD, []))                                   # an empty codeword carries no field: header still zero
+    both(4, (2).to_bytes(16, "big"), (ops.VALUE, 2))                   # now the header is the field order
+    both(3, b"".join(v.to_bytes(16, "big") for v in (1, 5, 10)), (ops.LEAFS, (1, 5, 10)))
+    both(1, b"".join(v.to_bytes(16, "big") for v in (20, 100)), (ops.CODEWORD, [20, 100]))
+    assert L.zkb_ps_push_object(ps, 5, _buf(b"x"), 1) == -2             # "Unknown code" (proof_stream_enum.rs:62)
+    L.zkb_ps_free(ps)
+
+
+def test_context_calls_fail_without_a_context(L):
+    """no CUDA device in the CPU container: zkb_ctx_create fails (there is no CPU fallback) and context-taking calls reject NULL"""
+    h = ctypes.c_void_p()
+    import torch
+    if not torch.cuda.is_available():
+        assert L.zkb_ctx_create(0, None, ctypes.byref(h)) != 0 and not h.value
+    assert L.zkb_ctx_assembly_threads(None, 4) == -2
+    assert L.zkb_air_create(None, None, ctypes.byref(h)) == -2
+    assert L.zkb_trace_lde_batch(None, None, 0, 0, None, 0, None, None, 0, 0, None, 0, None) == -2
+    assert L.zkb_coset_degree_batch(None, None, None, 0, 0, 0, None) == -2
+    assert L.zkb_air_combination(None, None, None, 0, None, None, None) == -2
