@@ -610,7 +610,7 @@ def signatures_arm(args, ctx, stream, rank, world, local, barrier):
         # below uses the reproducible byte stream the committed digests were made with
         c = cases[i % len(cases)]
         return starks[lane].prove(c["trace"], tcs, c["boundary"], zk.SignatureProofStream(c["doc"]),
-                                  deterministic_rng(seed) if seed is not None else os.urandom)
+                                  deterministic_rng(seed) if seed is not None else os.urandom, lockstep=False)
 
     from zk_stark_tutor_b200.context import pack as zk_pack
     for c in cases:

@@ -76,6 +76,9 @@ def test_rpsss_signature_through_device_stark(ctx):
     got = stark.prove(cpu.rp.trace(sk), tcs, cpu.rp.boundary_constraints(pk), zk.SignatureProofStream(doc), deterministic_rng(b"r2"))
     assert len(got) == 1156888
     assert got == want
+    # the reference's call structure (one call per polynomial) gives the same bytes as the lockstep pipeline
+    assert stark.prove(cpu.rp.trace(sk), tcs, cpu.rp.boundary_constraints(pk), zk.SignatureProofStream(doc), deterministic_rng(b"r2"),
+                       lockstep=False) == want
     assert cpu.verify(pk, doc, got) is None
     assert cpu.verify(pk, b"another document", got) is not None
     # a trace that violates the AIR is caught by the degree check (stark.rs:451-464)
@@ -98,6 +101,7 @@ def test_stark_prove_independent_stream_through_device_stark(ctx):
     dev = zk.Stark(4, 64, 128, rp.m, rp.N + 1, 3, ctx=ctx)
     got = dev.prove(rp.trace(x), tcs, rp.boundary_constraints(out), zk.IndependentProofStream(), deterministic_rng(b"q"), check_degrees=False)
     assert got == want
+    assert dev.prove(rp.trace(x), tcs, rp.boundary_constraints(out), zk.IndependentProofStream(), deterministic_rng(b"q"), lockstep=False) == want
     assert ref.verify(tcs, rp.boundary_constraints(out), PS.IndependentProofStream(PS.parse(got))) is None
 
 
@@ -113,9 +117,9 @@ def test_committed_rpsss_fixture_signatures(ctx):
     stark = zk.Stark(pr["expansion_factor"], pr["num_collinearity_checks"], pr["security_level"], pr["num_registers"], pr["num_cycles"],
                      pr["transition_constraints_degree"], ctx=ctx)
     tcs = [{tuple(k): int(v) for k, v in tc} for tc in fx["transition_constraints"]]
-    for c in fx["cases"]:
+    for k, c in enumerate(fx["cases"]):
         sig = stark.prove([[int(v) for v in row] for row in c["trace"]], tcs, [(cy, reg, int(v)) for cy, reg, v in c["boundary"]],
-                          zk.SignatureProofStream(c["document"].encode()), drng(c["rng_seed"].encode()))
+                          zk.SignatureProofStream(c["document"].encode()), drng(c["rng_seed"].encode()), lockstep=bool(k % 2))
         assert len(sig) == c["signature_bytes"] == 1156888
         assert hashlib.sha256(sig).hexdigest() == c["signature_sha256"]
 

@@ -260,9 +260,13 @@ class Stark:
     def sample_weights(self, number, randomness):                         # stark.rs:260-274 (all weights equal: SURVEY.md A.6)
         return [self.sample(bytes(i) + randomness) for i in range(number)]
 
-    def prove(self, trace, transition_constraints, boundary, proof_stream, rng, check_degrees=True):
+    def prove(self, trace, transition_constraints, boundary, proof_stream, rng, check_degrees=True, lockstep=True):
         """Returns the proof bytes (proof_stream.digest()).  proof_stream: the library's IndependentProofStream /
-        SignatureProofStream."""
+        SignatureProofStream.  lockstep=True (default) runs the batched pipeline with a batch of one - every stage a single
+        device call (0.9 ms + the byte source per RPSSS signature); lockstep=False keeps the reference's call structure
+        (fast_coset_divide per register, one LDE / commit per codeword: 4.8 ms).  Same draws from `rng`, same bytes."""
+        if lockstep:
+            return self.prove_batch([trace], transition_constraints, [boundary], [proof_stream], [rng], check_degrees=check_degrees)[0]
         import torch
         ctx, n, nr = self.ctx, self.fri_domain_length, self.num_registers
         dev = torch.device("cuda", ctx.device)
