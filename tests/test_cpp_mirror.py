@@ -80,3 +80,26 @@ def test_cpp_mirror_reference_tests_on_gpu(tmp_path):
     out = _run(_build(tmp_path, False), "all")
     assert "34 passed; 0 failed" in out
     _check_proof(out)
+
+
+def _build_example(tmp_path, with_oracle_backend):
+    exe = str(tmp_path / "lde_fri")
+    cmd = ["g++", "-O2", "-std=c++17", "-Wall", "-Wextra", "-Werror", "-I" + os.path.join(ROOT, "include"), os.path.join(ROOT, "examples", "lde_fri.cpp")]
+    if with_oracle_backend:
+        cbind.build()
+        cmd += [os.path.join(SRC, "oracle_backend.cpp"), "-L" + ORADIR, "-lzkoracle", "-Wl,-rpath," + ORADIR]
+    cmd += ["-o", exe, "-L" + LIBDIR, "-lzkb200", "-Wl,-rpath," + LIBDIR]
+    subprocess.check_call(cmd)
+    return exe
+
+
+def test_cpp_example_on_oracle_backend(tmp_path):
+    """examples/lde_fri.cpp (LDE -> commit -> open -> FRI prove -> verify through the C++ mirror) builds and accepts its own proof"""
+    out = subprocess.run([_build_example(tmp_path, True), "10"], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and "verify: ok" in out.stdout, out.stdout + out.stderr
+
+
+@pytest.mark.gpu
+def test_cpp_example_on_gpu(tmp_path):
+    out = subprocess.run([_build_example(tmp_path, False), "16"], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and "verify: ok" in out.stdout, out.stdout + out.stderr
