@@ -96,3 +96,32 @@ def test_sample_many_and_zerofier_of(monkeypatch):
     pts = [F.fpow(w, i) for i in range(27)]
     assert S.zerofier_of(pts) == PL.fast_zerofier(w, 1024, pts)
     assert S.zerofier_of([]) == [1]
+
+
+def test_flatten_constraints_matches_mpolynomial_evaluate():
+    """air.flatten_constraints: the flat (counts, coefs, exps) arrays handed to zkb_air_create evaluate to MPolynomial::evaluate
+    (m_polynomial.rs:97-126) at random points - short keys are zero padded, zero-coefficient entries are kept."""
+    from zk_stark_tutor_b200.air import flatten_constraints
+    from zk_stark_tutor_b200.context import unpack
+    from oracle.mpoly import MPolynomial
+    rnd = random.Random(21)
+    nr = 2
+    tcs = [MPolynomial({(0,): 7, (3, 1): 5, (0, 0, 2, 0, 1): P - 1, (27, 0, 0, 3): 0}), MPolynomial({(1, 1, 1, 1, 1): 9}), MPolynomial({})]
+    counts, coefs, exps = flatten_constraints(tcs, nr)
+    assert list(counts) == [4, 1, 0] and exps.shape == (5, 5) and coefs.shape == (5, 2)
+    cf = unpack(coefs)
+    for _ in range(5):
+        pt = [rnd.randrange(P) for _ in range(1 + 2 * nr)]
+        t = 0
+        for j, tc in enumerate(tcs):
+            acc = 0
+            for k in range(int(counts[j])):
+                term = cf[t]
+                for v, e in zip(pt, exps[t]):
+                    term = term * pow(v, int(e), P) % P
+                acc = (acc + term) % P
+                t += 1
+            assert acc == tc.evaluate(pt)
+    with pytest.raises(ValueError):
+        flatten_constraints([{(0, 0, 0, 0, 0, 1): 3}], nr)          # a sixth variable with 2 registers
+    assert flatten_constraints([{(0, 0, 0, 0, 0, 0): 3}], nr)[2].shape == (1, 5)   # trailing zero exponents beyond the variables are fine
