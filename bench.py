@@ -63,6 +63,7 @@ def parse():
     ap.add_argument("--proofs", type=int, default=1024)
     ap.add_argument("--proof-batch", type=int, default=64, help="proofs workload: proofs that advance in lockstep per launch (0: one proof per call sequence)")
     ap.add_argument("--columns", type=int, default=64)
+    ap.add_argument("--asm-threads", type=int, default=0, help="proofs / signatures: host threads per batched call for proof-stream assembly (0: workload default)")
     ap.add_argument("--lanes", type=int, default=4, help="columns in flight per GPU in the columns workload (streams + host threads)")
     return ap.parse_args()
 
@@ -471,7 +472,7 @@ def proofs_arm(args, ctx, stream, rank, world, local, barrier):
     mine = pm.partition(args.proofs, world, rank)
     pb = max(0, args.proof_batch)
     lanes = max(1, args.lanes if args.lanes != 4 else (4 if pb else 8))
-    pipe = pm.ProofPipeline(local, shape, GENERATOR, omega, lanes=lanes)
+    pipe = pm.ProofPipeline(local, shape, GENERATOR, omega, lanes=lanes, assembly_threads=args.asm_threads or None)
     lens = shape.column_lengths()
 
     def pinned(seed, n):
@@ -594,7 +595,7 @@ def signatures_arm(args, ctx, stream, rank, world, local, barrier):
     ctxs = [ctx] + [zk.Context(local, stream="own") for _ in range(lanes - 1)]
     if lanes > 1:
         for cx in ctxs:      # the lanes already are the host parallelism: few assembly threads per batched call (16: 8,339/s, 4: 9,666/s, 1: 9,724/s)
-            cx.check(cx.lib.zkb_ctx_assembly_threads(cx.h, 2))
+            cx.check(cx.lib.zkb_ctx_assembly_threads(cx.h, args.asm_threads or 2))
     starks = [zk.Stark(pr["expansion_factor"], pr["num_collinearity_checks"], pr["security_level"], pr["num_registers"], pr["num_cycles"],
                        pr["transition_constraints_degree"], ctx=cx) for cx in ctxs]
     stark = starks[0]

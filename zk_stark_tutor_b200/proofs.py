@@ -150,10 +150,15 @@ class ProofPipeline:
     """`lanes` proofs in flight on ONE GPU: one context (own CUDA stream) and one host thread per
     lane; the C calls release the GIL."""
 
-    def __init__(self, device, shape, offset, omega, lanes=8):
+    def __init__(self, device, shape, offset, omega, lanes=8, assembly_threads=None):
+        """assembly_threads: host threads per batched call for proof-stream assembly (zkb_ctx_assembly_threads; None = the library's 16).
+        With several lanes the lanes themselves are the host parallelism, so a few threads per call do better on a 16-core host."""
         import zk_stark_tutor_b200 as zk
         self.zk, self.shape = zk, shape
         self.ctxs = [zk.Context(device, stream="own") for _ in range(lanes)]
+        if assembly_threads:
+            for c in self.ctxs:
+                c.check(c.lib.zkb_ctx_assembly_threads(c.h, int(assembly_threads)))
         self.fris = [zk.FRI(offset, omega, shape.fri_len, shape.ef, shape.ncc, c) for c in self.ctxs]
 
     def run(self, proofs, make_stream, keep_digest=False):
