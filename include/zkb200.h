@@ -145,6 +145,10 @@ int zkb_merkle_verify(const uint8_t root[64], uint64_t index, const uint8_t* pat
 void zkb_blake2b512(const uint8_t* msg, size_t len, uint8_t out[64]);
 /* SHAKE256 XOF on the host (crypto/shake256.rs:7-19) */
 void zkb_shake256(const uint8_t* msg, size_t len, uint8_t* out, size_t out_len);
+/* The same function computed by the DEVICE sponge (one warp, csrc/keccak.cuh) that draws the Fiat-Shamir challenges
+ * inside the FRI kernels; out_len <= 136.  Exists so that the KATs of crypto/shake256.rs / proof_stream.rs:129-145 can be
+ * run against the device code. */
+int zkb_shake256_device(zkb_ctx* ctx, const uint8_t* msg, size_t len, uint8_t* out, size_t out_len);
 
 /* ---- FRI : src/fri.rs ------------------------------------------------------------------ */
 typedef struct zkb_fri_params {

@@ -148,6 +148,43 @@ def test_proof_stream_bytes(L):
         L.zkb_ps_free(ps)
 
 
+def test_proof_stream_incremental_sponge(L):
+    """zkb_ps_fiat_shamir keeps a running SHAKE256 sponge over the transcript (absorbs only the bytes pushed since the last
+    challenge; restarts once when the header flips to the field order): a challenge after EVERY push of a long random object
+    sequence equals SHAKE256 of the whole stream, as proof_stream.rs:36-40 computes it."""
+    import random
+    r = random.Random(5)
+    for doc in (None, b"doc"):
+        ps = ctypes.c_void_p()
+        assert L.zkb_ps_create(_buf(doc) if doc else None, len(doc) if doc else 0, 1 if doc else 0, ctypes.byref(ps)) == 0
+        ref = ops.SignatureProofStream(doc) if doc else ops.IndependentProofStream()
+        ch = (ctypes.c_uint8 * 32)()
+        for step in range(120):
+            kind = r.choice([0, 0, 0, 2, 2] if step < 40 else [0, 1, 2, 3, 4])        # Roots / Paths only first: zero header
+            if kind == 0:
+                root = bytes(r.randrange(256) for _ in range(64))
+                L.zkb_ps_push_root(ps, _buf(root), 64); ref.push((ops.ROOT, root))
+            elif kind == 1:
+                cw = [r.randrange(F.P) for _ in range(r.randrange(0, 40))]
+                L.zkb_ps_push_codeword(ps, _buf(b"".join(F.to_le16(v) for v in cw)) if cw else None, len(cw)); ref.push((ops.CODEWORD, cw))
+            elif kind == 2:
+                path = [bytes(r.randrange(256) for _ in range(64)) for _ in range(r.randrange(1, 13))]
+                L.zkb_ps_push_path(ps, _buf(b"".join(path)), len(path)); ref.push((ops.PATH, path))
+            elif kind == 3:
+                t = tuple(r.randrange(F.P) for _ in range(3))
+                L.zkb_ps_push_leafs(ps, _buf(F.to_le16(t[0])), _buf(F.to_le16(t[1])), _buf(F.to_le16(t[2]))); ref.push((ops.LEAFS, t))
+            else:
+                v = r.randrange(F.P)
+                L.zkb_ps_push_value(ps, _buf(F.to_le16(v))); ref.push((ops.VALUE, v))
+            if step % 3 != 2:                                   # some pushes without a challenge in between
+                L.zkb_ps_fiat_shamir(ps, 32, ch)
+                assert bytes(ch) == ref.fiat_shamir_prover(32), step
+        big = (ctypes.c_uint8 * 300)()
+        L.zkb_ps_fiat_shamir(ps, 300, big)
+        assert bytes(big) == ref.fiat_shamir_prover(300)
+        L.zkb_ps_free(ps)
+
+
 def test_proof_stream_raw_objects(L):
     """zkb_ps_push_object: objects the caller serialised itself (any path node size, stark.rs:785-808's test shape) give the oracle's
     wire bytes and header rule (order only once a field-carrying object is present, proof_stream_enum.rs:161-190)."""

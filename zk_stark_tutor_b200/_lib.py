@@ -86,6 +86,7 @@ PROTOTYPES = {
     "zkb_merkle_verify": (ctypes.c_int, [c_u8p, u64, c_u8p, sz, c_u8p]),
     "zkb_blake2b512": (None, [c_u8p, sz, c_u8p]),
     "zkb_shake256": (None, [c_u8p, sz, c_u8p, sz]),
+    "zkb_shake256_device": (ctypes.c_int, [vp, c_u8p, sz, c_u8p, sz]),
     "zkb_fri_num_rounds": (u64, [ctypes.POINTER(FriParams)]),
     "zkb_fri_fold": (ctypes.c_int, [vp, vp, sz, c_u8p, c_u8p, c_u8p, vp]),
     "zkb_fri_commit": (ctypes.c_int, [vp, ctypes.POINTER(FriParams), vp, sz, FS_CALLBACK, vp, ctypes.POINTER(vp)]),

@@ -214,6 +214,8 @@ int zkb_ctx_create(int device, void* stream, zkb_ctx** out) {
     }
     c->pinned_bytes = 1 << 20;
     if (cudaMallocHost(&c->pinned, c->pinned_bytes) != cudaSuccess) { delete c; return ZKB_ERR_CUDA; }
+    memset(c->pinned, 0, c->pinned_bytes);          // the root handshake reads a sequence flag from this buffer
+    if (ntt_device_init(c) != 0 || merkle_device_init(c) != 0 || fri_tail_device_init(c) != 0) { zkb_ctx_destroy(c); return ZKB_ERR_CUDA; }
     *out = c;
     return 0;
 }
@@ -228,6 +230,7 @@ void zkb_ctx_destroy(zkb_ctx* c) {
     for (auto e : c->prof_pool) cudaEventDestroy(e);
     if (c->scratch) cudaFree(c->scratch);
     if (c->tree_bars) cudaFree(c->tree_bars);
+    if (c->fs_dev) cudaFree(c->fs_dev);
     for (int i = 0; i < 3; i++) if (c->host_scratch[i]) cudaFreeHost(c->host_scratch[i]);
     if (c->pinned) cudaFreeHost(c->pinned);
     if (c->own_stream) cudaStreamDestroy(c->stream);
@@ -271,7 +274,7 @@ int zkb_ctx_zero_copy_inputs(zkb_ctx* c, int enable) {
 }
 const char* zkb_kernel_name(int kernel_id) {
     static const char* names[K_COUNT] = {"k_pow_table", "k_ntt_pass", "k_elementwise", "k_leaf8<false>", "k_leaf8<true>",
-                                         "k_node8", "k_tree", "k_open", "k_fold", "k_gather3", "k_leaf1"};
+                                         "k_node8", "k_tree", "k_open", "k_fold", "k_gather3", "k_leaf1", "k_fri_tail"};
     return (kernel_id >= 0 && kernel_id < K_COUNT) ? names[kernel_id] : nullptr;
 }
 

@@ -54,6 +54,8 @@ struct zkb_ctx {
     size_t assembly_threads = 16;    // host threads per batched call for proof-stream assembly (zkb_ctx_assembly_threads)
     bool zero_copy_inputs = true;    // pinned host LDE inputs are read in place by the first NTT pass (zkb_ctx_zero_copy_inputs)
     uint32_t* tree_bars = nullptr;   // k_tree's arrival counter (device; zero between launches)
+    void* fs_dev = nullptr;          // device Fiat-Shamir contexts (keccak.cuh FsDev x fs_dev_count) + the tail kernel's barrier word
+    size_t fs_dev_count = 0;
     uint32_t root_seq = 0;   // sequence number of the last root signalled through pinned memory
     uint64_t launches = 0;   // kernels launched through this context (bench "gpu_launches")
     // optional per-kernel-class device timing (CUDA events on the launching stream)
@@ -88,7 +90,7 @@ int set_err(zkb_ctx* c, int code, const char* fmt, ...);
 
 // kernel classes for zkb_ctx_profile_* (keep in sync with zkb_kernel_name)
 enum KernelId { K_POW_TABLE = 0, K_NTT_PASS = 1, K_ELEMENTWISE = 2, K_LEAF_TILE = 3, K_FOLD_LEAF_TILE = 4,
-                K_NODE_TILE = 5, K_MERKLE_SMALL = 6, K_OPEN = 7, K_FOLD = 8, K_GATHER = 9, K_LEAF1 = 10, K_COUNT = 11 };
+                K_NODE_TILE = 5, K_MERKLE_SMALL = 6, K_OPEN = 7, K_FOLD = 8, K_GATHER = 9, K_LEAF1 = 10, K_FRI_TAIL = 11, K_COUNT = 12 };
 
 // Brackets one launch with events when profiling is on; always counts the launch.
 struct LaunchScope {
@@ -97,6 +99,11 @@ struct LaunchScope {
     ~LaunchScope();
 };
 int prof_collect(zkb_ctx* c);
+
+// per-device kernel attributes (dynamic shared-memory opt-in) of ntt.cu / merkle.cu; called by zkb_ctx_create
+int ntt_device_init(zkb_ctx* c);
+int merkle_device_init(zkb_ctx* c);
+int fri_tail_device_init(zkb_ctx* c);
 
 int scratch_reserve(zkb_ctx* c, size_t bytes, void** out);
 // pinned host buffer `slot` of at least `bytes` (grow-only, owned by the context): D2H copies into pageable memory

@@ -15,11 +15,15 @@
 // value is written once to HBM and hashed while still in registers.  Every layer (codeword + pruned tree) stays on the device for the
 // query phase; only the 64-byte root goes to the host each round, where the Fiat-Shamir
 // callback turns it into alpha (SHAKE256 over a transcript of < 1.5 KB).
+#include <stddef.h>
+#include <stdlib.h>
 #include <string.h>
 #include <vector>
 #include "merkle.cuh"
 #include "ntt.cuh"
 #include "hosthash.hpp"
+#include "keccak.cuh"
+#include "fri_tail.cuh"
 
 namespace zkb {
 
@@ -68,6 +72,7 @@ struct zkb_fri_layers {
     std::vector<std::vector<uint8_t>> roots;
     void* arena = nullptr;               // one allocation: folded codewords + all trees
     void* owned_cw0 = nullptr;           // staged copy of a host codeword
+    std::vector<uint8_t> last_cw;        // host copy of the last codeword when the commit already brought it back
 };
 
 extern "C" {
@@ -116,8 +121,15 @@ void zkb_fri_layers_free(zkb_fri_layers* l) {
 // Shared body of zkb_fri_commit / zkb_lde_fri_commit.  Exactly one of `codeword` (n values)
 // and `coeffs` (n_coeffs <= n coefficients, extended to the coset codeword on the device
 // first: fast_coset_evaluate ntt_arithmetics.rs:161-170 with omega/offset of `p`) is set.
+// `dev_ps` non-null: the transcript is the library's own proof stream and the whole commit runs WITHOUT host hops -
+// the tree kernels do the Fiat-Shamir step on the device (keccak.cuh) and every layer of <= 2^17 values is handled
+// by the persistent tail kernel (fri_tail.cu); the roots are pushed to `dev_ps` afterwards (same bytes, same order).
+// Otherwise (`fs` callback: any foreign ProofStream) each round hands its root to the host as before.
+static int fri_commit_device_fs(zkb_ctx* c, zkb_fri_layers* L, const fe& omega_inv0, const DevPow& winv_tab,
+                                const std::vector<fe>& inv_offset, zkb_ps* ps);
+
 static int fri_commit_impl(zkb_ctx* c, const zkb_fri_params* p, const void* codeword, const void* coeffs,
-                           size_t n_coeffs, size_t n, zkb_fs_callback fs, void* user, zkb_fri_layers** out) {
+                           size_t n_coeffs, size_t n, zkb_fs_callback fs, void* user, zkb_fri_layers** out, zkb_ps* dev_ps = nullptr) {
     *out = nullptr;
     if (p->domain_length != n) return set_err(c, ZKB_ERR_LENGTH, "Length of the domain doesnt match the length of initial codeword");
     if (n < 2 || (n & (n - 1))) return set_err(c, ZKB_ERR_NOT_POW2, "Leafs len must be power of two (got %zu)", n);
@@ -189,6 +201,12 @@ static int fri_commit_impl(zkb_ctx* c, const zkb_fri_params* p, const void* code
         fe io = h_inv(offset);
         for (uint64_t r = 0; r < rounds; r++) { inv_offset[r] = io; io = h_mul(io, io); }
     }
+    if (dev_ps && rounds <= ZKB_FS_MAX_ROUNDS && getenv("ZKB_HOST_FS") == nullptr) {
+        rc = fri_commit_device_fs(c, L.get(), omega_inv0, winv_tab, inv_offset, dev_ps);
+        if (rc) return fail(rc);
+        *out = L.release();
+        return 0;
+    }
     // roots come back through mapped pinned memory: the top kernel writes root + sequence flag,
     // the host polls (no D2H copy, no stream synchronisation on the critical path)
     RootSignal sig;
@@ -232,6 +250,102 @@ static int fri_commit_impl(zkb_ctx* c, const zkb_fri_params* p, const void* code
         }
     }
     *out = L.release();
+    return 0;
+}
+
+static int ensure_fs_dev(zkb_ctx* c, size_t count) {
+    if (c->fs_dev_count >= count) return 0;
+    ZKB_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (c->fs_dev) cudaFree(c->fs_dev);
+    c->fs_dev = nullptr; c->fs_dev_count = 0;
+    ZKB_CUDA(c, cudaMalloc(&c->fs_dev, count * sizeof(FsDev) + 256));       // + the tail kernel's barrier word
+    ZKB_CUDA(c, cudaMemsetAsync(c->fs_dev, 0, count * sizeof(FsDev) + 256, c->stream));
+    c->fs_dev_count = count;
+    return 0;
+}
+
+#define ZKB_PINNED_FS_INIT 16384u     // c->pinned: staging of the FsDev head (sponge, kk_m, alpha, inv_off_m2[rounds])
+#define ZKB_PINNED_TAIL_OUT 65536u    // c->pinned: roots + last codeword written by the tail kernel
+
+static int fri_commit_device_fs(zkb_ctx* c, zkb_fri_layers* L, const fe& omega_inv0, const DevPow& winv_tab,
+                                const std::vector<fe>& inv_offset, zkb_ps* ps) {
+    const uint64_t rounds = L->rounds;
+    ZKB_TRY(ensure_fs_dev(c, 1));
+    FsDev* fs = (FsDev*)c->fs_dev;
+    uint32_t* bar = (uint32_t*)((uint8_t*)c->fs_dev + c->fs_dev_count * sizeof(FsDev));
+    {   // head of the FsDev: transcript sponge as `ps` stands now, and the per-round constants
+        FsDev* h = (FsDev*)(c->pinned + ZKB_PINNED_FS_INIT);
+        ps_export_sponge(ps, &h->sp);
+        h->kk_m = fe_zero(); h->alpha = fe_zero();
+        const fe r2 = ZKB_FE_R2;
+        for (uint64_t r = 0; r < rounds; r++) h->inv_off_m2[r] = fe_montmul(fe_to_mont(inv_offset[r]), r2);   // (1/offset_r) * R^2
+        const size_t head = offsetof(FsDev, inv_off_m2) + rounds * sizeof(fe);
+        ZKB_CUDA(c, cudaMemcpyAsync(fs, h, head, cudaMemcpyHostToDevice, c->stream));
+    }
+    // rounds handled by the throughput kernels (k_leaf8 / k_node8 / k_tree): every layer above the tail's limit
+    uint64_t r0 = 0;
+    fe omega_inv_r = omega_inv0;
+    while (r0 < rounds && !(L->layout[r0].top == 0 && L->layout[r0].log_n <= ZKB_TAIL_MAX_LOG)) {
+        const uint64_t r = r0;
+        FsHook hook;
+        hook.fs = fs; hook.round = (uint32_t)r; hook.want_alpha = r + 1 < rounds;
+        if (r == 0) {
+            ZKB_TRY(merkle_build_levels(c, L->cw[0], nullptr, L->len[0], L->layout[0], L->nodes[0], nullptr, &hook));
+        } else {
+            FoldArgs f;
+            f.cw = L->cw[r - 1]; f.next = (fe*)L->cw[r]; f.half = L->len[r];
+            f.winv = winv_tab; f.exp_mul = 1ull << (r - 1);
+            f.kk_m = fe_zero();
+            f.kk_dev = (const uint8_t*)&fs->kk_m; f.kk_stride = 0;
+            f.wr_inv_m = fe_to_mont(omega_inv_r);
+            ZKB_TRY(merkle_build_levels(c, nullptr, &f, L->len[r], L->layout[r], L->nodes[r], nullptr, &hook));
+            omega_inv_r = h_mul(omega_inv_r, omega_inv_r);
+        }
+        r0++;
+    }
+    const uint64_t last_len = L->len[rounds - 1];
+    const bool mapped_out = r0 < rounds && ZKB_PINNED_TAIL_OUT + ZKB_TAIL_HOST_CW_OFF + last_len * sizeof(fe) <= c->pinned_bytes;
+    RootSignal sig;
+    sig.host_root = c->pinned + ZKB_PINNED_TAIL_OUT;
+    sig.host_flag = reinterpret_cast<volatile uint32_t*>(c->pinned + 64);
+    sig.seq = ++c->root_seq;
+    if (r0 < rounds) {
+        TailArgs a;
+        memset(&a, 0, sizeof(a));
+        a.first_is_plain = r0 == 0;
+        a.cw_in = r0 == 0 ? L->cw[0] : L->cw[r0 - 1];
+        a.log_n0 = L->layout[r0].log_n;
+        a.n_rounds = (uint32_t)(rounds - r0);
+        a.r0 = (uint32_t)r0; a.total_rounds = (uint32_t)rounds;
+        for (uint64_t r = r0; r < rounds; r++) { a.cw[r - r0] = (fe*)L->cw[r]; a.nodes[r - r0] = L->nodes[r]; }
+        a.winv = winv_tab;
+        a.fs = fs; a.bar = bar;
+        if (mapped_out) { a.host_out = sig.host_root; a.host_flag = sig.host_flag; a.seq = sig.seq; }
+        ZKB_TRY(fri_tail_launch(c, a));
+    }
+    uint8_t* roots_host = c->pinned + ZKB_PINNED_TAIL_OUT;
+    if (mapped_out) {
+        uint64_t spins = 0;
+        for (;;) {
+            const uint32_t f = *sig.host_flag;
+            if (f == sig.seq) break;
+            if (f == ZKB_TAIL_TIMEOUT_FLAG) return set_err(c, ZKB_ERR_CUDA, "FRI tail kernel: grid barrier timed out");
+            if ((++spins & 0xFFFF) == 0) {
+                cudaError_t e = cudaStreamQuery(c->stream);
+                if (e != cudaSuccess && e != cudaErrorNotReady) return set_err(c, ZKB_ERR_CUDA, "FRI commit failed: %s", cudaGetErrorString(e));
+                if (e == cudaSuccess && *sig.host_flag != sig.seq) return set_err(c, ZKB_ERR_CUDA, "FRI tail kernel finished without signalling");
+            }
+        }
+        __sync_synchronize();
+        L->last_cw.assign(roots_host + ZKB_TAIL_HOST_CW_OFF, roots_host + ZKB_TAIL_HOST_CW_OFF + last_len * sizeof(fe));
+    } else {
+        ZKB_CUDA(c, cudaMemcpyAsync(roots_host, fs->roots, rounds * 64, cudaMemcpyDeviceToHost, c->stream));
+        ZKB_CUDA(c, cudaStreamSynchronize(c->stream));
+    }
+    for (uint64_t r = 0; r < rounds; r++) {
+        L->roots.emplace_back(roots_host + 64 * r, roots_host + 64 * r + 64);
+        zkb_ps_push_root(ps, roots_host + 64 * r, 64);                       // fri.rs:136-137, in round order
+    }
     return 0;
 }
 
@@ -322,6 +436,7 @@ static int ps_callback(void* user, uint32_t, const uint8_t root[64], int want_al
 
 static int push_last_codeword(zkb_fri_layers* L, zkb_ps* ps) {
     const uint64_t R = L->rounds;                           // fri.rs:166
+    if (L->last_cw.size() == L->len[R - 1] * 16) return zkb_ps_push_codeword(ps, L->last_cw.data(), L->len[R - 1]);
     std::vector<uint8_t> last(L->len[R - 1] * 16);
     ZKB_TRY(zkb_fri_layer_codeword(L, R - 1, last.data()));
     zkb_ps_push_codeword(ps, last.data(), L->len[R - 1]);
@@ -331,7 +446,7 @@ static int push_last_codeword(zkb_fri_layers* L, zkb_ps* ps) {
 int zkb_fri_commit_ps(zkb_ctx* c, const zkb_fri_params* p, const void* codeword, size_t n, zkb_ps* ps,
                       zkb_fri_layers** out) {
     if (!c || !p || !codeword || !ps || !out) return ZKB_ERR_ARG;
-    ZKB_TRY(fri_commit_impl(c, p, codeword, nullptr, 0, n, ps_callback, ps, out));
+    ZKB_TRY(fri_commit_impl(c, p, codeword, nullptr, 0, n, ps_callback, ps, out, ps));
     int rc = push_last_codeword(*out, ps);
     if (rc) { zkb_fri_layers_free(*out); *out = nullptr; }
     return rc;
@@ -340,7 +455,10 @@ int zkb_fri_commit_ps(zkb_ctx* c, const zkb_fri_params* p, const void* codeword,
 int zkb_lde_fri_commit_ps(zkb_ctx* c, const zkb_fri_params* p, const void* coeffs, size_t n_coeffs, zkb_ps* ps,
                           zkb_fri_layers** out) {
     if (!c || !p || !ps || !out) return ZKB_ERR_ARG;
-    ZKB_TRY(zkb_lde_fri_commit(c, p, coeffs, n_coeffs, ps_callback, ps, out));
+    if (n_coeffs && !coeffs) return ZKB_ERR_ARG;
+    if (n_coeffs > p->domain_length)
+        return set_err(c, ZKB_ERR_TOO_LONG, "coset_lde: %zu coefficients exceed root_order %llu", n_coeffs, (unsigned long long)p->domain_length);
+    ZKB_TRY(fri_commit_impl(c, p, nullptr, coeffs, n_coeffs, (size_t)p->domain_length, ps_callback, ps, out, ps));
     int rc = push_last_codeword(*out, ps);
     if (rc) { zkb_fri_layers_free(*out); *out = nullptr; }
     return rc;
@@ -352,7 +470,8 @@ int zkb_fri_prove(zkb_ctx* c, const zkb_fri_params* p, const void* codeword, siz
     const uint64_t ncc = p->num_colinearity_tests;
     if (zkb_fri_num_rounds(p) < 2) return set_err(c, ZKB_ERR_ROUNDS, "FRI::prove needs at least two rounds (fri.rs:225)");
     zkb_fri_layers* L = nullptr;
-    ZKB_TRY(zkb_fri_commit(c, p, codeword, n, ps_callback, ps, &L));
+    if (!codeword) return ZKB_ERR_ARG;
+    ZKB_TRY(fri_commit_impl(c, p, codeword, nullptr, 0, n, ps_callback, ps, &L, ps));
     struct Guard { zkb_fri_layers* l; ~Guard() { zkb_fri_layers_free(l); } } guard{L};
     const uint64_t R = L->rounds;
     ZKB_TRY(push_last_codeword(L, ps));

@@ -13,6 +13,7 @@
 #include <mutex>
 #include "hosthash.hpp"
 #include "fe128.cuh"
+#include "keccak.cuh"
 #include "../../include/zkb200.h"
 
 namespace zkb {
@@ -157,6 +158,46 @@ void zkb_ps::header(uint8_t out[16]) const {
     if (has_field) { out[0] = 0xCB; out[1] = 0x80; out[15] = 0x01; }
 }
 
+void zkb_ps::transcript_read(size_t off, size_t len, uint8_t* out) const {
+    uint8_t hdr[16];
+    header(hdr);
+    const size_t np = prefix.size();
+    for (size_t i = 0; i < len; ) {                       // three segments: prefix, 16-byte header, body
+        const size_t o = off + i;
+        if (o < np) { size_t k = std::min(len - i, np - o); memcpy(out + i, prefix.data() + o, k); i += k; }
+        else if (o < np + 16) { size_t k = std::min(len - i, np + 16 - o); memcpy(out + i, hdr + (o - np), k); i += k; }
+        else { size_t k = len - i; memcpy(out + i, body.data() + (o - np - 16), k); i += k; }
+    }
+}
+void zkb_ps::sponge_sync() {
+    if (sp_field != has_field) {                          // the header changed (once per stream): start over
+        memset(sp_st, 0, sizeof(sp_st));
+        sp_absorbed = 0;
+        sp_field = has_field;
+    }
+    const size_t total = transcript_len();
+    uint8_t block[136];
+    while (total - sp_absorbed >= 136) {
+        transcript_read(sp_absorbed, 136, block);
+        for (size_t i = 0; i < 17; i++) {
+            uint64_t w = 0;
+            for (int k = 7; k >= 0; k--) w = (w << 8) | block[8 * i + k];
+            sp_st[i] ^= w;
+        }
+        keccakf(sp_st);
+        sp_absorbed += 136;
+    }
+}
+namespace zkb {
+void ps_export_sponge(zkb_ps* ps, FsSponge* out) {
+    ps->sponge_sync();
+    memset(out, 0, sizeof(*out));
+    memcpy(out->st, ps->sp_st, sizeof(ps->sp_st));
+    out->fill = (uint32_t)(ps->transcript_len() - ps->sp_absorbed);
+    ps->transcript_read(ps->sp_absorbed, out->fill, out->buf);
+}
+}  // namespace zkb
+
 extern "C" {
 
 void zkb_blake2b512(const uint8_t* msg, size_t len, uint8_t out[64]) { host_blake2b512(msg, len, out); }
@@ -258,16 +299,31 @@ size_t zkb_ps_digest(const zkb_ps* ps, uint8_t* out, size_t cap) {
     }
     return total;
 }
-int zkb_ps_fiat_shamir(const zkb_ps* ps, size_t num_bytes, uint8_t* out) {
-    if (!ps || !out) return ZKB_ERR_ARG;
-    std::vector<uint8_t> buf;
-    buf.reserve(ps->prefix.size() + 16 + ps->body.size());
-    buf.insert(buf.end(), ps->prefix.begin(), ps->prefix.end());
-    uint8_t hdr[16];
-    ps->header(hdr);
-    buf.insert(buf.end(), hdr, hdr + 16);
-    buf.insert(buf.end(), ps->body.begin(), ps->body.end());
-    host_shake256(buf.data(), buf.size(), out, num_bytes);
+int zkb_ps_fiat_shamir(const zkb_ps* ps_c, size_t num_bytes, uint8_t* out) {
+    if (!ps_c || !out) return ZKB_ERR_ARG;
+    zkb_ps* ps = const_cast<zkb_ps*>(ps_c);                // the sponge is a cache of the transcript's complete blocks
+    ps->sponge_sync();
+    uint64_t st[25];
+    memcpy(st, ps->sp_st, sizeof(st));
+    uint8_t last[136];
+    const size_t rem = ps->transcript_len() - ps->sp_absorbed;   // < 136
+    memset(last, 0, sizeof(last));
+    ps->transcript_read(ps->sp_absorbed, rem, last);
+    last[rem] ^= 0x1F;
+    last[135] ^= 0x80;
+    for (size_t i = 0; i < 17; i++) {
+        uint64_t w = 0;
+        for (int k = 7; k >= 0; k--) w = (w << 8) | last[8 * i + k];
+        st[i] ^= w;
+    }
+    keccakf(st);
+    size_t produced = 0;
+    while (produced < num_bytes) {
+        const size_t take = std::min<size_t>(num_bytes - produced, 136);
+        for (size_t i = 0; i < take; i++) out[produced + i] = (uint8_t)(st[i / 8] >> (8 * (i % 8)));
+        produced += take;
+        if (produced < num_bytes) keccakf(st);
+    }
     return 0;
 }
 

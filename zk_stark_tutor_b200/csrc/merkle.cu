@@ -23,8 +23,8 @@
 #include <stdlib.h>
 #include <string.h>
 #include <vector>
-#include "merkle.cuh"
-#include "blake2b.cuh"
+#include "merkle_dev.cuh"
+#include "keccak.cuh"
 #include "hosthash.hpp"
 
 namespace zkb {
@@ -61,88 +61,6 @@ void TreeLayout::init(uint32_t log_n_) {
     total_nodes = off;
 }
 
-// ---- compression wrappers.  __noinline__ keeps ONE copy of each 2.2k-instruction body per
-// kernel instead of one per call site.
-__device__ __noinline__ void b2_leaf_call(const fe* a, uint64_t* h) {
-    uint64_t out[8];
-    blake2b_leaf(*a, out);
-#pragma unroll
-    for (int i = 0; i < 8; i++) h[i] = out[i];
-}
-__device__ __noinline__ void b2_node_call(const uint64_t* l, const uint64_t* r, uint64_t* h) {
-    uint64_t m[16], out[8];
-#pragma unroll
-    for (int i = 0; i < 8; i++) { m[i] = l[i]; m[8 + i] = r[i]; }
-    blake2b_compress_1block(m, 128, out);
-#pragma unroll
-    for (int i = 0; i < 8; i++) h[i] = out[i];
-}
-
-// ---- swizzled shared-memory digest store: node i = 4 x 16-byte chunks; a 128-byte line
-// holds nodes 2j, 2j+1; chunk position p in the line is stored at p ^ (line & 7).
-__device__ __forceinline__ void sm_store_digest(uint4* reg, uint32_t i, const uint64_t* h) {
-    uint32_t line = i >> 1, half = (i & 1u) << 2;
-#pragma unroll
-    for (uint32_t cidx = 0; cidx < 4; cidx++) {
-        uint32_t pos = (half | cidx) ^ (line & 7u);
-        reg[line * 8 + pos] = make_uint4((uint32_t)h[2 * cidx], (uint32_t)(h[2 * cidx] >> 32),
-                                         (uint32_t)h[2 * cidx + 1], (uint32_t)(h[2 * cidx + 1] >> 32));
-    }
-}
-__device__ __forceinline__ void sm_load_pair(const uint4* reg, uint32_t line, uint64_t* m) {
-#pragma unroll
-    for (uint32_t pidx = 0; pidx < 8; pidx++) {
-        uint4 x = reg[line * 8 + (pidx ^ (line & 7u))];
-        m[2 * pidx] = ((uint64_t)x.y << 32) | x.x;
-        m[2 * pidx + 1] = ((uint64_t)x.w << 32) | x.z;
-    }
-}
-__device__ __forceinline__ void g_store_digest(uint8_t* nodes, uint64_t idx, const uint64_t* h) {
-    uint4* dst = reinterpret_cast<uint4*>(nodes + idx * 64);
-#pragma unroll
-    for (int cidx = 0; cidx < 4; cidx++)
-        dst[cidx] = make_uint4((uint32_t)h[2 * cidx], (uint32_t)(h[2 * cidx] >> 32),
-                               (uint32_t)h[2 * cidx + 1], (uint32_t)(h[2 * cidx + 1] >> 32));
-}
-__device__ __forceinline__ void g_load_digest(const uint8_t* nodes, uint64_t idx, uint64_t* h) {
-    const uint4* src = reinterpret_cast<const uint4*>(nodes + idx * 64);
-#pragma unroll
-    for (int cidx = 0; cidx < 4; cidx++) {
-        uint4 x = __ldg(src + cidx);
-        h[2 * cidx] = ((uint64_t)x.y << 32) | x.x;
-        h[2 * cidx + 1] = ((uint64_t)x.w << 32) | x.z;
-    }
-}
-
-__device__ __forceinline__ fe pow2lvl_m(const DevPow& t, uint64_t e) {
-    fe lo = fe_ldg(t.lo + (e & ((1ull << t.lo_bits) - 1)));
-    fe hi = fe_ldg(t.hi + (e >> t.lo_bits));
-    return fe_montmul(hi, lo);
-}
-
-// The FRI split-and-fold (fri.rs:150-159) of element i: k_m = alpha/(offset*omega^i) * R
-__device__ __forceinline__ fe fold_one(const FoldArgs& f, uint64_t i, const fe& k_m) {
-    fe a = fe_ldg(f.cw + i), b = fe_ldg(f.cw + f.half + i);
-    fe s = fe_add(a, b), d = fe_sub(a, b);
-    fe v = fe_half(fe_add(s, fe_montmul(k_m, d)));
-    fe_store(f.next + i, v);
-    return v;
-}
-
-// Depth-first reduction of 8 digests produced one at a time by `next(j, out)`:
-// 7 node compressions, two pending digests at most per level.
-template <typename Next>
-__device__ __forceinline__ void reduce8(Next next, uint64_t* h) {
-    uint64_t d0[8], d1[8], a[8], b[8];
-    next(0, d0); next(1, d1); b2_node_call(d0, d1, a);          // level 1, #0
-    next(2, d0); next(3, d1); b2_node_call(d0, d1, d1);         // level 1, #1
-    b2_node_call(a, d1, b);                                     // level 2, #0
-    next(4, d0); next(5, d1); b2_node_call(d0, d1, a);          // level 1, #2
-    next(6, d0); next(7, d1); b2_node_call(d0, d1, d1);         // level 1, #3
-    b2_node_call(a, d1, a);                                     // level 2, #1
-    b2_node_call(b, a, h);                                      // level 3
-}
-
 // One thread per 8 leaves -> one level-3 node.  n_groups = n / 8.
 template <bool FOLD, int THREADS, int MINB>
 __global__ void __launch_bounds__(THREADS, MINB) k_leaf8(const fe* __restrict__ vals, FoldArgs f, uint64_t n_groups, uint8_t* __restrict__ out3) {
@@ -150,7 +68,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_leaf8(const fe* __restrict__ 
     if (g >= n_groups) return;
     const uint64_t i0 = g * 8;
     fe k_m;
-    if (FOLD) k_m = fe_montmul(f.kk_m, pow2lvl_m(f.winv, i0 * f.exp_mul));
+    if (FOLD) k_m = fe_montmul(f.kk_dev ? fe_ldg(reinterpret_cast<const fe*>(f.kk_dev)) : f.kk_m, pow2lvl_m(f.winv, i0 * f.exp_mul));
     uint64_t h[8];
     reduce8([&](int j, uint64_t* out) {
         fe v;
@@ -198,7 +116,26 @@ struct TopArgs {
     uint8_t* host_root;      // mapped pinned host memory (or nullptr)
     volatile uint32_t* host_flag;
     uint32_t seq;
+    FsDev* fs;               // device Fiat-Shamir (or nullptr): instance blockIdx.y at fs + blockIdx.y
+    uint32_t fs_round, fs_want_alpha;
 };
+
+// After the root of round `round`: Root(root) into the transcript sponge, the challenge, the next fold constant.
+// One warp; `root` = 8 words in shared memory.
+__device__ __forceinline__ void fs_after_root(FsDev* fs, FsSponge* sp, const uint64_t* root, uint32_t round, bool want_alpha, uint32_t lane) {
+    uint64_t* d = reinterpret_cast<uint64_t*>(sp);
+    const uint64_t* s = reinterpret_cast<const uint64_t*>(&fs->sp);
+    for (uint32_t i = lane; i < sizeof(FsSponge) / 8; i += 32) d[i] = s[i];
+    __syncwarp();
+    const fe alpha = fs_round_warp(sp, reinterpret_cast<const uint8_t*>(root), want_alpha, lane);
+    uint64_t* g = reinterpret_cast<uint64_t*>(&fs->sp);
+    for (uint32_t i = lane; i < sizeof(FsSponge) / 8; i += 32) g[i] = d[i];
+    if (lane < 8) reinterpret_cast<uint64_t*>(fs->roots[round])[lane] = root[lane];
+    if (lane == 0 && want_alpha) {
+        fe_store(&fs->alpha, alpha);
+        fe_store(&fs->kk_m, fe_montmul(alpha, fe_load(&fs->inv_off_m2[round])));
+    }
+}
 
 // One thread per leaf -> level-0 digests (the input of k_tree for small layers).
 template <bool FOLD>
@@ -212,7 +149,7 @@ __global__ void __launch_bounds__(256, 2) k_leaf1(const fe* __restrict__ vals, F
     if (FOLD) {
         f.cw += (uint64_t)inst * b.vals_stride;
         f.next += (uint64_t)inst * b.next_stride;
-        const fe kk = b.kk_m ? fe_ldg(b.kk_m + inst) : f.kk_m;
+        const fe kk = f.kk_dev ? fe_ldg(reinterpret_cast<const fe*>(f.kk_dev + (uint64_t)inst * f.kk_stride)) : b.kk_m ? fe_ldg(b.kk_m + inst) : f.kk_m;
         fe k_m = fe_montmul(kk, pow2lvl_m(f.winv, (uint64_t)i * f.exp_mul));
         v = fold_one(f, i, k_m);
     } else {
@@ -223,53 +160,10 @@ __global__ void __launch_bounds__(256, 2) k_leaf1(const fe* __restrict__ vals, F
     g_store_digest(out0, i, h);
 }
 
-__device__ __forceinline__ uint32_t dig_word(uint32_t i) { return i * 8 + (i >> 1); }
-static size_t dig_words_host(size_t i) { return i * 8 + (i >> 1); }
-
-// Reduce `n_in` digests held in `cur` to one, level by level, in shared memory.  The k-th
-// reduction (k = 0, 1, ...) produces relative level first_level + k, written to
-// out[first_level + k] at node offset (base >> (k + 1)) + j; `base` = global index of the first
-// input digest at its level.
-__device__ __forceinline__ void reduce_in_smem(uint64_t* cur, uint64_t* nxt, uint32_t n_in, uint8_t* const* out, uint64_t boff, uint32_t first_level,
-                                               uint64_t base, const TopArgs& a, bool is_root_chunk) {
-    const uint32_t tid = threadIdx.x, lane = tid & 31u, q = lane & 3u;
-    const uint32_t quad = tid >> 2, quads = blockDim.x >> 2, warp_quad0 = (tid >> 5) << 3;
-    uint32_t level = first_level;
-    for (uint32_t cnt = n_in >> 1; cnt >= 1; cnt >>= 1, level++) {
-        base >>= 1;
-        for (uint32_t j0 = 0; j0 < cnt; j0 += quads) {
-            if (j0 + warp_quad0 >= cnt) break;                      // no live quad in this warp
-            const uint32_t j = j0 + quad;
-            const bool live = j < cnt;
-            uint64_t h_lo, h_hi;
-            blake2b_quad(reinterpret_cast<const uint8_t*>(cur + (live ? 17u * j : 0u)), 128, lane, h_lo, h_hi);
-            if (live) {
-                uint64_t* s = nxt + dig_word(j);
-                s[q] = h_lo; s[4 + q] = h_hi;
-                unsigned long long* g = reinterpret_cast<unsigned long long*>(out[level] + boff + (base + j) * 64);
-                g[q] = h_lo; g[4 + q] = h_hi;
-                if (cnt == 1 && is_root_chunk && a.host_root) {   // the root: hand it to the polling host
-                    unsigned long long* hr = reinterpret_cast<unsigned long long*>(a.host_root);
-                    hr[q] = h_lo; hr[4 + q] = h_hi;
-                    __threadfence_system();
-                    __syncwarp(0xFu);
-                    if (q == 0) *a.host_flag = a.seq;
-                }
-            }
-        }
-        __syncthreads();
-        uint64_t* t = cur; cur = nxt; nxt = t;
-    }
-}
-__device__ __forceinline__ void load_chunk(uint64_t* buf, const uint8_t* src, uint32_t n_nodes, bool coherent) {
-    const unsigned long long* p = reinterpret_cast<const unsigned long long*>(src);
-    for (uint32_t w = threadIdx.x; w < n_nodes * 8; w += blockDim.x)
-        buf[dig_word(w >> 3) + (w & 7)] = coherent ? __ldcg(p + w) : __ldg(p + w);
-    __syncthreads();
-}
 __global__ void __launch_bounds__(512, 1) k_tree(TopArgs a) {
     extern __shared__ uint64_t tree_smem[];
     __shared__ uint32_t s_last;
+    __shared__ __align__(16) FsSponge s_sponge;
     const uint32_t chunk = 1u << a.chunk_log, chunks = a.count >> a.chunk_log;
     const uint32_t nmax = chunk > chunks ? chunk : chunks;
     const uint64_t boff = (uint64_t)blockIdx.y * a.batch_stride;   // instance blockIdx.y of a batch: every buffer shifts by boff
@@ -281,11 +175,23 @@ __global__ void __launch_bounds__(512, 1) k_tree(TopArgs a) {
     uint32_t n_in = chunk, first_level = 1;
     uint64_t base = (uint64_t)blockIdx.x * chunk;
     bool last_stage = chunks == 1;
+    auto out = [&](uint32_t level) -> uint8_t* { return a.level_out[level] + boff; };
 #pragma unroll 1
     for (;;) {
         load_chunk(bufA, src, n_in, first_level != 1);
-        reduce_in_smem(bufA, bufB, n_in, a.level_out, boff, first_level, base, a, last_stage);
-        if (last_stage) return;
+        const bool signal = last_stage && a.host_root != nullptr;
+        const uint64_t* root = reduce_in_smem(bufA, bufB, n_in, out, first_level, base, [&](uint32_t q, uint64_t h_lo, uint64_t h_hi) {
+            if (!signal) return;                               // the root: hand it to the polling host
+            unsigned long long* hr = reinterpret_cast<unsigned long long*>(a.host_root);
+            hr[q] = h_lo; hr[4 + q] = h_hi;
+            __threadfence_system();
+            __syncwarp(0xFu);
+            if (q == 0) { __threadfence_system(); *a.host_flag = a.seq; }   // the flag store is ordered after all four lanes' root stores
+        });
+        if (last_stage) {
+            if (a.fs && threadIdx.x < 32) fs_after_root(a.fs + blockIdx.y, &s_sponge, root, a.fs_round, a.fs_want_alpha != 0, threadIdx.x);
+            return;
+        }
         if (threadIdx.x == 0) {                // (the __syncthreads closing the reduction ordered the CTA's stores before this)
             __threadfence();
             const uint32_t arrived = atomicAdd(bar, 1u);
@@ -389,13 +295,13 @@ static uint32_t tree_chunks_log() {  // larger ones are cut into 2^this chunks (
     if (v < 0) { const char* e = getenv("ZKB_TREE_CHUNKS_LOG"); v = e ? atoi(e) : 7; if (v > 10) v = 10; if (v < 1) v = 1; }
     return (uint32_t)v;
 }
-static int launch_top(zkb_ctx* c, const TopArgs& a, uint32_t batch = 1) {
-    static bool attr_set = false;
+// per-device kernel attributes, set when a context is created on the device (zkb_ctx_create)
+int merkle_device_init(zkb_ctx* c) {
     const size_t max_smem = (size_t)(dig_words_host(ZKB_TREE_MAX_CHUNK) + 8 + dig_words_host(ZKB_TREE_MAX_CHUNK / 2) + 8) * sizeof(uint64_t);
-    if (!attr_set) {
-        ZKB_CUDA(c, cudaFuncSetAttribute(k_tree, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem));
-        attr_set = true;
-    }
+    ZKB_CUDA(c, cudaFuncSetAttribute(k_tree, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem));
+    return 0;
+}
+static int launch_top(zkb_ctx* c, const TopArgs& a, uint32_t batch = 1) {
     if (a.count > (1u << 20) || a.count < 2) return set_err(c, ZKB_ERR_ARG, "internal: k_tree takes 2..2^20 nodes");
     const uint32_t log_c = ilog2_u64(a.count);
     TopArgs b = a;
@@ -448,10 +354,14 @@ int wait_root(zkb_ctx* c, const RootSignal& s, uint8_t root_out[64]) {
 }
 
 int merkle_build_levels(zkb_ctx* c, const fe* vals, const FoldArgs* fold, uint64_t n,
-                        const TreeLayout& L, uint8_t* nodes, const RootSignal* signal) {
+                        const TreeLayout& L, uint8_t* nodes, const RootSignal* signal, const FsHook* fs) {
     const uint32_t log_n = L.log_n;
     TopArgs a;
     memset(&a, 0, sizeof(a));
+    if (fs && fs->fs) {
+        if (n < 2) return set_err(c, ZKB_ERR_ARG, "internal: device Fiat-Shamir needs a tree of at least two leaves");
+        a.fs = fs->fs; a.fs_round = fs->round; a.fs_want_alpha = fs->want_alpha;
+    }
     if (signal && n > 1) { a.host_root = signal->host_root; a.host_flag = signal->host_flag; a.seq = signal->seq; }
     if (L.top == 0) {                                   // small layer: thread per leaf, then the latency-mode tree
         FoldArgs fa;
@@ -511,7 +421,7 @@ int merkle_build_levels(zkb_ctx* c, const fe* vals, const FoldArgs* fold, uint64
 }
 
 int merkle_build_levels_batch(zkb_ctx* c, const fe* vals, const FoldArgs* fold, uint64_t n,
-                              const TreeLayout& L, uint8_t* nodes, const BatchArgs& b) {
+                              const TreeLayout& L, uint8_t* nodes, const BatchArgs& b, const FsHook* fs) {
     if (L.top != 0) return set_err(c, ZKB_ERR_ARG, "internal: batched trees are limited to 2^%u leaves", tree_leaf_log());
     if (b.batch < 1 || b.batch > ZKB_MAX_BATCH) return set_err(c, ZKB_ERR_ARG, "batch of %u trees not supported (max %u)", b.batch, ZKB_MAX_BATCH);
     FoldArgs fa;
@@ -530,6 +440,7 @@ int merkle_build_levels_batch(zkb_ctx* c, const fe* vals, const FoldArgs* fold, 
     a.nodes_in = nodes + L.level_off[0] * 64;
     a.count = (uint32_t)n;
     a.batch_stride = b.nodes_stride;
+    if (fs && fs->fs) { a.fs = fs->fs; a.fs_round = fs->round; a.fs_want_alpha = fs->want_alpha; }
     for (uint32_t l = 1; l <= L.log_n; l++) a.level_out[l] = nodes + L.level_off[l] * 64;
     return launch_top(c, a, b.batch);
 }

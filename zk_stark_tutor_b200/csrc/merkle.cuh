@@ -31,6 +31,18 @@ struct FoldArgs {
     uint64_t exp_mul;    // 2^round: (omega_r^-1)^i = (omega_0^-1)^(i*exp_mul)
     fe kk_m;             // alpha / offset_r, Montgomery form
     fe wr_inv_m;         // omega_r^-1, Montgomery form
+    // device Fiat-Shamir (keccak.cuh): when non-null the fold constant is READ from device memory (instance b of a batch at
+    // kk_dev + b * kk_stride bytes) - the previous layer's tree kernel left it there, no host hop in between
+    const uint8_t* kk_dev = nullptr;
+    uint64_t kk_stride = 0;
+};
+struct FsDev;
+// Device Fiat-Shamir hook of a tree build: after the root, the top kernel appends Root(root) to the transcript sponge in
+// fs (instance b of a batch: fs + b), stores the root in fs->roots[round] and - if want_alpha - leaves the next fold constant in fs->kk_m.
+struct FsHook {
+    FsDev* fs = nullptr;
+    uint32_t round = 0;
+    uint32_t want_alpha = 0;
 };
 
 // Build every stored level of the tree over `n` = 2^log_n values.  If `fold` is non-null
@@ -45,7 +57,7 @@ struct RootSignal {
     uint32_t seq;
 };
 int merkle_build_levels(zkb_ctx* c, const fe* vals, const FoldArgs* fold, uint64_t n,
-                        const TreeLayout& layout, uint8_t* nodes, const RootSignal* signal = nullptr);
+                        const TreeLayout& layout, uint8_t* nodes, const RootSignal* signal = nullptr, const FsHook* fs = nullptr);
 
 // Batched small trees (n <= 2^ZKB_TREE_LEAF_LOG, i.e. layout.top == 0): `batch` independent instances with
 // identical layouts, instance b = blockIdx.y working on buffers offset by b * stride.  One leaf launch and one
@@ -59,7 +71,7 @@ struct BatchArgs {
     const fe* kk_m = nullptr;    // per-instance alpha / offset_r in Montgomery form (overrides FoldArgs::kk_m)
 };
 int merkle_build_levels_batch(zkb_ctx* c, const fe* vals, const FoldArgs* fold, uint64_t n,
-                              const TreeLayout& layout, uint8_t* nodes, const BatchArgs& b);
+                              const TreeLayout& layout, uint8_t* nodes, const BatchArgs& b, const FsHook* fs = nullptr);
 // roots of a batch -> host (batch x 64 bytes), one strided copy; synchronises the stream
 int merkle_batch_roots(zkb_ctx* c, const TreeLayout& layout, const uint8_t* nodes, const BatchArgs& b, uint8_t* roots_host);
 // Spin until *signal->host_flag == signal->seq (falls back to a stream sync on a CUDA error).

@@ -306,15 +306,24 @@ static int launch_rr_t(zkb_ctx* c, const PassParams& p, uint32_t tiles, uint32_t
     const size_t smem = (S * (B + 1) + S) * sizeof(fe);
     dim3 grid(tiles, batch);
     LaunchScope ls(c, K_NTT_PASS);
-    if (p.transposed) {
-        static bool set_t = false;
-        if (!set_t) { ZKB_CUDA(c, cudaFuncSetAttribute(k_ntt_rr<LR1, LR2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)); set_t = true; }
-        k_ntt_rr<LR1, LR2, true><<<grid, ZKB_NTT_THREADS, smem, c->stream>>>(p);
-    } else {
-        static bool set_n = false;
-        if (!set_n) { ZKB_CUDA(c, cudaFuncSetAttribute(k_ntt_rr<LR1, LR2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)); set_n = true; }
-        k_ntt_rr<LR1, LR2, false><<<grid, ZKB_NTT_THREADS, smem, c->stream>>>(p);
-    }
+    if (p.transposed) k_ntt_rr<LR1, LR2, true><<<grid, ZKB_NTT_THREADS, smem, c->stream>>>(p);
+    else k_ntt_rr<LR1, LR2, false><<<grid, ZKB_NTT_THREADS, smem, c->stream>>>(p);
+    return 0;
+}
+template <int LR1, int LR2>
+static cudaError_t rr_attrs() {
+    cudaError_t e = cudaFuncSetAttribute(k_ntt_rr<LR1, LR2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_ntt_rr<LR1, LR2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    return e;
+}
+// The dynamic shared-memory opt-in is a per-DEVICE attribute of a kernel: it is set for the context's device
+// when the context is created (zkb_ctx_create, after cudaSetDevice), not behind a process-wide flag.
+int ntt_device_init(zkb_ctx* c) {
+    ZKB_CUDA(c, (rr_attrs<4, 4>()));
+    ZKB_CUDA(c, (rr_attrs<4, 3>()));
+    ZKB_CUDA(c, (rr_attrs<3, 3>()));
+    ZKB_CUDA(c, (rr_attrs<3, 2>()));
+    ZKB_CUDA(c, cudaFuncSetAttribute(k_ntt_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
     return 0;
 }
 // register-radix pass for log_s in 5..8
@@ -338,11 +347,6 @@ static size_t pass_smem_bytes(const PassParams& p) {
 }
 
 static int launch_pass(zkb_ctx* c, const PassParams& p, uint32_t tiles, uint32_t batch) {
-    static bool attr_set = false;
-    if (!attr_set) {
-        ZKB_CUDA(c, cudaFuncSetAttribute(k_ntt_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-        attr_set = true;
-    }
     dim3 grid(tiles, batch);
     { LaunchScope ls(c, K_NTT_PASS); k_ntt_pass<<<grid, ZKB_NTT_THREADS, pass_smem_bytes(p), c->stream>>>(p); }
     ZKB_CUDA(c, cudaGetLastError());
