@@ -19,6 +19,8 @@
 // At the end CTA 0 hands every root of the commit and the last codeword to the polling host through mapped
 // pinned memory.  Tree layout as TreeLayout with top == 0 (every level stored, level l at node offset
 // 2^(log_n+1) - 2^(log_n+1-l)), so FRI::query opens these layers like any other tree.
+#include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include "merkle_dev.cuh"
 #include "keccak.cuh"
@@ -28,18 +30,20 @@ namespace zkb {
 
 __device__ __forceinline__ uint64_t lvl_off(uint32_t log_n, uint32_t l) { return (2ull << log_n) - (2ull << (log_n - l)); }
 
+// Arrive + wait on a monotonically increasing counter in L2.  Release / acquire at gpu scope (both cumulative, and the
+// block barriers on either side extend them to the whole CTA) instead of two full membars around a relaxed atomic.
 __device__ __forceinline__ void grid_arrive_wait(uint32_t* bar, uint32_t target, volatile uint32_t* timeout_flag, uint32_t* dead) {
     __syncthreads();                                   // the CTA's stores precede the arrival
     if (threadIdx.x == 0) {
-        __threadfence();
-        atomicAdd(bar, 1u);
+        asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(bar) : "memory");
         const long long t0 = clock64();
-        uint32_t spins = 0;
-        while (*reinterpret_cast<volatile uint32_t*>(bar) < target) {
+        uint32_t spins = 0, v;
+        for (;;) {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar) : "memory");
+            if (v >= target) break;
             // a co-resident grid cannot deadlock here; the bound only keeps a broken launch from hanging the GPU
             if ((++spins & 0x3FFu) == 0 && clock64() - t0 > (4ll << 30)) { if (timeout_flag) *timeout_flag = ZKB_TAIL_TIMEOUT_FLAG; *dead = 1; break; }
         }
-        __threadfence();
     }
     __syncthreads();
 }
@@ -60,12 +64,14 @@ __global__ void __launch_bounds__(ZKB_TAIL_THREADS, 1) k_fri_tail(TailArgs a) {
     }
     __syncthreads();
     uint32_t arrivals = 0;
+#define ZKB_TAIL_STAMP(slot) do { if (a.dbg && cta == 0 && tid == 0) a.dbg[k * 8 + (slot)] = clock64(); } while (0)
 #pragma unroll 1
     for (uint32_t k = 0; k < a.n_rounds; k++) {
         const uint32_t log_n = a.log_n0 - k, n = 1u << log_n, round = a.r0 + k;
         const uint32_t chunk_log = log_n > 9 ? log_n - 7 : (log_n < 2 ? log_n : 2);
         const uint32_t chunk = 1u << chunk_log, chunks = n >> chunk_log;
         uint8_t* const nodes = a.nodes[k];
+        ZKB_TAIL_STAMP(0);
         if (cta < chunks) {
             // ---- leaf phase: (fold +) leaf hash of this CTA's chunk
             const bool plain = k == 0 && a.first_is_plain;
@@ -94,16 +100,20 @@ __global__ void __launch_bounds__(ZKB_TAIL_THREADS, 1) k_fri_tail(TailArgs a) {
                 g_store_digest(nodes, i, h);
             }
             __syncthreads();
+            ZKB_TAIL_STAMP(1);
             // ---- chunk phase: levels 1 .. chunk_log of this chunk
             reduce_in_smem(bufA, bufB, chunk, [&](uint32_t level) -> uint8_t* { return nodes + lvl_off(log_n, level) * 64; }, 1,
                            (uint64_t)cta * chunk, [](uint32_t, uint64_t, uint64_t) {});
         }
+        ZKB_TAIL_STAMP(2);
         grid_arrive_wait(a.bar, (++arrivals) * gridDim.x, a.host_flag, &s_dead);
+        ZKB_TAIL_STAMP(3);
         // ---- top phase (every CTA): chunk roots -> root, then the transcript
         load_chunk(bufA, nodes + lvl_off(log_n, chunk_log) * 64, chunks, true);
         const uint64_t* root = reduce_in_smem(bufA, bufB, chunks,
             [&](uint32_t level) -> uint8_t* { return cta == 0 ? nodes + lvl_off(log_n, level) * 64 : nullptr; },
             chunk_log + 1, 0, [](uint32_t, uint64_t, uint64_t) {});
+        ZKB_TAIL_STAMP(4);
         if (tid < 32) {
             const bool want = round + 1 < a.total_rounds;
             const fe alpha = fs_round_warp(&s_sp, reinterpret_cast<const uint8_t*>(root), want, lane);
@@ -111,6 +121,7 @@ __global__ void __launch_bounds__(ZKB_TAIL_THREADS, 1) k_fri_tail(TailArgs a) {
             if (cta == 0 && lane < 8) reinterpret_cast<uint64_t*>(a.fs->roots[round])[lane] = root[lane];
         }
         __syncthreads();
+        ZKB_TAIL_STAMP(5);
     }
     // ---- epilogue: results to the host
     if (cta == 0) {
@@ -148,11 +159,27 @@ int fri_tail_launch(zkb_ctx* c, const TailArgs& a) {
         return set_err(c, ZKB_ERR_ARG, "internal: FRI tail takes 1..%u rounds of at most 2^%u values", ZKB_TAIL_MAX_ROUNDS, ZKB_TAIL_MAX_LOG);
     if (c->sm_count < (int)ZKB_TAIL_CTAS) return set_err(c, ZKB_ERR_CUDA, "the persistent FRI tail needs %u SMs (device has %d)", ZKB_TAIL_CTAS, c->sm_count);
     TailArgs args = a;
+    static const bool debug = getenv("ZKB_TAIL_DEBUG") != nullptr;
+    DevBuf dbg;
+    if (debug) {
+        ZKB_TRY(dbg.alloc(c, ZKB_TAIL_MAX_ROUNDS * 8 * sizeof(unsigned long long)));
+        ZKB_CUDA(c, cudaMemsetAsync(dbg.p, 0, ZKB_TAIL_MAX_ROUNDS * 8 * sizeof(unsigned long long), c->stream));
+        args.dbg = (unsigned long long*)dbg.p;
+    }
     void* params[] = {&args};
     ZKB_CUDA(c, cudaMemsetAsync(args.bar, 0, sizeof(uint32_t), c->stream));     // arrive counter of the grid barrier
     {
         LaunchScope ls(c, K_FRI_TAIL);
         ZKB_CUDA(c, cudaLaunchCooperativeKernel((const void*)k_fri_tail, dim3(ZKB_TAIL_CTAS), dim3(ZKB_TAIL_THREADS), params, tail_smem_bytes(), c->stream));
+    }
+    if (debug) {
+        unsigned long long h[ZKB_TAIL_MAX_ROUNDS * 8];
+        ZKB_CUDA(c, cudaMemcpyAsync(h, dbg.p, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+        ZKB_CUDA(c, cudaStreamSynchronize(c->stream));
+        for (uint32_t k = 0; k < a.n_rounds; k++)
+            fprintf(stderr, "tail round %2u (2^%2u): leaf %6llu chunk %6llu barrier %6llu load+top %6llu fs %6llu clk; total %6llu\n", a.r0 + k, a.log_n0 - k,
+                    h[k * 8 + 1] - h[k * 8], h[k * 8 + 2] - h[k * 8 + 1], h[k * 8 + 3] - h[k * 8 + 2], h[k * 8 + 4] - h[k * 8 + 3],
+                    h[k * 8 + 5] - h[k * 8 + 4], h[k * 8 + 5] - h[k * 8]);
     }
     return 0;
 }

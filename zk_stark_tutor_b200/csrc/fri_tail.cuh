@@ -26,6 +26,7 @@ struct TailArgs {
     uint8_t* host_out;               // mapped pinned host memory or nullptr
     volatile uint32_t* host_flag;
     uint32_t seq;
+    unsigned long long* dbg;         // ZKB_TAIL_DEBUG: 8 clock stamps per round written by CTA 0 (or nullptr)
 };
 
 int fri_tail_device_init(zkb_ctx* c);

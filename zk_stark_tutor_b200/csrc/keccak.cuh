@@ -15,9 +15,10 @@
 // the state (pad 0x1F .. 0x80, one permutation), takes the last 16 of the 32 squeezed bytes as a
 // big-endian integer mod p (Field::sample) and multiplies by 1/offset_r for the fold.
 //
-// Keccak-f on a warp: lane x + 5y holds state lane A[x][y]; theta = 5 + 2 shuffles, rho = a
-// per-lane rotate, pi = one shuffle, chi = 2 shuffles: ~130 clk per round instead of ~440 for one
-// thread holding all 25 lanes (the challenge is on the critical path between two FRI layers).
+// Keccak-f on a warp: lane x + 5y holds state lane A[x][y]; theta = 4 + 2 shuffles, rho = a per-lane
+// rotate, pi + chi = 3 shuffles (three dependent shuffle stages per round; measured 283 clk per round on B200
+// = 3.5 us per permutation; one thread holding all 25 lanes would be bound by ALU issue at ~360 clk per round).  The challenge sits on the critical path between two
+// FRI layers.
 #pragma once
 #include <stdint.h>
 #include "fe128.cuh"
@@ -46,14 +47,6 @@ struct FsDev {
 
 #if defined(__CUDACC__)
 
-static __constant__ uint64_t ZKB_KECCAK_RC[24] = {
-    0x0000000000000001ULL, 0x0000000000008082ULL, 0x800000000000808aULL, 0x8000000080008000ULL,
-    0x000000000000808bULL, 0x0000000080000001ULL, 0x8000000080008081ULL, 0x8000000000008009ULL,
-    0x000000000000008aULL, 0x0000000000000088ULL, 0x0000000080008009ULL, 0x000000008000000aULL,
-    0x000000008000808bULL, 0x800000000000008bULL, 0x8000000000008089ULL, 0x8000000000008003ULL,
-    0x8000000000008002ULL, 0x8000000000000080ULL, 0x000000000000800aULL, 0x800000008000000aULL,
-    0x8000000080008081ULL, 0x8000000000008080ULL, 0x0000000080000001ULL, 0x8000000080008008ULL};
-
 __device__ __forceinline__ uint64_t rotl64_var(uint64_t v, uint32_t n) {   // n in 0..63
     uint32_t lo = (uint32_t)v, hi = (uint32_t)(v >> 32);
     if (n & 32u) { uint32_t t = lo; lo = hi; hi = t; }
@@ -63,7 +56,14 @@ __device__ __forceinline__ uint64_t rotl64_var(uint64_t v, uint32_t n) {   // n 
 }
 
 // One Keccak-f[1600] permutation; lane l < 25 holds A[l % 5][l / 5] (= state word l).  All 32 lanes call.
-__device__ __forceinline__ uint64_t keccak_f_warp(uint64_t a, uint32_t lane) {
+// Per round THREE shuffle stages sit on the dependency chain: (1) the four other lanes of the column for theta's
+// parity, (2) the parities of columns x-1 / x+1, (3) rho+pi+chi in one go - every lane fetches the three rotated
+// values its chi needs straight from their pre-pi source lanes (B[x'][y] = rot(A[(x' + 3y) % 5][x']), x' = x, x+1, x+2).
+// Fully unrolled: the round constant is an immediate.
+struct KeccakLane {
+    uint32_t rho, col1, col2, col3, col4, xm1, xp1, src0, src1, src2;
+};
+__device__ __forceinline__ KeccakLane keccak_lane(uint32_t lane) {
     // rho offsets r[x][y] at index x + 5y
     const uint32_t RHO = (lane == 0) ? 0 : (lane == 1) ? 1 : (lane == 2) ? 62 : (lane == 3) ? 28 : (lane == 4) ? 27 :
                          (lane == 5) ? 36 : (lane == 6) ? 44 : (lane == 7) ? 6 : (lane == 8) ? 55 : (lane == 9) ? 20 :
@@ -72,24 +72,48 @@ __device__ __forceinline__ uint64_t keccak_f_warp(uint64_t a, uint32_t lane) {
                          (lane == 20) ? 18 : (lane == 21) ? 2 : (lane == 22) ? 61 : (lane == 23) ? 56 : 14;
     const uint32_t l = lane < 25 ? lane : 24;          // idle lanes mirror lane 24 (valid shuffle sources only)
     const uint32_t x = l % 5u, y = l / 5u;
-    const uint32_t xm1 = (x + 4u) % 5u, xp1 = (x + 1u) % 5u, xp2 = (x + 2u) % 5u;
-    const uint32_t pi_src = ((x + 3u * y) % 5u) + 5u * x;      // B[x][y] = rot(A[(x + 3y) % 5][x])
-    const uint32_t chi1 = xp1 + 5u * y, chi2 = xp2 + 5u * y;
+    KeccakLane k;
+    k.rho = RHO;
+    k.col1 = x + 5u * ((y + 1u) % 5u); k.col2 = x + 5u * ((y + 2u) % 5u);
+    k.col3 = x + 5u * ((y + 3u) % 5u); k.col4 = x + 5u * ((y + 4u) % 5u);
+    k.xm1 = (x + 4u) % 5u; k.xp1 = (x + 1u) % 5u;
+    const uint32_t x1 = (x + 1u) % 5u, x2 = (x + 2u) % 5u;
+    k.src0 = ((x + 3u * y) % 5u) + 5u * x;
+    k.src1 = ((x1 + 3u * y) % 5u) + 5u * x1;
+    k.src2 = ((x2 + 3u * y) % 5u) + 5u * x2;
+    return k;
+}
+// (An exchange through shared memory - one 64-bit STS + k LDS per stage - was measured too: 304 clk per round
+// against 283 for the shuffles below; the first version, four stages + round constant from constant memory: 367.)
+template <int ROUND>
+__device__ __forceinline__ uint64_t keccak_round(uint64_t a, const KeccakLane& k, uint32_t lane) {
+    constexpr uint64_t RC[24] = {
+        0x0000000000000001ULL, 0x0000000000008082ULL, 0x800000000000808aULL, 0x8000000080008000ULL,
+        0x000000000000808bULL, 0x0000000080000001ULL, 0x8000000080008081ULL, 0x8000000000008009ULL,
+        0x000000000000008aULL, 0x0000000000000088ULL, 0x0000000080008009ULL, 0x000000008000000aULL,
+        0x000000008000808bULL, 0x800000000000008bULL, 0x8000000000008089ULL, 0x8000000000008003ULL,
+        0x8000000000008002ULL, 0x8000000000000080ULL, 0x000000000000800aULL, 0x800000008000000aULL,
+        0x8000000080008081ULL, 0x8000000000008080ULL, 0x0000000080000001ULL, 0x8000000080008008ULL};
     const unsigned FULL = 0xFFFFFFFFu;
-#pragma unroll 1
-    for (int round = 0; round < 24; round++) {
-        // theta
-        uint64_t c = __shfl_sync(FULL, a, x) ^ __shfl_sync(FULL, a, x + 5) ^ __shfl_sync(FULL, a, x + 10) ^
-                     __shfl_sync(FULL, a, x + 15) ^ __shfl_sync(FULL, a, x + 20);
-        uint64_t cp = __shfl_sync(FULL, c, xp1);
-        a ^= __shfl_sync(FULL, c, xm1) ^ ((cp << 1) | (cp >> 63));
-        // rho + pi
-        uint64_t b = __shfl_sync(FULL, rotl64_var(a, RHO), pi_src);
-        // chi
-        a = b ^ (~__shfl_sync(FULL, b, chi1) & __shfl_sync(FULL, b, chi2));
-        // iota
-        if (lane == 0) a ^= ZKB_KECCAK_RC[round];
-    }
+    // theta
+    const uint64_t c = a ^ __shfl_sync(FULL, a, k.col1) ^ __shfl_sync(FULL, a, k.col2) ^ __shfl_sync(FULL, a, k.col3) ^ __shfl_sync(FULL, a, k.col4);
+    const uint64_t cp = __shfl_sync(FULL, c, k.xp1);
+    a ^= __shfl_sync(FULL, c, k.xm1) ^ ((cp << 1) | (cp >> 63));
+    // rho, then pi + chi
+    const uint64_t r = rotl64_var(a, k.rho);
+    const uint64_t b0 = __shfl_sync(FULL, r, k.src0), b1 = __shfl_sync(FULL, r, k.src1), b2 = __shfl_sync(FULL, r, k.src2);
+    a = b0 ^ (~b1 & b2);
+    // iota
+    if (lane == 0) a ^= RC[ROUND];
+    return a;
+}
+static __device__ __noinline__ uint64_t keccak_f_warp(uint64_t a, uint32_t lane) {
+    const KeccakLane k = keccak_lane(lane);
+#define ZKB_KR(i) a = keccak_round<i>(a, k, lane)
+    ZKB_KR(0);  ZKB_KR(1);  ZKB_KR(2);  ZKB_KR(3);  ZKB_KR(4);  ZKB_KR(5);  ZKB_KR(6);  ZKB_KR(7);
+    ZKB_KR(8);  ZKB_KR(9);  ZKB_KR(10); ZKB_KR(11); ZKB_KR(12); ZKB_KR(13); ZKB_KR(14); ZKB_KR(15);
+    ZKB_KR(16); ZKB_KR(17); ZKB_KR(18); ZKB_KR(19); ZKB_KR(20); ZKB_KR(21); ZKB_KR(22); ZKB_KR(23);
+#undef ZKB_KR
     return a;
 }
 

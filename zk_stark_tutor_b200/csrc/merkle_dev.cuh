@@ -86,7 +86,10 @@ __device__ __forceinline__ uint64_t* reduce_in_smem(uint64_t* cur, uint64_t* nxt
     const uint32_t tid = threadIdx.x, lane = tid & 31u, q = lane & 3u;
     const uint32_t quad = tid >> 2, quads = blockDim.x >> 2, warp_quad0 = (tid >> 5) << 3;
     uint32_t level = first_level;
-    for (uint32_t cnt = n_in >> 1; cnt >= 1; cnt >>= 1, level++) {
+    uint32_t cnt = n_in >> 1;
+    // levels wider than one warp's eight quads: all warps, block barrier per level.  (One THREAD per node for the widest,
+    // throughput-bound levels was measured and is slower: its register pressure costs every other phase of the kernel more.)
+    for (; cnt > 8; cnt >>= 1, level++) {
         base >>= 1;
         uint8_t* const dst = out(level);
         for (uint32_t j0 = 0; j0 < cnt; j0 += quads) {
@@ -102,12 +105,38 @@ __device__ __forceinline__ uint64_t* reduce_in_smem(uint64_t* cur, uint64_t* nxt
                     unsigned long long* g = reinterpret_cast<unsigned long long*>(dst + (base + j) * 64);
                     g[q] = h_lo; g[4 + q] = h_hi;
                 }
-                if (cnt == 1) on_root(q, h_lo, h_hi);
             }
         }
         __syncthreads();
         uint64_t* t = cur; cur = nxt; nxt = t;
     }
+    // the last (<= 4) levels fit the eight quads of warp 0: no block barrier on this part of the chain
+    const uint32_t tail_levels = cnt >= 1 ? 32u - __clz(cnt) : 0u;
+    if (tid < 32) {
+        uint64_t* c2 = cur; uint64_t* n2 = nxt;
+        uint64_t b2 = base;
+        uint32_t lv = level;
+        for (uint32_t w = cnt; w >= 1; w >>= 1, lv++) {
+            b2 >>= 1;
+            uint8_t* const dst = out(lv);
+            const bool live = quad < w;
+            uint64_t h_lo, h_hi;
+            blake2b_quad(reinterpret_cast<const uint8_t*>(c2 + (live ? 17u * quad : 0u)), 128, lane, h_lo, h_hi);
+            if (live) {
+                uint64_t* s = n2 + dig_word(quad);
+                s[q] = h_lo; s[4 + q] = h_hi;
+                if (dst) {
+                    unsigned long long* g = reinterpret_cast<unsigned long long*>(dst + (b2 + quad) * 64);
+                    g[q] = h_lo; g[4 + q] = h_hi;
+                }
+                if (w == 1) on_root(q, h_lo, h_hi);
+            }
+            __syncwarp();
+            uint64_t* t = c2; c2 = n2; n2 = t;
+        }
+    }
+    if (tail_levels & 1u) { uint64_t* t = cur; cur = nxt; nxt = t; }
+    __syncthreads();
     return cur;
 }
 __device__ __forceinline__ void load_chunk(uint64_t* buf, const uint8_t* src, uint32_t n_nodes, bool coherent) {
