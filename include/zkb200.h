@@ -48,6 +48,7 @@ typedef struct zkb_ctx zkb_ctx;
 typedef struct zkb_tree zkb_tree;
 typedef struct zkb_fri_layers zkb_fri_layers;
 typedef struct zkb_ps zkb_ps;
+struct zkb_fri_params;
 
 /* ---- context ------------------------------------------------------------------------ */
 /* One context per GPU.  `stream` = a cudaStream_t to run on (e.g. torch's current stream; pass
@@ -104,6 +105,41 @@ int zkb_ntt_batch(zkb_ctx* ctx, const uint8_t root[16], int inverse, const void*
  * (n = number of GPUs, after the all-to-all). */
 int zkb_ntt_strided(zkb_ctx* ctx, const uint8_t root[16], int inverse, const void* in, size_t n, size_t stride,
                     size_t count, void* out);
+
+/* ---- one NTT across the GPUs of a box (BASELINE configs[4]) ----------------------------------------
+ * ntt / intt (ntt.rs:7-68) of N = world * n_local values as a four-step transform: rank r holds the CYCLIC slice
+ * x[r + world*m]; after the transform it holds X[k2 + n_local*k1] for k2 in [r*blk, (r+1)*blk), blk = n_local / world, laid out
+ * [k1 * blk + (k2 - r*blk)].  The twiddle and the all-to-all exchange are fused into the last pass of the local transform: its
+ * stores go straight into the receiving GPU's HBM over NVLink (peer access inside one process, CUDA IPC between processes).
+ * world: 1, 2, 4, 8 or 16. */
+typedef struct zkb_ntt4 zkb_ntt4;
+/* rank `rank` of `world`, on ctx's GPU; allocates the (double-buffered) receive buffer of n_local values */
+int zkb_ntt4_create(zkb_ctx* ctx, uint32_t rank, uint32_t world, size_t n_local, zkb_ntt4** plan);
+void zkb_ntt4_free(zkb_ntt4* plan);
+/* one process holds every rank (a context per GPU; several ranks may share a GPU): plans[r] = rank r */
+int zkb_ntt4_connect_local(zkb_ntt4* const* plans, size_t world);
+/* one process per GPU: export this rank's 128-byte handle, all-gather the handles over any transport (rank-major), connect */
+int zkb_ntt4_export(zkb_ntt4* plan, uint8_t handle[128]);
+int zkb_ntt4_connect_ipc(zkb_ntt4* plan, const uint8_t* all_handles /* world x 128 bytes */);
+/* steps 1-3 (local transform, twiddle, stores into the peers' buffers), asynchronous on the context's stream.  `root` = the
+ * primitive (world*n_local)-th root of the WHOLE transform; inverse != 0: intt (root^-1, N^-1 applied in finish). */
+int zkb_ntt4_scatter(zkb_ntt4* plan, const uint8_t root[16], int inverse, const void* x_local);
+/* step 4 (world-point transforms across the received pieces) -> out (n_local values).  Every rank's scatter of this transform
+ * must have completed first: the caller orders that in the stream (zkb_ntt4_run: events; between processes any stream-ordered
+ * collective on the context's stream, e.g. a one-element NCCL all-reduce, or a host barrier after zkb_ctx_sync). */
+int zkb_ntt4_finish(zkb_ntt4* plan, void* out);
+/* scatter on every rank, events, finish on every rank (one process).  Asynchronous for device pointers. */
+int zkb_ntt4_run(zkb_ntt4* const* plans, size_t world, const uint8_t root[16], int inverse, const void* const* x_local, void* const* out);
+/* the whole transform in one call: ctxs[r] runs rank r (plans are created and released inside) */
+int zkb_ntt_4step(zkb_ctx* const* ctxs, size_t world, const uint8_t root[16], int inverse, const void* const* x_local, size_t n_local,
+                  void* const* out);
+
+/* ---- independent columns across the GPUs of a box (BASELINE configs[3]; stark.rs:373-381 per register) -------
+ * Column i (n_coeffs coefficients; host pointer, or device pointer on the GPU of ctxs[i % n_ctx]) is extended to the FRI domain and
+ * FRI-committed (zkb_lde_fri_commit_ps with a fresh IndependentProofStream) on ctxs[i % n_ctx], one host thread per context;
+ * roots_out receives ncols x zkb_fri_num_rounds(p) x 64 bytes.  No field data crosses NVLink. */
+int zkb_lde_commit_batch(zkb_ctx* const* ctxs, size_t n_ctx, const struct zkb_fri_params* p, const void* const* cols, size_t n_coeffs,
+                         size_t ncols, uint8_t* roots_out);
 
 /* ---- polynomial helpers : src/field/polynomial.rs, src/fft/ntt_arithmetics.rs --------- */
 /* Polynomial::scale polynomial.rs:109-121: out[i] = factor^i * coeffs[i] */

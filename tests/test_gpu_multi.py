@@ -53,6 +53,61 @@ def test_four_step_cuda_steps_emulated_on_one_gpu(world, log_n):
     ctx.close()
 
 
+@pytest.mark.parametrize("world,log_n,inverse", [(2, 6, False), (8, 12, False), (2, 14, False), (8, 16, True), (4, 20, False), (8, 22, False),
+                                                  (16, 20, False), (8, 26, False)])
+def test_four_step_fused_exchange_emulated_on_one_gpu(world, log_n, inverse):
+    """zkb_ntt4_*: every rank of the fused four-step transform (twiddle + exchange stores inside the last local pass, then the
+    register-radix cross stage) in ONE process on one GPU - the same kernels and the same peer-pointer stores the multi-GPU run
+    uses, with the barrier reduced to stream order.  2^26 / 8 ranks is BASELINE configs[4] at full size."""
+    import torch
+    ctx = zk.Context(0)
+    n = 1 << log_n
+    L = n // world
+    x = C.synth(0x5EED0005, n)
+    w = F.primitive_nth_root(n)
+    plans = [fs.Ntt4Plan(ctx, r, world, L) for r in range(world)]
+    fs.connect_local(plans)
+    xs = [cuda(fs.scatter_cyclic(x, r, world)) for r in range(world)]
+    outs = [torch.empty_like(t) for t in xs]
+    for rep in range(2):                                              # twice: both halves of the double-buffered receive side
+        fs.run_local(plans, w, xs, outs, inverse)
+    ctx.sync()
+    got = fs.gather_natural([host(o).reshape(world, L // world, 2) for o in outs])
+    del xs, outs
+    want = C.ntt(w, x, inverse=inverse)
+    assert np.array_equal(got, want)
+    for p in plans:
+        p.close()
+    ctx.close()
+
+
+def test_lde_commit_batch_abi():
+    """zkb_lde_commit_batch (configs[3] through the C ABI): columns dealt over the contexts of one process; roots == the oracle's"""
+    import ctypes
+    import torch
+    from oracle import proof_stream as PS, fastfri
+    from oracle.fri import FRI as OFRI
+    ngpu = max(1, min(torch.cuda.device_count(), 4))
+    ctxs = [zk.Context(d, stream="own") for d in range(ngpu)] + [zk.Context(0, stream="own")]     # two contexts on GPU 0 as well
+    log_n, ncols = 13, 7
+    n = 1 << log_n
+    w = F.primitive_nth_root(n)
+    fri = zk.FRI(F.GENERATOR, w, n, 4, 64, ctxs[0])
+    cols = [np.ascontiguousarray(C.synth(0x5EED0004 + c, n // 4)) for c in range(ncols)]
+    rounds = fri.num_rounds()
+    roots = np.zeros((ncols, rounds, 64), dtype=np.uint8)
+    ca = (ctypes.c_void_p * len(ctxs))(*[c.h for c in ctxs])
+    pa = (ctypes.c_void_p * ncols)(*[c.ctypes.data for c in cols])
+    ctxs[0].check(ctxs[0].lib.zkb_lde_commit_batch(ca, len(ctxs), ctypes.byref(fri.params), pa, n // 4, ncols,
+                                                   roots.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8))))
+    for c in range(ncols):
+        ofri = OFRI(F.GENERATOR, w, n, 4, 64)
+        _, trees, _ = fastfri.commit(ofri, C.coset_lde(w, n, F.GENERATOR, cols[c]), PS.IndependentProofStream())
+        assert [bytes(roots[c, r]) for r in range(rounds)] == [t.root for t in trees]
+    for c in ctxs:
+        c.close()
+
+
 def test_ntt_strided_ragged_counts():
     import torch
     ctx = zk.Context(0)
@@ -88,7 +143,15 @@ def _nccl_worker(rank, world, port, log_n, q):
     xl = torch.from_numpy(fs.scatter_cyclic(x, rank, world).view(np.int64)).cuda()
     piece = fs.ntt_4step(fs.CudaEngine(ctx), w, xl, rank, world)
     ctx.sync()
+    plan = fs.Ntt4Plan(ctx, rank, world, n // world)                 # the native path: exchange fused into the last local pass, CUDA IPC
+    plan.connect_group()
+    for _ in range(3):
+        fused = fs.ntt_4step_fused(plan, w, xl)
+    torch.cuda.synchronize()
+    assert torch.equal(fused.reshape(-1, 2), piece.reshape(-1, 2)), "fused exchange != NCCL all-to-all path"
     q.put((rank, piece.cpu().numpy().view(np.uint64).tobytes()))
+    dist.barrier()
+    plan.close()
     dist.barrier()
     ctx.close()
     dist.destroy_process_group()
@@ -101,7 +164,7 @@ def test_four_step_nccl_all_gpus():
     world = 1 << (world.bit_length() - 1)
     if world < 2:
         pytest.skip("needs >= 2 GPUs (the single-GPU emulation above covers the CUDA steps)")
-    log_n = 20
+    log_n = 26 if world >= 8 else 22
     mpc = mp.get_context("spawn")
     q = mpc.Queue()
     port = _free_port()

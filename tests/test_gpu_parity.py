@@ -60,7 +60,7 @@ def test_ntt_reference_kats(ctx):
     assert zk.intt(w, [int(v) for v in k["coeffs"]], ctx) == [int(v) for v in k["values"]]
 
 
-@pytest.mark.parametrize("log_n", list(range(1, 15)) + [16, 17, 20, 21, 22])
+@pytest.mark.parametrize("log_n", list(range(1, 15)) + [16, 17, 20, 21, 22, 23])
 def test_ntt_vs_oracle(ctx, log_n):
     n = 1 << log_n
     x = C.synth(0x5EED0002, n)
@@ -118,9 +118,10 @@ def test_ntt_device_resident_and_batched(ctx):
     assert np.array_equal(zk.ntt_batch(w, rag, ctx=ctx), want_r)
 
 
-@pytest.mark.parametrize("log_n", [24])
+@pytest.mark.parametrize("log_n", [24, 25, 26])
 def test_ntt_full_size_roundtrip_and_spot(ctx, log_n):
-    """BASELINE configs[1] top size: oracle on the whole vector (C oracle, seconds)."""
+    """BASELINE configs[1] top size (2^24) and north_star's upper end on ONE GPU (2^25, 2^26: four register-radix passes):
+    oracle on the whole vector (C oracle, seconds)."""
     n = 1 << log_n
     x = C.synth(0x5EED0002, n)
     w = F.primitive_nth_root(n)

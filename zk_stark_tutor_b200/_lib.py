@@ -69,6 +69,16 @@ PROTOTYPES = {
     "zkb_intt": (ctypes.c_int, [vp, c_u8p, vp, sz, vp]),
     "zkb_ntt_batch": (ctypes.c_int, [vp, c_u8p, ctypes.c_int, vp, sz, sz, vp, sz, sz]),
     "zkb_ntt_strided": (ctypes.c_int, [vp, c_u8p, ctypes.c_int, vp, sz, sz, sz, vp]),
+    "zkb_ntt4_create": (ctypes.c_int, [vp, ctypes.c_uint32, ctypes.c_uint32, sz, ctypes.POINTER(vp)]),
+    "zkb_ntt4_free": (None, [vp]),
+    "zkb_ntt4_connect_local": (ctypes.c_int, [ctypes.POINTER(vp), sz]),
+    "zkb_ntt4_export": (ctypes.c_int, [vp, c_u8p]),
+    "zkb_ntt4_connect_ipc": (ctypes.c_int, [vp, c_u8p]),
+    "zkb_ntt4_scatter": (ctypes.c_int, [vp, c_u8p, ctypes.c_int, vp]),
+    "zkb_ntt4_finish": (ctypes.c_int, [vp, vp]),
+    "zkb_ntt4_run": (ctypes.c_int, [ctypes.POINTER(vp), sz, c_u8p, ctypes.c_int, ctypes.POINTER(vp), ctypes.POINTER(vp)]),
+    "zkb_ntt_4step": (ctypes.c_int, [ctypes.POINTER(vp), sz, c_u8p, ctypes.c_int, ctypes.POINTER(vp), sz, ctypes.POINTER(vp)]),
+    "zkb_lde_commit_batch": (ctypes.c_int, [ctypes.POINTER(vp), sz, ctypes.POINTER(FriParams), ctypes.POINTER(vp), sz, sz, c_u8p]),
     "zkb_poly_scale": (ctypes.c_int, [vp, c_u8p, vp, sz, vp]),
     "zkb_coset_lde": (ctypes.c_int, [vp, c_u8p, u64, c_u8p, vp, sz, vp]),
     "zkb_coset_lde_batch": (ctypes.c_int, [vp, c_u8p, u64, c_u8p, vp, sz, sz, vp, sz, sz]),

@@ -50,6 +50,16 @@ struct PassParams {
     uint32_t has_post;           // multiply stored value by `post` (n^-1 for the iNTT)
     fe post;
     const fe* tw_s;              // w_S^j * R, j < S/2
+    // two-level outer index (four-pass transforms): outer = oa + outer_a_count * ob
+    uint32_t outer_a_count;      // 0: single level
+    uint64_t ld_outer2, st_outer2;
+    // final pass only (k_ntt_rr<.., .., true, true>): the four-step NTT's exchange fused into the store.
+    // out[k] *= osc_base^k (running product per thread), then element k goes to peer[k >> log_blk] + peer_row + (k & (blk - 1))
+    uint32_t has_oscale;
+    DevPow osc;
+    uint32_t n_peers, log_blk;
+    uint64_t peer_row;
+    fe* peer[ZKB_NTT_MAX_PEERS];
 };
 
 __device__ __forceinline__ fe pow2lvl(const DevPow& t, uint64_t e) {
@@ -62,15 +72,26 @@ __device__ __forceinline__ uint32_t bitrev(uint32_t x, uint32_t bits) { return _
 
 #define ZKB_NTT_THREADS 256
 
+// block -> (outer offset in, outer offset out, inner)
+__device__ __forceinline__ void tile_origin(const PassParams& p, uint64_t& in_base, uint64_t& out_base, uint32_t& inner) {
+    const uint32_t outer = blockIdx.x / p.inner_count;
+    inner = blockIdx.x % p.inner_count;
+    uint32_t oa = outer, ob = 0;
+    if (p.outer_a_count) { oa = outer % p.outer_a_count; ob = outer / p.outer_a_count; }
+    in_base = (uint64_t)oa * p.ld_outer + (uint64_t)ob * p.ld_outer2 + (uint64_t)inner * p.ld_inner;
+    out_base = (uint64_t)oa * p.st_outer + (uint64_t)ob * p.st_outer2 + (uint64_t)inner * p.st_inner;
+}
+
 __global__ void __launch_bounds__(ZKB_NTT_THREADS) k_ntt_pass(const PassParams p) {
     extern __shared__ uint4 smem_raw[];
     fe* sm = reinterpret_cast<fe*>(smem_raw);
     const uint32_t S = 1u << p.log_s, B = 1u << p.log_b;
     const uint32_t tid = threadIdx.x;
-    const uint32_t outer = blockIdx.x / p.inner_count, inner = blockIdx.x % p.inner_count;
-    const uint64_t in_base = (uint64_t)outer * p.ld_outer + (uint64_t)inner * p.ld_inner;
+    uint64_t in_base, out_base;
+    uint32_t inner;
+    tile_origin(p, in_base, out_base, inner);
     const fe* in = p.in + (uint64_t)blockIdx.y * p.in_batch;
-    fe* out = p.out + (uint64_t)blockIdx.y * p.out_batch + (uint64_t)outer * p.st_outer + (uint64_t)inner * p.st_inner;
+    fe* out = p.out + (uint64_t)blockIdx.y * p.out_batch + out_base;
     fe* tws = sm + (p.transposed ? (size_t)B * (S + 1) : (size_t)S * B);
     for (uint32_t j = tid; j < (S >> 1); j += ZKB_NTT_THREADS) tws[j] = fe_ldg(p.tw_s + j);
 
@@ -235,7 +256,7 @@ template <int LOGR> __host__ __device__ constexpr int brev_c(int i) {
     return r;
 }
 
-template <int LR1, int LR2, bool TRANSPOSED>
+template <int LR1, int LR2, bool TRANSPOSED, bool EXCHANGE = false>
 __global__ void __launch_bounds__(ZKB_NTT_THREADS, 2) k_ntt_rr(const PassParams p) {
     extern __shared__ uint4 smem_raw[];
     constexpr uint32_t R1 = 1u << LR1, R2 = 1u << LR2, S = R1 * R2;
@@ -243,10 +264,11 @@ __global__ void __launch_bounds__(ZKB_NTT_THREADS, 2) k_ntt_rr(const PassParams 
     const uint32_t B = 1u << p.log_b, pitch = B + 1;
     fe* tws = sm + (size_t)S * pitch;                      // w_S^j * R, j < S
     const uint32_t tid = threadIdx.x;
-    const uint32_t outer = blockIdx.x / p.inner_count, inner = blockIdx.x % p.inner_count;
-    const uint64_t in_base = (uint64_t)outer * p.ld_outer + (uint64_t)inner * p.ld_inner;
+    uint64_t in_base, out_base;
+    uint32_t inner;
+    tile_origin(p, in_base, out_base, inner);
     const fe* in = p.in + (uint64_t)blockIdx.y * p.in_batch;
-    fe* out = p.out + (uint64_t)blockIdx.y * p.out_batch + (uint64_t)outer * p.st_outer + (uint64_t)inner * p.st_inner;
+    fe* out = p.out + (uint64_t)blockIdx.y * p.out_batch + out_base;
     for (uint32_t j = tid; j < S; j += ZKB_NTT_THREADS) tws[j] = fe_ldg(p.tw_s + j);
     __syncthreads();
     // ---- step 1
@@ -287,6 +309,12 @@ __global__ void __launch_bounds__(ZKB_NTT_THREADS, 2) k_ntt_rr(const PassParams 
             t = pow2lvl_c(p.tw, (uint64_t)ka * col * p.tw_mul);
             step = pow2lvl_c(p.tw, (uint64_t)R1 * col * p.tw_mul);
         }
+        fe ot, ostep;                                          // EXCHANGE: running osc_base^(output index)
+        const uint64_t lin0 = out_base + (uint64_t)ka * p.st_k + (uint64_t)b * p.st_b;
+        if (EXCHANGE && p.has_oscale) {
+            ot = pow2lvl_c(p.osc, lin0);
+            ostep = pow2lvl_c(p.osc, (uint64_t)R1 * p.st_k);
+        }
 #pragma unroll
         for (uint32_t kb = 0; kb < R2; kb++) {
             fe y = x[brev_c<LR2>(kb)];
@@ -295,7 +323,17 @@ __global__ void __launch_bounds__(ZKB_NTT_THREADS, 2) k_ntt_rr(const PassParams 
                 else y = mm(y, t);
             }
             if (p.has_post) y = mm(y, p.post);
-            fe_store(out + (uint64_t)(ka + R1 * kb) * p.st_k + (uint64_t)b * p.st_b, y);
+            if (EXCHANGE) {
+                if (p.has_oscale) {
+                    if (kb + 1 < R2) { fe2 r = mm2(y, ot, ot, ostep); y = r.a; ot = r.b; }
+                    else y = mm(y, ot);
+                }
+                const uint64_t lin = lin0 + (uint64_t)(R1 * kb) * p.st_k;
+                fe* dst = p.n_peers ? p.peer[lin >> p.log_blk] + p.peer_row + (lin & ((1ull << p.log_blk) - 1)) : p.out + lin;
+                fe_store(dst, y);
+            } else {
+                fe_store(out + (uint64_t)(ka + R1 * kb) * p.st_k + (uint64_t)b * p.st_b, y);
+            }
         }
     }
 }
@@ -306,7 +344,8 @@ static int launch_rr_t(zkb_ctx* c, const PassParams& p, uint32_t tiles, uint32_t
     const size_t smem = (S * (B + 1) + S) * sizeof(fe);
     dim3 grid(tiles, batch);
     LaunchScope ls(c, K_NTT_PASS);
-    if (p.transposed) k_ntt_rr<LR1, LR2, true><<<grid, ZKB_NTT_THREADS, smem, c->stream>>>(p);
+    if (p.transposed && (p.has_oscale || p.n_peers)) k_ntt_rr<LR1, LR2, true, true><<<grid, ZKB_NTT_THREADS, smem, c->stream>>>(p);
+    else if (p.transposed) k_ntt_rr<LR1, LR2, true><<<grid, ZKB_NTT_THREADS, smem, c->stream>>>(p);
     else k_ntt_rr<LR1, LR2, false><<<grid, ZKB_NTT_THREADS, smem, c->stream>>>(p);
     return 0;
 }
@@ -314,6 +353,7 @@ template <int LR1, int LR2>
 static cudaError_t rr_attrs() {
     cudaError_t e = cudaFuncSetAttribute(k_ntt_rr<LR1, LR2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_ntt_rr<LR1, LR2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_ntt_rr<LR1, LR2, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
     return e;
 }
 // The dynamic shared-memory opt-in is a per-DEVICE attribute of a kernel: it is set for the context's device
@@ -376,28 +416,30 @@ int ntt_exec(zkb_ctx* c, fe root, const fe* d_in, size_t n_in, size_t in_stride,
                                         cudaMemcpyDeviceToDevice, c->stream));
         return 0;
     }
-    if (log_n > 30) return set_err(c, ZKB_ERR_ARG, "ntt: length 2^%u not supported on one GPU", log_n);
+    if (log_n > 31) return set_err(c, ZKB_ERR_ARG, "ntt: length 2^%u not supported on one GPU", log_n);
     if (o.inverse) root = h_inv(root);
     PassParams base;
     memset(&base, 0, sizeof(base));
-    if (o.inverse) {
+    if (o.inverse && !o.no_post) {
         base.has_post = 1;
         base.post = fe_to_mont(h_inv(h_from_u64(N)));
     }
     DevPow sc{};
     if (o.has_scale) ZKB_TRY(get_pow_table(c, o.scale_base, log_n, &sc));
 
-    uint32_t a, b2 = 0, c3;
+    // Pass plan: N = N_0 * ... * N_{P-1}.  2^13..2^32: every pass is 5..8 bits wide and runs in the register-radix
+    // kernel (two passes up to 2^16, three up to 2^24, four above: Bailey's split applied P - 1 times).
+    uint32_t wdt[4] = {0, 0, 0, 0};
     int passes;
-    // 2^13..2^24: every pass is 5..8 bits wide and runs in the register-radix kernel
-    const bool fast = log_n > TILE_LOG && log_n <= 24;
-    if (log_n <= TILE_LOG) { passes = 1; a = 0; c3 = log_n; }
-    else if (log_n <= 16) { passes = 2; a = (log_n + 1) / 2; c3 = log_n - a; }
-    else if (fast) { passes = 3; a = (log_n + 2) / 3; b2 = (log_n - a + 1) / 2; c3 = log_n - a - b2; }
-    else if (log_n <= 20) { passes = 2; a = (log_n + 1) / 2; c3 = log_n - a; }
-    else { passes = 3; a = (log_n + 2) / 3; b2 = (log_n - a + 1) / 2; c3 = log_n - a - b2; }
+    const bool fast = log_n > TILE_LOG;
+    if (!fast) { passes = 1; wdt[0] = log_n; }
+    else {
+        passes = log_n <= 16 ? 2 : log_n <= 24 ? 3 : 4;
+        uint32_t left = log_n;
+        for (int i = 0; i < passes; i++) { wdt[i] = (left + (passes - i) - 1) / (passes - i); left -= wdt[i]; }
+    }
+    if (o.exchange && (!fast || batch != 1)) return set_err(c, ZKB_ERR_ARG, "internal: fused exchange needs one transform of at least 2^%u values", TILE_LOG + 1);
     auto tw_table = [&](uint32_t log_s, const fe** out) -> int {
-        if (!fast) return tw_s_table(c, root, log_n, log_s, out);
         fe ws = root;                                        // full table w_S^j * R, j < S
         for (uint32_t i = 0; i < log_n - log_s; i++) ws = h_mul(ws, ws);
         DevPow t;
@@ -405,11 +447,6 @@ int ntt_exec(zkb_ctx* c, fe root, const fe* d_in, size_t n_in, size_t in_stride,
         *out = t.lo;
         return 0;
     };
-    auto launch = [&](const PassParams& p, uint32_t tiles) -> int {
-        return fast ? launch_pass_rr(c, p, tiles, (uint32_t)batch) : launch_pass(c, p, tiles, (uint32_t)batch);
-    };
-    const uint64_t N1 = 1ull << a, N2 = 1ull << b2, N3 = 1ull << c3, M = N2 * N3;
-
     if (passes == 1) {
         // One tile: the literal radix-2 DIT of ntt.rs:26-46 (bit-reversed load, twiddles
         // root^k from one table, explicit e - o*w) - op for op the reference's loop, so the
@@ -430,58 +467,127 @@ int ntt_exec(zkb_ctx* c, fe root, const fe* d_in, size_t n_in, size_t in_stride,
     ZKB_TRY(get_pow_table(c, root, log_n, &tw));
     fe* A = nullptr;
     ZKB_TRY(scratch_reserve(c, sizeof(fe) * N * batch, (void**)&A));
-    {   // pass 1: N1-point transforms down the columns (stride M), B adjacent columns per tile
+    // M[i] = N / (N_0 ... N_i): stride of digit n_i in the working layout A[k_0 M_0 + ... + k_i M_i + m]
+    uint64_t M[4], Nprod[5];
+    Nprod[0] = 1;
+    for (int i = 0; i < passes; i++) { Nprod[i + 1] = Nprod[i] << wdt[i]; M[i] = N >> (ilog2_u64(Nprod[i + 1])); }
+    for (int i = 0; i + 1 < passes; i++) {
+        // pass i: N_i-point transforms over digit n_i (stride M_i) for every prefix (k_0 .. k_{i-1}) and column m < M_i,
+        // B adjacent columns per tile; then the twiddle w_{M_{i-1}}^(k_i m) = w_N^(k_i m N_0...N_{i-1})
         PassParams p = base;
         p.has_post = 0;
-        p.in = d_in; p.out = A;
-        p.log_s = a;
-        uint32_t lb = TILE_LOG - a;
-        if ((1ull << lb) > M) lb = ilog2_u64(M);
+        p.in = i == 0 ? d_in : A; p.out = A;
+        p.log_s = wdt[i];
+        uint32_t lb = TILE_LOG - wdt[i];
+        if ((1ull << lb) > M[i]) lb = ilog2_u64(M[i]);
         p.log_b = lb; p.transposed = 0;
-        p.inner_count = (uint32_t)(M >> lb);
-        p.ld_s = M; p.ld_b = 1; p.ld_outer = 0; p.ld_inner = 1ull << lb;
-        p.st_k = M; p.st_b = 1; p.st_outer = 0; p.st_inner = 1ull << lb;
-        p.in_batch = in_stride; p.out_batch = N;
-        p.has_valid = n_in < N; p.n_valid = n_in;
-        uint64_t rows = (n_in + M - 1) / M;            // rows n1 that hold any data
-        if (rows == 0) rows = 1;
-        uint32_t rl = ilog2_u64(rows);                 // ceil log2
-        p.skip_log = a - rl;
-        p.has_tw = 1; p.tw = tw; p.tw_mul = 1;
-        p.has_scale = o.has_scale; p.sc = sc;
-        ZKB_TRY(tw_table(a, &p.tw_s));
-        ZKB_TRY(launch(p, p.inner_count));
+        p.inner_count = (uint32_t)(M[i] >> lb);
+        p.ld_s = M[i]; p.ld_b = 1; p.ld_inner = 1ull << lb;
+        p.st_k = M[i]; p.st_b = 1; p.st_inner = 1ull << lb;
+        p.ld_outer = p.st_outer = i == 0 ? 0 : M[i - 1];
+        p.in_batch = i == 0 ? in_stride : N; p.out_batch = N;
+        if (i == 0) {
+            p.has_valid = n_in < N; p.n_valid = n_in;
+            uint64_t rows = (n_in + M[0] - 1) / M[0];      // rows n_0 that hold any data
+            if (rows == 0) rows = 1;
+            p.skip_log = wdt[0] - ilog2_u64(rows);          // ceil log2
+            p.has_scale = o.has_scale; p.sc = sc;
+        }
+        p.has_tw = 1; p.tw = tw; p.tw_mul = Nprod[i];
+        ZKB_TRY(tw_table(wdt[i], &p.tw_s));
+        ZKB_TRY(launch_pass_rr(c, p, (uint32_t)(Nprod[i] * p.inner_count), (uint32_t)batch));
     }
-    if (passes == 3) {   // pass 2: N2-point transforms inside each row k1 (stride N3), in place
-        PassParams p = base;
-        p.has_post = 0;
-        p.in = A; p.out = A;
-        p.log_s = b2;
-        uint32_t lb = TILE_LOG - b2;
-        if ((1ull << lb) > N3) lb = c3;
-        p.log_b = lb; p.transposed = 0;
-        p.inner_count = (uint32_t)(N3 >> lb);
-        p.ld_s = N3; p.ld_b = 1; p.ld_outer = M; p.ld_inner = 1ull << lb;
-        p.st_k = N3; p.st_b = 1; p.st_outer = M; p.st_inner = 1ull << lb;
-        p.in_batch = N; p.out_batch = N;
-        p.has_tw = 1; p.tw = tw; p.tw_mul = N1;
-        ZKB_TRY(tw_table(b2, &p.tw_s));
-        ZKB_TRY(launch(p, (uint32_t)(N1 * p.inner_count)));
-    }
-    {   // final pass: N3-point transforms along contiguous runs, transposing store
+    {   // final pass: N_{P-1}-point transforms along contiguous runs; tile = B consecutive k_0 (stride M_0 in, contiguous out),
+        // outer = (k_1 .. k_{P-2}); transposing store X[k_0 + N_0 k_1 + N_0 N_1 k_2 + ...]
+        const int f = passes - 1;
         PassParams p = base;
         p.in = A; p.out = d_out;
-        p.log_s = c3;
-        uint32_t lb = TILE_LOG - c3;
-        if ((1ull << lb) > N1) lb = a;
+        p.log_s = wdt[f];
+        uint32_t lb = TILE_LOG - wdt[f];
+        if (lb > wdt[0]) lb = wdt[0];
         p.log_b = lb; p.transposed = 1;
-        p.inner_count = (uint32_t)(N1 >> lb);
-        p.ld_s = 1; p.ld_b = M; p.ld_outer = N3; p.ld_inner = (1ull << lb) * M;
-        p.st_k = N1 * N2; p.st_b = 1; p.st_outer = N1; p.st_inner = 1ull << lb;
+        p.inner_count = (uint32_t)(Nprod[1] >> lb);
+        p.ld_s = 1; p.ld_b = M[0]; p.ld_inner = (1ull << lb) * M[0];
+        p.st_k = Nprod[f]; p.st_b = 1; p.st_inner = 1ull << lb;
+        uint64_t outer = 1;
+        if (passes == 3) { outer = 1ull << wdt[1]; p.ld_outer = M[1]; p.st_outer = Nprod[1]; }
+        if (passes == 4) {
+            outer = 1ull << (wdt[1] + wdt[2]);
+            p.outer_a_count = 1u << wdt[1];
+            p.ld_outer = M[1]; p.st_outer = Nprod[1];          // k_1
+            p.ld_outer2 = M[2]; p.st_outer2 = Nprod[2];        // k_2
+        }
         p.in_batch = N; p.out_batch = out_stride;
-        ZKB_TRY(tw_table(c3, &p.tw_s));
-        ZKB_TRY(launch(p, (uint32_t)(N2 * p.inner_count)));
+        if (o.exchange) {
+            const NttExchange& x = *o.exchange;
+            p.has_oscale = 1;
+            ZKB_TRY(get_pow_table(c, x.oscale_base, log_n, &p.osc));
+            p.n_peers = x.n_peers; p.log_blk = x.log_blk; p.peer_row = x.peer_row;
+            for (uint32_t q = 0; q < x.n_peers && q < ZKB_NTT_MAX_PEERS; q++) p.peer[q] = x.peer[q];
+        }
+        ZKB_TRY(tw_table(wdt[f], &p.tw_s));
+        ZKB_TRY(launch_pass_rr(c, p, (uint32_t)(outer * p.inner_count), (uint32_t)batch));
     }
+    return 0;
+}
+
+// ---- cross-rank stage of the four-step NTT: `blk` interleaved G-point transforms, element n1 of column i at in[n1 * blk + i],
+// output k1 at out[k1 * blk + i].  One thread per column, the whole transform in registers (G <= 16); HBM-bound.
+template <int LOGG>
+__global__ void __launch_bounds__(256) k_ntt_cross(const fe* __restrict__ in, fe* __restrict__ out, uint64_t blk, const fe* __restrict__ tw_g,
+                                                   uint32_t has_post, fe post) {
+    constexpr uint32_t G = 1u << LOGG;
+    __shared__ fe tws[G];
+    if (threadIdx.x < G) tws[threadIdx.x] = fe_ldg(tw_g + threadIdx.x);
+    __syncthreads();
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= blk) return;
+    fe x[G];
+#pragma unroll
+    for (uint32_t n1 = 0; n1 < G; n1++) x[n1] = fe_ldg(in + (uint64_t)n1 * blk + i);
+    dft_dif<LOGG>(x, tws, 1);
+#pragma unroll
+    for (uint32_t k1 = 0; k1 < G; k1++) {
+        fe y = x[brev_c<LOGG>(k1)];
+        if (has_post) y = mm(y, post);
+        fe_store(out + (uint64_t)k1 * blk + i, y);
+    }
+}
+
+// root_g: primitive 2^log_g-th root (canonical); post: nullptr or a Montgomery-form factor applied to every output
+int ntt_cross_exec(zkb_ctx* c, const fe& root_g, uint32_t log_g, const fe* d_in, fe* d_out, uint64_t blk, const fe* post) {
+    if (log_g < 1 || log_g > 4) return set_err(c, ZKB_ERR_ARG, "four-step NTT: 2, 4, 8 or 16 ranks");
+    DevPow t;
+    ZKB_TRY(get_pow_table(c, root_g, log_g, &t));
+    const unsigned blocks = (unsigned)((blk + 255) / 256);
+    const fe pf = post ? *post : fe_zero();
+    LaunchScope ls(c, K_NTT_PASS);
+    switch (log_g) {
+        case 1: k_ntt_cross<1><<<blocks, 256, 0, c->stream>>>(d_in, d_out, blk, t.lo, post != nullptr, pf); break;
+        case 2: k_ntt_cross<2><<<blocks, 256, 0, c->stream>>>(d_in, d_out, blk, t.lo, post != nullptr, pf); break;
+        case 3: k_ntt_cross<3><<<blocks, 256, 0, c->stream>>>(d_in, d_out, blk, t.lo, post != nullptr, pf); break;
+        default: k_ntt_cross<4><<<blocks, 256, 0, c->stream>>>(d_in, d_out, blk, t.lo, post != nullptr, pf); break;
+    }
+    ZKB_CUDA(c, cudaGetLastError());
+    return 0;
+}
+
+// out[k] = in[k] * base^k scattered like NttExchange (the unfused fallback for local transforms below 2^13)
+__global__ void k_twiddle_scatter(const fe* __restrict__ in, uint64_t n, DevPow sc, PassParams p) {
+    const uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const fe y = fe_montmul(fe_ldg(in + k), pow2lvl(sc, k));
+    fe_store(p.peer[k >> p.log_blk] + p.peer_row + (k & ((1ull << p.log_blk) - 1)), y);
+}
+int ntt_twiddle_scatter(zkb_ctx* c, const fe* d_in, uint64_t n, const NttExchange& x) {
+    PassParams p;
+    memset(&p, 0, sizeof(p));
+    p.n_peers = x.n_peers; p.log_blk = x.log_blk; p.peer_row = x.peer_row;
+    for (uint32_t q = 0; q < x.n_peers && q < ZKB_NTT_MAX_PEERS; q++) p.peer[q] = x.peer[q];
+    DevPow sc;
+    ZKB_TRY(get_pow_table(c, x.oscale_base, ilog2_u64(n), &sc));
+    { LaunchScope ls(c, K_ELEMENTWISE); k_twiddle_scatter<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(d_in, n, sc, p); }
+    ZKB_CUDA(c, cudaGetLastError());
     return 0;
 }
 

@@ -85,3 +85,102 @@ def gather_natural(pieces):
         for k1 in range(world):
             out[k1 * L + q * blk:k1 * L + (q + 1) * blk] = p[k1]
     return out
+
+
+# ---- the native path: exchange fused into the last local pass (csrc/ntt4.cu, zkb_ntt4_*) -------------------------
+class Ntt4Plan:
+    """zkb_ntt4: rank `rank` of a `world`-rank four-step transform of world * n_local values on ctx's GPU.  The twiddle and the
+    exchange are part of the last pass of the local transform: its stores land in the receiving GPU's HBM over NVLink."""
+
+    def __init__(self, ctx, rank, world, n_local):
+        import ctypes
+        self.ctx, self.rank, self.world, self.n_local = ctx, rank, world, n_local
+        self.h = ctypes.c_void_p()
+        ctx.check(ctx.lib.zkb_ntt4_create(ctx.h, rank, world, n_local, ctypes.byref(self.h)))
+
+    def export(self):
+        import ctypes
+        buf = (ctypes.c_uint8 * 128)()
+        self.ctx.check(self.ctx.lib.zkb_ntt4_export(self.h, buf))
+        return bytes(buf)
+
+    def connect_ipc(self, all_handles):
+        import ctypes
+        raw = b"".join(all_handles)
+        assert len(raw) == 128 * self.world
+        self.ctx.check(self.ctx.lib.zkb_ntt4_connect_ipc(self.h, (ctypes.c_uint8 * len(raw)).from_buffer_copy(raw)))
+
+    def connect_group(self, group=None):
+        """one process per GPU: all-gather the IPC handles over torch.distributed (any backend), then open the peers' buffers"""
+        import torch
+        import torch.distributed as dist
+        if self.world == 1:
+            return
+        backend = dist.get_backend(group)
+        dev = torch.device("cuda", self.ctx.device) if backend == "nccl" else torch.device("cpu")
+        mine = torch.frombuffer(bytearray(self.export()), dtype=torch.uint8).to(dev)
+        parts = [torch.empty_like(mine) for _ in range(self.world)]
+        dist.all_gather(parts, mine, group=group)
+        self.connect_ipc([bytes(p.cpu().numpy().tobytes()) for p in parts])
+
+    def scatter(self, w, x_local, inverse=False):
+        from .context import Vec, le16
+        v = Vec(x_local)
+        assert v.n == self.n_local
+        self.ctx.check(self.ctx.lib.zkb_ntt4_scatter(self.h, le16(w), 1 if inverse else 0, v.ptr))
+        return v
+
+    def finish(self, out):
+        from .context import Vec
+        v = Vec(out)
+        assert v.n == self.n_local
+        self.ctx.check(self.ctx.lib.zkb_ntt4_finish(self.h, v.ptr))
+        return out
+
+    def close(self):
+        if self.h is not None and self.h.value:
+            self.ctx.lib.zkb_ntt4_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def connect_local(plans):
+    """every rank in this process (one context per GPU, or several ranks on one GPU)"""
+    import ctypes
+    arr = (ctypes.c_void_p * len(plans))(*[p.h for p in plans])
+    plans[0].ctx.check(plans[0].ctx.lib.zkb_ntt4_connect_local(arr, len(plans)))
+
+
+def run_local(plans, w, xs, outs, inverse=False):
+    """zkb_ntt4_run: scatter on every rank, events, finish on every rank; xs / outs: per-rank CUDA tensors (n_local, 2)"""
+    import ctypes
+    from .context import le16
+    n = len(plans)
+    pa = (ctypes.c_void_p * n)(*[p.h for p in plans])
+    xa = (ctypes.c_void_p * n)(*[x.data_ptr() for x in xs])
+    oa = (ctypes.c_void_p * n)(*[o.data_ptr() for o in outs])
+    plans[0].ctx.check(plans[0].ctx.lib.zkb_ntt4_run(pa, n, le16(w), 1 if inverse else 0, xa, oa))
+    return outs
+
+
+def ntt_4step_fused(plan, w, x_local, out=None, group=None, inverse=False):
+    """One process per GPU (torch.distributed, NCCL): scatter -> a one-element all-reduce on the context's stream (the
+    stream-ordered barrier: it completes once every rank's scatter kernels have) -> finish.  No host synchronisation.
+    The context must run on torch's current stream.  Returns (world, L/world, 2) like ntt_4step."""
+    import torch
+    import torch.distributed as dist
+    if out is None:
+        out = torch.empty_like(x_local)
+    plan.scatter(w, x_local, inverse)
+    if plan.world > 1:
+        token = getattr(plan, "_token", None)
+        if token is None:
+            token = plan._token = torch.zeros(1, dtype=torch.int32, device=x_local.device)
+        dist.all_reduce(token, group=group)
+    plan.finish(out)
+    return out.view(plan.world, plan.n_local // plan.world, 2)
