@@ -52,8 +52,9 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--log-n", type=int, default=24)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--cpu-log-n", type=int, default=14, help="codeword size of the bounded CPU sample")
+    ap.add_argument("--cpu-log-n", type=int, default=20, help="codeword size of the bounded single-core CPU sample (cpu_baseline)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-sub-records", action="store_true", help="default workload: skip the configs[3] / configs[4] sub-records")
     ap.add_argument("--workload", default="codeword", choices=["codeword", "columns", "ntt", "ntt4step", "proofs", "signatures"],
                     help="codeword: one 2^log_n codeword per rank (weak scaling, the default, BASELINE configs[2]); "
                          "columns: BASELINE configs[3], --columns trace columns of 2^log_n (default 64 x 2^22) dealt "
@@ -164,21 +165,53 @@ def reference_arm(args):
                           "cpu_baseline": {"value": cores / dt, "unit": "signatures/s", "cores": cores, "kind": "port", "sample": sample},
                           "e2e": {"value": cores / dt, "unit": "signatures/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}), flush=True)
         return
-    steps, warmup = max(1, min(args.steps, 3)), min(args.warmup, 1)
-    eps, ms = cpu_run(args.cpu_log_n, cores, steps, warmup)
-    sample = "%d independent 2^%d codewords per step (one per host thread), LDE + FRI commit each" % (cores, args.cpu_log_n)
+    # ---- the metric's own workload (configs[2] / configs[3]): every host thread runs whole LDE + FRI commits with the reference's
+    # algorithms.  Same --steps / --warmup as the B200 arm; a "step" is a BOUNDED SAMPLE of the workload - one codeword per host
+    # thread, of the largest size (<= 2^20) for which all steps fit in ~150 s, calibrated on a 2^12 codeword - because one 2^24
+    # codeword takes the reference's algorithm ~10 minutes per core.  `config` names the workload the B200 arm ran; the sample and
+    # the flagged n log n extrapolation to it are in cpu_baseline.
+    columns_mode = args.workload == "columns"
+    log_n = 22 if (columns_mode and args.log_n == 24) else args.log_n
+    steps, warmup = max(1, args.steps), max(0, args.warmup)
+    t0 = time.perf_counter()
+    cpu_lde_fri_commit(12, SEED)
+    t12 = time.perf_counter() - t0
+    budget = 150.0 / (steps + warmup) / 1.5                  # per step; 1.5: all threads share the memory system
+    sample_log = 12
+    while sample_log < min(20, log_n) and t12 * ((1 << (sample_log + 1)) * (sample_log + 1)) / ((1 << 12) * 12) <= budget:
+        sample_log += 1
+    if args.cpu_log_n != 20:
+        sample_log = args.cpu_log_n
+    eps, ms = cpu_run(sample_log, cores, steps, warmup)
+    n = 1 << log_n
+    rounds = fri_rounds(n)
+    ext = eps * sample_log / log_n
+    sample = ("%d independent 2^%d codewords per step (one per host thread), LDE + FRI commit each, faithful-algorithm C port of the reference "
+              "(bit-serial mul_mod, per-element pow / xgcd, recursive allocating Merkle; Rust crate, no rustc in the image); %d steps + %d warm-up"
+              % (cores, sample_log, steps, warmup))
     line = {
         "impl": "reference", "metric": METRIC, "value": eps / 1e6, "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": warmup,
-        "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u128 (prime field, integer)",
-        "data": "synthetic",
-        "config": {"workload": "coset LDE + Merkle + full FRI commit (ef 4, 64 colinearity tests); CPU sample: " + sample,
-                   "log_n": args.cpu_log_n},
-        "cpu_baseline": {"value": eps / 1e6, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample +
-                         "; faithful-algorithm C port of the reference (Rust crate, no rustc in the image)"},
+        "ms_per_step": ms, "higher_is_better": True, "scaling": "strong" if columns_mode else "weak", "vs_baseline": None,
+        "dtype": "u128 (prime field, integer)", "data": "synthetic",
+        "config": codeword_config(args, log_n, rounds, n >> (rounds - 1), columns_mode, args.gpus, args.lanes if (columns_mode and args.lanes > 1) else 0),
+        "cpu_baseline": {"value": eps / 1e6, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+                         "sample_log_n": sample_log,
+                         "extrapolated": {"log_n": log_n, "value": ext / 1e6,
+                                          "how": "FLAGGED EXTRAPOLATION, not a measurement: measured elements/s at 2^%d x (%d / %d), i.e. n log n scaling"
+                                                 % (sample_log, sample_log, log_n)}},
         "e2e": {"value": eps / 1e6, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
+
+
+def fri_rounds(n):
+    """FRI::num_rounds fri.rs:40-50"""
+    r = 0
+    while n > EF and n > 4 * NCC:
+        n //= 2
+        r += 1
+    return r
 
 
 # ---------------------------------------------------------------- clocks --------------------
@@ -218,63 +251,153 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------- B200 arm ------------------
+def load_golden():
+    try:
+        return json.load(open(os.path.join(ROOT, "tests", "golden", "bench_digests.json")))
+    except (OSError, ValueError):
+        return {}
+
+
+def load_peaks():
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        return peaks, "measured (MEASURED_PEAKS.json)"
+    except (OSError, ValueError):
+        return {"hbm_gbs": 6650.0}, "fallback (B200_PROFILING.md)"
+
+
+def probe_int_pipes(local):
+    """Measured issue rates of the integer pipes on this GPU (csrc/probe.cu, ~0.1 s): T lane-ops/s, BLAKE2b G compressions/s."""
+    from zk_stark_tutor_b200 import _lib
+    out = {}
+    try:
+        pl = ctypes.CDLL(os.path.join(os.path.dirname(_lib.LIB_PATH), "libzkb200_probe.so"))
+        for kind, name in ((0, "alu"), (1, "imad"), (3, "prmt"), (40, "imad_wide"), (6, "blake2b_Gcompress_per_s")):
+            r, pm = ctypes.c_double(0), ctypes.c_double(0)
+            if pl.zkb_probe_int_pipe(local, kind, ctypes.byref(r), ctypes.byref(pm)) == 0:
+                out[name] = r.value / (1e9 if kind == 6 else 1e12)
+    except OSError:
+        pass
+    return out
+
+
+class Env:
+    """what every workload needs: ranks, the explicit stream, the library context on it, the barrier"""
+
+    def __init__(self, args):
+        import torch
+        import torch.distributed as dist
+        import zk_stark_tutor_b200 as zk
+        self.torch, self.dist, self.zk = torch, dist, zk
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py: no CUDA device - the B200 path has no CPU fallback")
+        torch.cuda.set_device(self.local)
+        if self.world > 1:
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            dist.init_process_group("nccl", device_id=torch.device("cuda", self.local))
+        self.stream = torch.cuda.Stream()        # one explicit stream: library kernels, L2 flush and timing events
+        torch.cuda.set_stream(self.stream)
+        self.ctx = zk.Context(self.local, stream=self.stream.cuda_stream)
+        self.flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")          # > 126 MB L2
+        self.golden = load_golden()
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def max_over_ranks(self, ms):
+        t = self.torch.tensor([ms], dtype=self.torch.float64, device="cuda")
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def all_ok(self, ok):
+        t = self.torch.tensor([0 if ok else 1], dtype=self.torch.int32, device="cuda")
+        if self.world > 1:
+            self.dist.all_reduce(t)
+        return int(t.item()) == 0
+
+    def close(self):
+        self.ctx.close()
+        if self.world > 1:
+            self.dist.destroy_process_group()
+
+
 def b200_arm(args):
-    import torch
-    import torch.distributed as dist
-    import zk_stark_tutor_b200 as zk
-    from zk_stark_tutor_b200 import _lib, synth
-
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device - the B200 path has no CPU fallback")
-    torch.cuda.set_device(local)
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    stream = torch.cuda.Stream()                 # one explicit stream: library kernels, L2 flush and timing events
-    torch.cuda.set_stream(stream)
-    ctx = zk.Context(local, stream=stream.cuda_stream)
-    if args.workload in ("ntt", "ntt4step"):
-        return ntt_arm(args, ctx, stream, rank, world, local, barrier)
+    env = Env(args)
+    a = (args, env.ctx, env.stream, env.rank, env.world, env.local, env.barrier)
     if args.workload == "proofs":
-        return proofs_arm(args, ctx, stream, rank, world, local, barrier)
+        return proofs_arm(*a)
     if args.workload == "signatures":
-        return signatures_arm(args, ctx, stream, rank, world, local, barrier)
-    columns_mode = args.workload == "columns"
-    if columns_mode and args.log_n == 24:
-        args.log_n = 22
-    from zk_stark_tutor_b200 import columns as colmod
+        return signatures_arm(*a)
+    if args.workload == "ntt":
+        line = ntt_record(args, env, four=False, steps=args.steps)
+    elif args.workload == "ntt4step":
+        line = ntt_record(args, env, four=True, steps=args.steps)
+    elif args.workload == "columns":
+        line = lde_commit_record(args, env, True, args.steps)
+    else:
+        line = lde_commit_record(args, env, False, args.steps)
+        if not args.no_sub_records and args.log_n == 24:
+            # BASELINE configs[3] and configs[4] in the same line: short runs (<= 3 timed steps each) with their own parity check,
+            # clocks and e2e, so that the driver's 1/2/4/8-GPU records carry the strong-scaling batch and the four-step NTT too
+            sub_steps = max(2, min(args.steps, 3))
+            sub = {"configs[3]": lde_commit_record(args, env, True, sub_steps, sub=True),
+                   "configs[4]": ntt_record(args, env, four=True, steps=sub_steps, sub=True)}
+            if env.rank == 0:
+                line["configs"] = sub
+    if env.rank == 0:
+        print(json.dumps(line), flush=True)
+    env.close()
+
+
+def lde_commit_record(args, env, columns_mode, steps, sub=False):
+    """configs[2] (one codeword per rank, weak) or configs[3] (--columns columns of 2^22 dealt round-robin, strong):
+    coset LDE + Merkle + full FRI commit per column through zkb_lde_fri_commit_ps.  Returns the JSON record (rank 0) or None."""
+    import hashlib
+    torch, zk = env.torch, env.zk
+    from zk_stark_tutor_b200 import synth, columns as colmod
+    rank, world, local, ctx, stream = env.rank, env.world, env.local, env.ctx, env.stream
+    log_n = 22 if (columns_mode and args.log_n == 24) else args.log_n
     my_cols = colmod.partition(args.columns, world, rank) if columns_mode else [rank]
-    log_n = args.log_n
     n, n_coeffs = 1 << log_n, (1 << log_n) // EF
     field = zk.Field()
     omega = field.primitive_nth_root(n)
     fri = zk.FRI(GENERATOR, omega, n, EF, NCC, ctx)
     rounds = fri.num_rounds()
     last_len = n >> (rounds - 1)
-    # one pinned host / device coefficient buffer per local column (columns mode: seeds s + col)
+    # one pinned host / device coefficient buffer per local column (seeds SEED + column)
     host_cols = [torch.from_numpy(synth.elements(SEED + c, n_coeffs).view(np.int64)).pin_memory() for c in my_cols]
     dev_cols = [h.cuda(non_blocking=True) for h in host_cols]
-    host_coeffs, dev_coeffs = host_cols[0], dev_cols[0]
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")          # > 126 MB L2
     lib = ctx.lib
 
-    def one(coeffs_ptr):
+    def one(coeffs_ptr, want_digest=False):
         ps = zk.IndependentProofStream()
         h = ctypes.c_void_p()
         ctx.check(lib.zkb_lde_fri_commit_ps(ctx.h, ctypes.byref(fri.params), coeffs_ptr, n_coeffs, ps.h, ctypes.byref(h)))
-        proof_bytes = lib.zkb_ps_digest(ps.h, None, 0)      # transcript so far: R roots + last codeword
+        out = hashlib.sha256(ps.digest()).hexdigest() if want_digest else lib.zkb_ps_digest(ps.h, None, 0)   # R roots + last codeword
         lib.zkb_fri_layers_free(h)
         ps.close()
-        return proof_bytes
+        return out
+
+    # ---- parity before timing: the proof-stream bytes of the columns the oracle digested (tests/golden/bench_digests.json,
+    # made by tools/make_bench_digests.py with the CPU oracle) must be reproduced exactly
+    gold = env.golden.get("configs3" if columns_mode else "configs2", {})
+    checked, ok = [], True
+    for k, c in enumerate(my_cols):
+        key = str(c) if columns_mode else (str(log_n) if c == 0 else None)
+        if key in gold and (not columns_mode or log_n == 22):
+            got = one(dev_cols[k].data_ptr(), want_digest=True)
+            checked.append(c)
+            if got != gold[key]:
+                ok = False
+                print("bench.py: PARITY FAILURE %s column %d: %s != golden %s" % ("configs[3]" if columns_mode else "configs[2]", c, got, gold[key]), file=sys.stderr)
+    if not env.all_ok(ok):
+        raise SystemExit("bench.py: GPU result differs from the oracle's committed digest - no number reported")
 
     pipe = None
     if columns_mode and args.lanes > 1:
@@ -287,20 +410,20 @@ def b200_arm(args):
             return pipe.run(bufs, zk.IndependentProofStream, keep_roots=False)
         return [one(b.data_ptr()) for b in bufs]
 
-    def timed(coeffs_ptr, steps, profile):
-        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
-        barrier()
+    def timed(bufs, nsteps, profile):
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(nsteps)]
+        env.barrier()
         ctxs = pipe.ctxs if pipe is not None else [ctx]
         if profile:
             for cx in ctxs:
                 cx.profile(True, reset=True)
         l0 = sum(cx.launches for cx in ctxs)
         for a, b in evs:
-            flush.fill_(1)                                   # L2 flush between steps (untimed)
+            env.flush.fill_(1)                               # L2 flush between steps (untimed)
             a.record(stream)
-            step(coeffs_ptr)                                 # host-synchronous: returns when the GPU work is done
+            step(bufs)                                       # host-synchronous: returns when the GPU work is done
             b.record(stream)
-        barrier()
+        env.barrier()
         launches = sum(cx.launches for cx in ctxs) - l0
         prof = {}
         if profile:
@@ -309,114 +432,116 @@ def b200_arm(args):
                     pm, pc = prof.get(k, (0.0, 0))
                     prof[k] = (pm + ms, pc + cnt)
                 cx.profile(False)
-        ms = sum(a.elapsed_time(b) for a, b in evs)
-        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item()), launches, prof
+        return env.max_over_ranks(sum(a.elapsed_time(b) for a, b in evs)), launches, prof
 
     for _ in range(max(args.warmup, 3)):
         step(dev_cols)
     sampler = ClockSampler(local) if rank == 0 else None
-    total_ms, launches, _ = timed(dev_cols, args.steps, False)
+    total_ms, launches, _ = timed(dev_cols, steps, False)
     clocks = sampler.stop() if sampler else None
     # per-kernel device time (CUDA events around every launch) in a separate pass: the two event records per
     # launch cost ~0.1 ms per step, which does not belong in the headline number
-    prof_steps = max(1, min(args.steps, 5))
+    prof_steps = max(1, min(steps, 5))
     _, _, prof = timed(dev_cols, prof_steps, True)
     for _ in range(2):
         step(host_cols)
-    e2e_steps = max(3, args.steps // 2)
+    e2e_steps = max(3, steps // 2)
     e2e_ms, _, _ = timed(host_cols, e2e_steps, False)
+    if pipe is not None:
+        pipe.close()
+    del dev_cols, host_cols
+    torch.cuda.empty_cache()
+    if rank != 0:
+        return None
 
-    if rank == 0:
-        ms_per_step = total_ms / args.steps
-        units = (args.columns if columns_mode else world) * n        # codeword elements processed by all ranks per step
-        value = units / (ms_per_step * 1e-3) / 1e6
-        e2e_value = units / (e2e_ms / e2e_steps * 1e-3) / 1e6
-        cols_here = len(my_cols)
-        # ---- roofline of the dominant kernel: layer-0 leaf hashing (k_leaf8<false>), one launch per step
-        peaks = {}
-        try:
-            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        except OSError:
-            pass
-        hbm_peak, peak_src = (peaks["hbm_gbs"], "measured (MEASURED_PEAKS.json)") if "hbm_gbs" in peaks else (6650.0, "fallback (B200_PROFILING.md)")
-        kern = {k: {"ms_per_step": v[0] / prof_steps, "launches_per_step": v[1] / prof_steps} for k, v in prof.items()}
-        dom = max(prof.items(), key=lambda kv: kv[1][0])[0] if prof else None
-        roof = None
-        if "k_leaf8<false>" in prof:
-            ms_l, cnt = prof["k_leaf8<false>"]
-            dur = ms_l / cnt * 1e-3
-            alg_bytes = 16 * n + 64 * (n >> 3)               # read every value once, write the level-3 nodes
-            compressions = n + (n - (n >> 3))                # n leaves + levels 1..3
-            alu_ops = compressions * 2144                    # SURVEY.md 8d canonical ALU-op count per compression
-            probe = {}
-            try:
-                pl = ctypes.CDLL(os.path.join(os.path.dirname(_lib.LIB_PATH), "libzkb200_probe.so"))
-                for kind, name in ((0, "alu"), (1, "imad"), (2, "alu+imad"), (3, "prmt"), (4, "shf"), (5, "add64_pairs"), (6, "blake2b_Gcompress_per_s")):
-                    r, pm = ctypes.c_double(0), ctypes.c_double(0)
-                    if pl.zkb_probe_int_pipe(local, kind, ctypes.byref(r), ctypes.byref(pm)) == 0:
-                        probe[name] = r.value / (1e9 if kind == 6 else 1e12)
-            except OSError:
-                pass
-            achieved = alg_bytes / dur / 1e9
-            traffic = None
-            try:
-                tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("k_leaf8<false>", {})
-                if tr.get("log_n") == log_n:
-                    traffic = tr["dram_bytes_per_launch"]
-            except (OSError, ValueError):
-                pass
-            roof = {"kernel": "k_leaf8<false> (layer-0: 8 leaf hashes + 7 nodes per thread)", "bound": "hbm",
-                    "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": traffic,
-                    "peak_source": peak_src, "algorithmic_bytes": alg_bytes, "launch_ms": dur * 1e3, "share_of_step": ms_l / prof_steps / ms_per_step,
-                    "note": "this kernel is bound by the integer ALU pipe, not HBM (ncu: sm__inst_executed_pipe_alu 94.5 % of peak, "
-                            "profiles/r01_ncu_full_leaf8_nttrr.txt); the bench contract offers hbm|tensor only, the binding view is int_pipe",
-                    "int_pipe": {"compressions_per_s": compressions / dur, "achieved_Tops": alu_ops / dur / 1e12,
-                                 "peak_Tops_measured": probe, "ops_per_compression": 2144,
-                                 "alu_pipe_instr_per_compression": 2014,
-                                 "frac_of_alu_pipe": (compressions / dur * 2014 / (probe["prmt"] * 1e12)) if probe.get("prmt") else None,
-                                 "frac_of_measured_blake2b_ceiling": (compressions / dur / (probe["blake2b_Gcompress_per_s"] * 1e9))
-                                 if probe.get("blake2b_Gcompress_per_s") else None,
-                                 "note": "ALU-pipe peak = the measured single-pipe rate (PRMT/SHF/LOP3/IADD3 all issue at 0.5 warp-instr/clk/SMSP = "
-                                         "18.6 T lane-ops/s); BLAKE2b needs 2,014 ALU-pipe instructions per compression"}}
-        line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if columns_mode else "weak", "vs_baseline": None,
-            "dtype": "u128 (prime field p = 1 + 407*2^119, 4x32-bit limb Montgomery; BLAKE2b-512 on u32 pairs)", "data": "synthetic",
-            "config": {"workload": ("configs[3]: %d trace columns x 2^%d dealt round-robin over %d GPU(s); per column: " % (args.columns, log_n, world)
-                                    if columns_mode else "configs[2]: ") +
-                                   "coset LDE (2^%d coefficients -> 2^%d codeword) + Merkle commit + full FRI commit "
-                                   "(%d roots, %d folds, last codeword %d; ef 4, 64 colinearity tests)%s"
-                                   % (log_n - 2, log_n, rounds, rounds - 1, last_len, "" if columns_mode else ", one codeword per GPU"),
-                       "log_n": log_n, "expansion_factor": EF, "num_colinearity_tests": NCC, "rounds": rounds,
-                       "l2": "flushed between steps (256 MiB write, untimed); per-step CUDA events summed; working set per step > L2",
-                       "parallelism": "independent codewords / columns per rank, no data-path collective"
-                                      + (", %d columns in flight per GPU" % args.lanes if pipe is not None else "")},
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": cols_here * n_coeffs * 16, "d2h_bytes_per_step": cols_here * (rounds * 64 + last_len * 16),
-                    "ms_per_step": e2e_ms / e2e_steps, "api": "zkb_lde_fri_commit_ps with pinned host coefficients"},
-            "gpu_launches": launches, "kernels": kern, "dominant_kernel": dom,
-            "kernels_note": "per-kernel times from %d separately profiled step(s) (events around every launch); value / ms_per_step are timed without them" % prof_steps,
-            "roofline": roof, "clocks": clocks,
-        }
-        if not args.no_cpu_baseline and world == 1:
-            t0 = time.perf_counter()
-            cl = args.cpu_log_n
-            cpu_lde_fri_commit(cl, SEED)
-            dt = time.perf_counter() - t0
-            reps = max(1, int(10.0 / max(dt, 1e-3)))
-            t0 = time.perf_counter()
-            for k in range(reps):
-                cpu_lde_fri_commit(cl, SEED + k)
-            dt = (time.perf_counter() - t0) / reps
-            line["cpu_baseline"] = {"value": (1 << cl) / dt / 1e6, "unit": UNIT, "cores": 1, "kind": "port",
-                                    "sample": "%d x (LDE + FRI commit of one 2^%d codeword), reference algorithm (bit-serial mul_mod, per-element "
-                                              "pow/xgcd, recursive Merkle) restated in C; the Rust reference cannot be built here" % (reps, cl)}
-        print(json.dumps(line), flush=True)
-    ctx.close()
-    if world > 1:
-        dist.destroy_process_group()
+    ms_per_step = total_ms / steps
+    units = (args.columns if columns_mode else world) * n        # codeword elements processed by all ranks per step
+    value = units / (ms_per_step * 1e-3) / 1e6
+    e2e_value = units / (e2e_ms / e2e_steps * 1e-3) / 1e6
+    cols_here = len(my_cols)
+    peaks, peak_src = load_peaks()
+    kern = {k: {"ms_per_step": v[0] / prof_steps, "launches_per_step": v[1] / prof_steps} for k, v in prof.items()}
+    dom = max(prof.items(), key=lambda kv: kv[1][0])[0] if prof else None
+    roof = None
+    if "k_leaf8<false>" in prof and not sub:
+        # ---- roofline of the dominant kernel: layer-0 leaf hashing (k_leaf8<false>), one launch per column.  The binding bound
+        # is the integer ALU pipe (ncu: sm__inst_executed_pipe_alu 94.6 %, profiles/), so `frac` is the ALU-pipe fraction:
+        # achieved = compressions/s x 2,014 ALU-pipe instructions (SASS count of one BLAKE2b compression) in T lane-ops/s,
+        # peak = the ALU pipe's issue rate measured on this GPU in this run (csrc/probe.cu).  The HBM view is reported beside it.
+        ms_l, cnt = prof["k_leaf8<false>"]
+        dur = ms_l / cnt * 1e-3
+        alg_bytes = 16 * n + 64 * (n >> 3)               # read every value once, write the level-3 nodes
+        compressions = n + (n - (n >> 3))                # n leaves + levels 1..3
+        probe = probe_int_pipes(local)
+        alu_peak = probe.get("prmt") or probe.get("alu")
+        achieved_alu = compressions / dur * 2014 / 1e12
+        roof = {"kernel": "k_leaf8<false> (layer 0: 8 decimal leaf hashes + 7 nodes per thread)", "bound": "int-alu-pipe",
+                "achieved": achieved_alu, "peak": alu_peak, "unit": "T lane-ops/s", "frac": (achieved_alu / alu_peak) if alu_peak else None,
+                "traffic": None,
+                "peak_source": "ALU-pipe issue rate measured live on this GPU (csrc/probe.cu: PRMT / LOP3 / IADD3 / SHF all issue at 0.5 warp-instr/clk/SMSP)",
+                "launch_ms": dur * 1e3, "share_of_step": ms_l / prof_steps / ms_per_step,
+                "compressions_per_launch": compressions, "alu_pipe_instr_per_compression": 2014, "canonical_ops_per_compression": 2144,
+                "compressions_per_s": compressions / dur,
+                "frac_of_measured_blake2b_ceiling": (compressions / dur / (probe["blake2b_Gcompress_per_s"] * 1e9)) if probe.get("blake2b_Gcompress_per_s") else None,
+                "peak_int_pipes_measured": probe,
+                "hbm": {"bound": "hbm", "achieved": alg_bytes / dur / 1e9, "peak": peaks.get("hbm_gbs"), "unit": "GB/s",
+                        "frac": alg_bytes / dur / 1e9 / peaks["hbm_gbs"] if peaks.get("hbm_gbs") else None, "peak_source": peak_src,
+                        "algorithmic_bytes": alg_bytes,
+                        "note": "not the binding bound: the kernel moves 24 B per leaf and executes 3,776 ALU-pipe instructions per leaf"},
+                "note": "traffic: not measured in this run (ncu capture: profiles/r01_ncu_full_final_leaf8_ntt_node8.txt, 413 MB DRAM for 403 MB algorithmic at 2^24)"}
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if columns_mode else "weak", "vs_baseline": None,
+        "dtype": "u128 (prime field p = 1 + 407*2^119, 4x32-bit limb Montgomery; BLAKE2b-512 on u32 pairs)", "data": "synthetic",
+        "config": codeword_config(args, log_n, rounds, last_len, columns_mode, world, args.lanes if pipe is not None else 0),
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": cols_here * n_coeffs * 16, "d2h_bytes_per_step": cols_here * (rounds * 64 + last_len * 16),
+                "ms_per_step": e2e_ms / e2e_steps, "api": "zkb_lde_fri_commit_ps with pinned host coefficients"},
+        "gpu_launches": launches, "kernels": kern, "dominant_kernel": dom,
+        "kernels_note": "per-kernel times from %d separately profiled step(s) (events around every launch); value / ms_per_step are timed without them" % prof_steps,
+        "parity": {"checked_before_timing": "sha256 of the proof-stream bytes (roots + last codeword) == tests/golden/bench_digests.json (CPU oracle)",
+                   "columns_checked_on_rank0": checked},
+        "roofline": roof, "clocks": clocks,
+    }
+    if not args.no_cpu_baseline and world == 1 and not sub:
+        line["cpu_baseline"] = cpu_baseline_record(args)
+    return line
+
+
+def codeword_config(args, log_n, rounds, last_len, columns_mode, world, lanes):
+    """the `config` object of the LDE + FRI-commit workloads; the reference arm prints the same one (its bounded sample is
+    described in cpu_baseline.sample)"""
+    return {"workload": ("configs[3]: %d trace columns x 2^%d dealt round-robin over %d GPU(s); per column: " % (args.columns, log_n, world)
+                         if columns_mode else "configs[2]: ") +
+                        "coset LDE (2^%d coefficients -> 2^%d codeword) + Merkle commit + full FRI commit "
+                        "(%d roots, %d folds, last codeword %d; ef 4, 64 colinearity tests)%s"
+                        % (log_n - 2, log_n, rounds, rounds - 1, last_len, "" if columns_mode else ", one codeword per GPU"),
+            "log_n": log_n, "expansion_factor": EF, "num_colinearity_tests": NCC, "rounds": rounds,
+            "l2": "flushed between steps (256 MiB write, untimed); per-step CUDA events summed; working set per step > L2",
+            "parallelism": "independent codewords / columns per rank, no data-path collective"
+                           + (", %d columns in flight per GPU" % lanes if lanes else "")}
+
+
+def cpu_baseline_record(args):
+    """The reference's algorithm (faithful C port: bit-serial mul_mod, per-element pow / xgcd, recursive allocating Merkle) on ONE host
+    core, on a bounded sample of the workload: whole LDE + FRI commits of one 2^cpu_log_n codeword for ~10-30 s.  BASELINE.md 3.3:
+    measured at the sample size, n log n extrapolation to the workload's size flagged as such."""
+    cl = args.cpu_log_n
+    t0 = time.perf_counter()
+    cpu_lde_fri_commit(cl, SEED)
+    dt = time.perf_counter() - t0
+    reps = max(0, int(12.0 / max(dt, 1e-3)) - 1)
+    if reps:
+        t0 = time.perf_counter()
+        for k in range(reps):
+            cpu_lde_fri_commit(cl, SEED + 1 + k)
+        dt = (time.perf_counter() - t0) / reps
+    eps = (1 << cl) / dt
+    ext = eps * cl / args.log_n                     # work per element grows with log2 n (NTT stages, tree depth, FRI rounds)
+    return {"value": eps / 1e6, "unit": UNIT, "cores": 1, "kind": "port",
+            "sample": "%d x (LDE + FRI commit of one 2^%d codeword), reference algorithm (bit-serial mul_mod, per-element pow/xgcd, recursive "
+                      "Merkle) restated in C, 1 thread; %.1f s per codeword; the Rust reference cannot be built here (no rustc)" % (max(reps, 1), cl, dt),
+            "extrapolated": {"log_n": args.log_n, "value": ext / 1e6, "seconds_per_codeword": (1 << args.log_n) / ext,
+                             "how": "FLAGGED EXTRAPOLATION, not a measurement: measured elements/s at 2^%d x (%d / %d), i.e. n log n scaling" % (cl, cl, args.log_n)}}
 
 
 def cpu_proof(seed):
@@ -721,97 +846,147 @@ def signatures_arm(args, ctx, stream, rank, world, local, barrier):
         dist.destroy_process_group()
 
 
-def ntt_arm(args, ctx, stream, rank, world, local, barrier):
-    """configs[1] (forward + inverse NTT per rank) and configs[4] (one NTT over all ranks)."""
-    import torch
-    import torch.distributed as dist
-    import zk_stark_tutor_b200 as zk
+def ntt_record(args, env, four, steps, sub=False):
+    """configs[1] (forward + inverse NTT per rank) and configs[4] (ONE NTT over all ranks: four-step, the twiddle and the exchange
+    fused into the last local pass as NVLink peer stores - csrc/ntt4.cu - with a one-element NCCL all-reduce as the barrier)."""
+    torch, dist, zk = env.torch, env.dist, env.zk
     from zk_stark_tutor_b200 import synth, ntt_4step as fs
-    four = args.workload == "ntt4step"
+    rank, world, local, ctx, stream = env.rank, env.world, env.local, env.ctx, env.stream
     log_n = 26 if (four and args.log_n == 24) else args.log_n
     n = 1 << log_n
     field = zk.Field()
     w = field.primitive_nth_root(n)
     L = n // world if four else n
-    x = torch.from_numpy(synth.elements(SEED + rank, L).view(np.int64)).cuda()
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
-    eng = fs.CudaEngine(ctx)
+    seed_ntt = 0x5EED0005
+    # four-step: the global input is stream 0x5EED0005 whatever the number of ranks; rank r owns the cyclic slice x[r + world*m]
+    hx = torch.from_numpy((synth.elements(seed_ntt, L, start=rank, step=world) if four else synth.elements(SEED + rank, L)).view(np.int64)).pin_memory()
+    x = hx.cuda()
+    out = torch.empty_like(x)
+    hout = torch.empty_like(hx).pin_memory() if four else None
+    plan = None
+    if four:
+        plan = fs.Ntt4Plan(ctx, rank, world, L)
+        plan.connect_group()
 
-    def step():
+    def step(src=None):
         if four:
-            return fs.ntt_4step(eng, w, x, rank, world)
+            if src is not None:                              # e2e: pinned host slice in, transformed slice back to pinned host memory
+                x.copy_(src, non_blocking=True)
+            fs.ntt_4step_fused(plan, w, x, out)
+            if src is not None:
+                hout.copy_(out, non_blocking=True)
+                stream.synchronize()
+            return out
         return zk.intt(w, zk.ntt(w, x, ctx), ctx)
 
+    parity = None
+    if four:
+        # ---- parity before timing: position-weighted checksums of the whole transform against the CPU oracle's (bench_digests.json)
+        step()
+        gold = env.golden.get("configs4", {}).get(str(log_n))
+        blk = L // world
+        k = (torch.arange(blk, device="cuda", dtype=torch.int64) + rank * blk)[None, :] + L * torch.arange(world, device="cuda", dtype=torch.int64)[:, None] + 1
+        o = out.view(world, blk, 2)
+        sums = torch.stack([o[..., 0].sum(), o[..., 1].sum(), (o[..., 0] * k).sum(), (o[..., 1] * k).sum()])
+        if world > 1:
+            dist.all_reduce(sums)
+        got = [int(v) & ((1 << 64) - 1) for v in sums.tolist()]
+        if gold:
+            want = [gold["sum_lo"], gold["sum_hi"], gold["wsum_lo"], gold["wsum_hi"]]
+            if got != want:
+                raise SystemExit("bench.py: PARITY FAILURE configs[4]: checksums %s != oracle %s - no number reported" % (got, want))
+            parity = {"checked_before_timing": "sum and position-weighted sum (mod 2^64) of both 64-bit halves over all 2^%d outputs == the CPU oracle's "
+                                               "(tests/golden/bench_digests.json)" % log_n, "checksums": got}
+        else:
+            parity = {"checked_before_timing": None, "note": "no oracle digest committed for 2^%d" % log_n, "checksums": got}
     for _ in range(max(args.warmup, 3)):
         step()
-    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    barrier()
-    ctx.profile(True, reset=True)
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    sampler = ClockSampler(local) if rank == 0 else None
+    env.barrier()
     l0 = ctx.launches
     for a, b in evs:
-        flush.fill_(1)
+        env.flush.fill_(1)
         a.record(stream)
         step()
         b.record(stream)
-    barrier()
+    env.barrier()
+    clocks = sampler.stop() if sampler else None
     launches = ctx.launches - l0
+    total_ms = env.max_over_ranks(sum(a.elapsed_time(b) for a, b in evs))
+    # per-kernel times in a separate profiled pass
+    ctx.profile(True, reset=True)
+    for _ in range(steps):
+        step()
     prof = ctx.profile_read()
     ctx.profile(False)
-    ms = sum(a.elapsed_time(b) for a, b in evs)
-    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    if rank == 0:
-        ms_per_step = float(t.item()) / args.steps
-        units = n if four else 2 * n * world                       # elements transformed per step
-        log_l = (L.bit_length() - 1)
-        muls = (L // 2) * log_l * (world if four else 2 * world) + (n if not four else 0)
-        peaks = {}
-        try:
-            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        except OSError:
-            pass
-        hbm_peak = peaks.get("hbm_gbs", 6650.0)
-        kms, kcnt = prof.get("k_ntt_pass", (0.0, 1))
-        alg_bytes = 32 * L                                          # one pass: every element read once, written once
-        achieved = alg_bytes / (kms / max(kcnt, 1) * 1e-3) / 1e9 if kms else None
-        # integer-pipe view (SURVEY.md 8d: 20 IMAD per field multiplication): measured IMAD / IMAD.WIDE issue rates
-        int_pipe = {"field_mul_per_s": muls / (ms_per_step * 1e-3), "imad_per_field_mul": 20}
-        try:
-            from zk_stark_tutor_b200 import _lib as _zl
-            pl = ctypes.CDLL(os.path.join(os.path.dirname(_zl.LIB_PATH), "libzkb200_probe.so"))
-            for kind, name in ((1, "imad_Tops_measured"), (40, "imad_wide_Tops_measured")):
-                r, pm_ = ctypes.c_double(0), ctypes.c_double(0)
-                if pl.zkb_probe_int_pipe(local, kind, ctypes.byref(r), ctypes.byref(pm_)) == 0:
-                    int_pipe[name] = r.value / 1e12
-            if int_pipe.get("imad_wide_Tops_measured"):
-                # the multiplication as built: 16 limb products + 4 reduction products + 1 low product, all 32x32->64 (IMAD.WIDE)
-                peak_mul = int_pipe["imad_wide_Tops_measured"] * 1e12 / 21
-                int_pipe["field_mul_per_s_at_imad_wide_peak"] = peak_mul
-                int_pipe["frac_of_imad_wide_roofline"] = int_pipe["field_mul_per_s"] / peak_mul
-                int_pipe["note"] = ("algorithmic multiplications ((N/2) log2 N per transform, + N for the inverse scaling) against the measured "
-                                    "IMAD.WIDE issue rate / 21; the pass executes ~1.25x the algorithmic count (inter-pass twiddles)")
-        except OSError:
-            pass
-        line = {
-            "metric": "NTT throughput, elements/s" + (" (one 2^%d NTT over %d GPUs, four-step + NCCL all-to-all)" % (log_n, world) if four
-                                                       else " (forward + inverse NTT of 2^%d per GPU)" % log_n),
-            "value": units / (ms_per_step * 1e-3) / 1e6, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if four else "weak", "vs_baseline": None,
-            "dtype": "u128 (prime field, 4x32-bit limb Montgomery)", "data": "synthetic",
-            "config": {"workload": ("configs[4]: one 2^%d-element NTT split over %d GPU(s): local 2^%d NTT, twiddle, NCCL all-to-all, %d-point cross-GPU NTT"
-                                    % (log_n, world, log_l, world)) if four else "configs[1]: forward + inverse NTT of 2^%d elements" % log_n,
-                       "log_n": log_n, "l2": "flushed between steps (256 MiB write, untimed)"},
-            "field_mul_per_s": muls / (ms_per_step * 1e-3), "int_pipe": int_pipe,
-            "gpu_launches": launches, "kernels": {k: {"ms_per_step": v[0] / args.steps, "launches_per_step": v[1] / args.steps} for k, v in prof.items()},
-            "roofline": {"kernel": "k_ntt_pass / k_ntt_rr (one HBM pass of the NTT)", "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                         "frac": (achieved / hbm_peak) if achieved else None, "traffic": None,
-                         "note": "per pass: 32 B per element algorithmic; the pass is integer-pipe bound (DESIGN.md 4)"},
-        }
-        print(json.dumps(line), flush=True)
-    ctx.close()
-    if world > 1:
-        dist.destroy_process_group()
+    e2e = None
+    if four:
+        step(hx)
+        evs2 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        env.barrier()
+        for a, b in evs2:
+            env.flush.fill_(1)
+            a.record(stream)
+            step(hx)
+            b.record(stream)
+        env.barrier()
+        e2e_ms = env.max_over_ranks(sum(a.elapsed_time(b) for a, b in evs2)) / steps
+        e2e = {"value": n / (e2e_ms * 1e-3) / 1e6, "unit": UNIT, "h2d_bytes_per_step": L * 16, "d2h_bytes_per_step": L * 16, "ms_per_step": e2e_ms,
+               "api": "zkb_ntt4_scatter / zkb_ntt4_finish: pinned host slice in (H2D), transformed slice out (D2H), per rank, inside the timed region"}
+    if plan is not None:
+        env.barrier()
+        plan.close()
+    del x, out, hx, hout
+    torch.cuda.empty_cache()
+    if rank != 0:
+        return None
+    ms_per_step = total_ms / steps
+    units = n if four else 2 * n * world                       # elements transformed per step
+    log_l = (L.bit_length() - 1)
+    muls = (L // 2) * log_l * (world if four else 2 * world) + (n if not four else 0)
+    peaks, peak_src = load_peaks()
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    kms, kcnt = prof.get("k_ntt_pass", (0.0, 1))
+    alg_bytes = 32 * L                                          # one pass: every element read once, written once
+    achieved = alg_bytes / (kms / max(kcnt, 1) * 1e-3) / 1e9 if kms else None
+    # integer-pipe view (SURVEY.md 8d: 20 IMAD per field multiplication): measured IMAD / IMAD.WIDE issue rates
+    int_pipe = {"field_mul_per_s": muls / (ms_per_step * 1e-3), "imad_per_field_mul": 20}
+    probe = probe_int_pipes(local) if not sub else {}
+    if probe.get("imad_wide"):
+        # the multiplication as built: 16 limb products + 4 reduction products + 1 low product, all 32x32->64 (IMAD.WIDE)
+        peak_mul = probe["imad_wide"] * 1e12 / 21
+        int_pipe.update({"imad_Tops_measured": probe.get("imad"), "imad_wide_Tops_measured": probe["imad_wide"],
+                         "field_mul_per_s_at_imad_wide_peak": peak_mul, "frac_of_imad_wide_roofline": int_pipe["field_mul_per_s"] / peak_mul,
+                         "note": "algorithmic multiplications ((N/2) log2 N per transform, + N for the inverse scaling) against the measured "
+                                 "IMAD.WIDE issue rate / 21; the pass executes ~1.25x the algorithmic count (inter-pass twiddles)"})
+    line = {
+        "metric": "NTT throughput, elements/s" + (" (one 2^%d NTT over %d GPUs, four-step, exchange fused into the last local pass)" % (log_n, world) if four
+                                                   else " (forward + inverse NTT of 2^%d per GPU)" % log_n),
+        "value": units / (ms_per_step * 1e-3) / 1e6, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if four else "weak", "vs_baseline": None,
+        "dtype": "u128 (prime field, 4x32-bit limb Montgomery)", "data": "synthetic",
+        "config": {"workload": ("configs[4]: one 2^%d-element NTT split over %d GPU(s): local 2^%d NTT whose last pass applies w^(r*k2) and stores straight into "
+                                "the receiving GPU's HBM (NVLink peer stores, CUDA IPC), one-element NCCL all-reduce as barrier, %d-point cross-GPU NTT"
+                                % (log_n, world, log_l, world)) if four else "configs[1]: forward + inverse NTT of 2^%d elements" % log_n,
+                   "log_n": log_n, "l2": "flushed between steps (256 MiB write, untimed)"},
+        "field_mul_per_s": muls / (ms_per_step * 1e-3), "int_pipe": int_pipe,
+        "gpu_launches": launches, "kernels": {k: {"ms_per_step": v[0] / steps, "launches_per_step": v[1] / steps} for k, v in prof.items()},
+        "roofline": {"kernel": "k_ntt_rr (one HBM pass of the NTT)", "bound": "int-fma-heavy-pipe" if int_pipe.get("frac_of_imad_wide_roofline") else "hbm",
+                     "achieved": int_pipe.get("field_mul_per_s") if int_pipe.get("frac_of_imad_wide_roofline") else achieved,
+                     "peak": int_pipe.get("field_mul_per_s_at_imad_wide_peak") if int_pipe.get("frac_of_imad_wide_roofline") else hbm_peak,
+                     "unit": "field-mul/s" if int_pipe.get("frac_of_imad_wide_roofline") else "GB/s",
+                     "frac": int_pipe.get("frac_of_imad_wide_roofline") or ((achieved / hbm_peak) if achieved else None), "traffic": None,
+                     "hbm": {"achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": (achieved / hbm_peak) if achieved else None, "peak_source": peak_src,
+                             "note": "per pass: 32 B per element algorithmic"},
+                     "note": "the passes are bound by the FMA-heavy pipe (IMAD.WIDE), DESIGN.md 4"},
+        "clocks": clocks,
+    }
+    if e2e:
+        line["e2e"] = e2e
+    if parity:
+        line["parity"] = parity
+    return line
 
 
 def main():

@@ -41,6 +41,9 @@ class ColumnPipeline:
         self.ctxs = [zk.Context(device, stream="own") for _ in range(lanes)]
         for c in self.ctxs:      # with several lanes the copy engines overlap a staged H2D with the other lanes' kernels
             c.check(c.lib.zkb_ctx_zero_copy_inputs(c.h, 0))
+            # ... and the lanes hide each other's latency: per-round launches (device Fiat-Shamir, no host hop) instead of the
+            # 128-SM persistent tail kernel (64 x 2^22 columns, 4 lanes, one B200: 166 ms with the persistent tail, 159 ms with host hops)
+            c.check(c.lib.zkb_ctx_tail_threads(c.h, 0))
         offset, omega, n, ef, ncc = fri_params
         self.fris = [zk.FRI(offset, omega, n, ef, ncc, c) for c in self.ctxs]
 

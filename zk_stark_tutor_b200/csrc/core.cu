@@ -216,6 +216,7 @@ int zkb_ctx_create(int device, void* stream, zkb_ctx** out) {
     if (cudaMallocHost(&c->pinned, c->pinned_bytes) != cudaSuccess) { delete c; return ZKB_ERR_CUDA; }
     memset(c->pinned, 0, c->pinned_bytes);          // the root handshake reads a sequence flag from this buffer
     if (ntt_device_init(c) != 0 || merkle_device_init(c) != 0 || fri_tail_device_init(c) != 0) { zkb_ctx_destroy(c); return ZKB_ERR_CUDA; }
+    if (const char* e = getenv("ZKB_TAIL_THREADS")) { int t = atoi(e); if (t == 0 || t == 128 || t == 256 || t == 512) c->tail_threads = (uint32_t)t; }
     *out = c;
     return 0;
 }
@@ -250,6 +251,12 @@ uint64_t zkb_ctx_launches(const zkb_ctx* c) { return c ? c->launches : 0; }
 int zkb_ctx_assembly_threads(zkb_ctx* c, int threads) {
     if (!c || threads < 1) return ZKB_ERR_ARG;
     c->assembly_threads = (size_t)threads;
+    return 0;
+}
+
+int zkb_ctx_tail_threads(zkb_ctx* c, int threads) {
+    if (!c || (threads != 0 && threads != 128 && threads != 256 && threads != 512)) return ZKB_ERR_ARG;
+    c->tail_threads = (uint32_t)threads;
     return 0;
 }
 

@@ -54,6 +54,7 @@ struct zkb_ctx {
     size_t assembly_threads = 16;    // host threads per batched call for proof-stream assembly (zkb_ctx_assembly_threads)
     bool zero_copy_inputs = true;    // pinned host LDE inputs are read in place by the first NTT pass (zkb_ctx_zero_copy_inputs)
     uint32_t* tree_bars = nullptr;   // k_tree's arrival counter (device; zero between launches)
+    uint32_t tail_threads = 512;     // threads per CTA of the persistent FRI tail kernel (zkb_ctx_tail_threads)
     void* fs_dev = nullptr;          // device Fiat-Shamir contexts (keccak.cuh FsDev x fs_dev_count) + the tail kernel's barrier word
     size_t fs_dev_count = 0;
     uint32_t root_seq = 0;   // sequence number of the last root signalled through pinned memory

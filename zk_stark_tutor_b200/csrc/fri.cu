@@ -285,7 +285,10 @@ static int fri_commit_device_fs(zkb_ctx* c, zkb_fri_layers* L, const fe& omega_i
     // rounds handled by the throughput kernels (k_leaf8 / k_node8 / k_tree): every layer above the tail's limit
     uint64_t r0 = 0;
     fe omega_inv_r = omega_inv0;
-    while (r0 < rounds && !(L->layout[r0].top == 0 && L->layout[r0].log_n <= ZKB_TAIL_MAX_LOG)) {
+    // (c->tail_threads == 0: no persistent tail at all - every round runs as its own small launches, still without host hops;
+    // for callers that keep several contexts busy on one GPU, where the other lanes hide the latency and a 128-SM cooperative
+    // kernel would only get in their way)
+    while (r0 < rounds && (c->tail_threads == 0 || !(L->layout[r0].top == 0 && L->layout[r0].log_n <= ZKB_TAIL_MAX_LOG))) {
         const uint64_t r = r0;
         FsHook hook;
         hook.fs = fs; hook.round = (uint32_t)r; hook.want_alpha = r + 1 < rounds;

@@ -78,7 +78,7 @@ __global__ void __launch_bounds__(ZKB_TAIL_THREADS, 1) k_fri_tail(TailArgs a) {
             const fe* src = k == 0 ? a.cw_in : a.cw[k - 1];
             fe* dst = a.cw[k];
             const fe kk = s_kk;
-            for (uint32_t j = tid; j < chunk; j += ZKB_TAIL_THREADS) {
+            for (uint32_t j = tid; j < chunk; j += blockDim.x) {
                 const uint32_t i = cta * chunk + j;
                 fe v;
                 if (plain) {
@@ -128,11 +128,11 @@ __global__ void __launch_bounds__(ZKB_TAIL_THREADS, 1) k_fri_tail(TailArgs a) {
         if (a.host_out) {
             const uint64_t* r = reinterpret_cast<const uint64_t*>(a.fs->roots);
             uint64_t* o = reinterpret_cast<uint64_t*>(a.host_out);
-            for (uint32_t i = tid; i < a.total_rounds * 8; i += ZKB_TAIL_THREADS) o[i] = __ldcg(r + i);
+            for (uint32_t i = tid; i < a.total_rounds * 8; i += blockDim.x) o[i] = __ldcg(r + i);
             const uint32_t last_n = 1u << (a.log_n0 - (a.n_rounds - 1));
             const uint4* lc = reinterpret_cast<const uint4*>(a.n_rounds == 1 && a.first_is_plain ? a.cw_in : a.cw[a.n_rounds - 1]);
             uint4* lo = reinterpret_cast<uint4*>(a.host_out + ZKB_TAIL_HOST_CW_OFF);
-            for (uint32_t i = tid; i < last_n; i += ZKB_TAIL_THREADS) lo[i] = __ldcg(lc + i);
+            for (uint32_t i = tid; i < last_n; i += blockDim.x) lo[i] = __ldcg(lc + i);
             __threadfence_system();
             __syncthreads();
             if (tid == 0 && !s_dead) { __threadfence_system(); *a.host_flag = a.seq; }
@@ -170,7 +170,10 @@ int fri_tail_launch(zkb_ctx* c, const TailArgs& a) {
     ZKB_CUDA(c, cudaMemsetAsync(args.bar, 0, sizeof(uint32_t), c->stream));     // arrive counter of the grid barrier
     {
         LaunchScope ls(c, K_FRI_TAIL);
-        ZKB_CUDA(c, cudaLaunchCooperativeKernel((const void*)k_fri_tail, dim3(ZKB_TAIL_CTAS), dim3(ZKB_TAIL_THREADS), params, tail_smem_bytes(), c->stream));
+        // 512 threads per CTA = the whole register file of 128 SMs for the duration of the (latency-bound) tail: right for one
+        // codeword at a time; a context that shares its GPU with other contexts' kernels (column / proof pipelines) asks for 256
+        // (zkb_ctx_tail_threads), which leaves half of every SM to the other lanes' throughput kernels
+        ZKB_CUDA(c, cudaLaunchCooperativeKernel((const void*)k_fri_tail, dim3(ZKB_TAIL_CTAS), dim3(c->tail_threads), params, tail_smem_bytes(), c->stream));
     }
     if (debug) {
         unsigned long long h[ZKB_TAIL_MAX_ROUNDS * 8];

@@ -13,8 +13,9 @@ def _splitmix64(seed, idx):
         return z ^ (z >> np.uint64(31))
 
 
-def elements(seed, n, start=0):
-    j = np.arange(start, start + n, dtype=np.uint64)
+def elements(seed, n, start=0, step=1):
+    """n elements j = start, start + step, ... of stream `seed` (a strided slice of the stream: a rank's cyclic share)"""
+    j = np.uint64(start) + np.arange(n, dtype=np.uint64) * np.uint64(step)
     hi = _splitmix64(seed, j * np.uint64(2))
     lo = _splitmix64(seed, j * np.uint64(2) + np.uint64(1))
     p_hi, p_lo = np.uint64(P >> 64), np.uint64(P & ((1 << 64) - 1))
