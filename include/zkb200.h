@@ -69,6 +69,9 @@ int zkb_ctx_zero_copy_inputs(zkb_ctx* ctx, int enable);
  * `threads` host threads per call (default 16).  A caller that keeps several batches in flight on its own threads should lower it
  * (8 batches in flight on a 16-core host: 1-4 threads beat 16 by 16 %). */
 int zkb_ctx_assembly_threads(zkb_ctx* ctx, int threads);
+/* enable != 0: the batched entry points wait for the GPU by polling with short sleeps instead of cudaStreamSynchronize's
+ * spinning - for callers that keep more contexts in flight than they have idle cores. */
+int zkb_ctx_blocking_sync(zkb_ctx* ctx, int enable);
 /* Threads per CTA (128, 256 or 512; default 512) of the persistent kernel that runs the small layers of FRI::commit (csrc/fri_tail.cu).
  * 512 takes the whole register file of 128 SMs while that latency-bound kernel runs - best for one codeword at a time.  A caller that
  * keeps several contexts busy on one GPU (column pipelines) sets 0: no persistent kernel, every round as its own small launches (the

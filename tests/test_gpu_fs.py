@@ -147,3 +147,51 @@ def test_device_fs_back_to_back_calls(ctx):
         fastfri.commit(OFRI(F.GENERATOR, w, n, 4, 64), cw, ops)
         zk.FRI(F.GENERATOR, w, n, 4, 64, ctx).commit(cuda(cw), ps).close()
         assert ps.digest() == ops.digest()
+
+
+@pytest.mark.parametrize("log_n,ncc,B", [(12, 64, 5), (10, 16, 3), (13, 8, 2), (17, 4, 2)])
+def test_batch_device_assembly_equals_host_assembly(ctx, log_n, ncc, B):
+    """zkb_fri_prove_batch / zkb_merkle_build_batch / zkb_merkle_open_ps_batch: device Fiat-Shamir + objects framed by the kernels
+    (k_open_wire, k_leafs_wire) == the round-1 path (host hop per round, host threads frame every node; ZKB_HOST_ASSEMBLY=1) ==
+    the single-instance calls, byte for byte, for several tree depths (ragged record alignments)."""
+    import torch
+    n = 1 << log_n
+    w = F.primitive_nth_root(n)
+    fri = zk.FRI(F.GENERATOR, w, n, 4, ncc, ctx)
+    cws = np.stack([C.coset_lde(w, n, F.GENERATOR, C.synth(4242 + b, n // 4)) for b in range(B)])
+    d = cuda(cws.reshape(-1, 2))
+    k = 2 * ncc
+    rng = np.random.RandomState(log_n)
+    open_idx = np.ascontiguousarray(rng.randint(0, n, size=(B, k)).astype(np.uint64))
+
+    def run_batch():
+        streams = [zk.SignatureProofStream(b"doc %d" % b) for b in range(B)]
+        handles = (ctypes.c_void_p * B)(*[s.h.value for s in streams])
+        trees = (ctypes.c_void_p * B)()
+        ctx.check(ctx.lib.zkb_merkle_build_batch(ctx.h, d.data_ptr(), n, n, B, trees, handles))
+        top = np.empty((B, ncc), dtype=np.uint64)
+        ctx.check(ctx.lib.zkb_fri_prove_batch(ctx.h, ctypes.byref(fri.params), d.data_ptr(), n, n, B, handles,
+                                              top.ctypes.data_as(ctypes.POINTER(ctypes.c_uint64))))
+        ctx.check(ctx.lib.zkb_merkle_open_ps_batch(trees, B, open_idx.ctypes.data_as(ctypes.POINTER(ctypes.c_uint64)), k, handles))
+        for i in range(B - 1, -1, -1):
+            ctx.lib.zkb_merkle_free(trees[i])
+        return top.tolist(), [s.digest() for s in streams]
+
+    dev = run_batch()
+    os.environ["ZKB_HOST_ASSEMBLY"] = "1"
+    try:
+        hst = run_batch()
+    finally:
+        os.environ.pop("ZKB_HOST_ASSEMBLY", None)
+    assert dev[0] == hst[0]
+    assert dev[1] == hst[1]
+    # and against the single-instance entry points
+    for b in range(B):
+        ps = zk.SignatureProofStream(b"doc %d" % b)
+        tree = zk.MerkleTree(cuda(cws[b]), ctx)
+        ps.push((PS.ROOT, tree.root()))
+        top = fri.prove(cuda(cws[b]), ps)
+        ctx.check(ctx.lib.zkb_merkle_open_ps(tree.h, open_idx[b].ctypes.data_as(ctypes.POINTER(ctypes.c_uint64)), k, ps.h))
+        assert top == dev[0][b]
+        assert ps.digest() == dev[1][b], b
+        tree.close()

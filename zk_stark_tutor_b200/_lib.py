@@ -54,6 +54,7 @@ PROTOTYPES = {
     "zkb_ctx_zero_copy_inputs": (ctypes.c_int, [vp, ctypes.c_int]),
     "zkb_ctx_assembly_threads": (ctypes.c_int, [vp, ctypes.c_int]),
     "zkb_ctx_tail_threads": (ctypes.c_int, [vp, ctypes.c_int]),
+    "zkb_ctx_blocking_sync": (ctypes.c_int, [vp, ctypes.c_int]),
     "zkb_ctx_profile": (ctypes.c_int, [vp, ctypes.c_int]),
     "zkb_ctx_profile_read": (ctypes.c_int, [vp, ctypes.c_int, ctypes.POINTER(ctypes.c_double), c_u64p]),
     "zkb_kernel_name": (ctypes.c_char_p, [ctypes.c_int]),

@@ -81,7 +81,7 @@ static int air_check_flag(zkb_air* a, const char* what) {
     uint32_t flag = 0;
     uint32_t* d_flag = (uint32_t*)((uint8_t*)a->tables + a->o_flag);
     ZKB_CUDA(c, cudaMemcpyAsync(&flag, d_flag, 4, cudaMemcpyDeviceToHost, c->stream));
-    ZKB_CUDA(c, cudaStreamSynchronize(c->stream));
+    ZKB_CUDA(c, ctx_stream_sync(c));
     if (flag) {
         cudaMemsetAsync(d_flag, 0, 4, c->stream);
         return set_err(c, ZKB_ERR_DIV_ZERO, "%s vanishes on the FRI domain (divide by zero)", what);
@@ -199,7 +199,7 @@ int zkb_air_set_interpolants(zkb_air* a, size_t batch, const void* interpolants,
     o.has_scale = true;
     o.scale_base = a->offset;
     ZKB_TRY(ntt_exec(c, a->omega, (const fe*)d_in, interp_len, interp_len, a->ib, a->n, cols, ilog2_u64(a->n), o));
-    if (in.p) ZKB_CUDA(c, cudaStreamSynchronize(c->stream));        // the caller's host buffer has been consumed
+    if (in.p) ZKB_CUDA(c, ctx_stream_sync(c));        // the caller's host buffer has been consumed
     return 0;
 }
 
@@ -259,7 +259,7 @@ int zkb_air_combine(zkb_air* a, size_t batch, const uint8_t* weights, const void
         k_air_combine<<<dim3((unsigned)((a->n + 127) / 128), (unsigned)batch), 128, 0, c->stream>>>(l);
     }
     ZKB_CUDA(c, cudaGetLastError());
-    ZKB_CUDA(c, cudaStreamSynchronize(c->stream));           // `weights` is the caller's (pageable) host memory
+    ZKB_CUDA(c, ctx_stream_sync(c));           // `weights` is the caller's (pageable) host memory
     return 0;
 }
 

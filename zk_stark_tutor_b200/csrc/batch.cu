@@ -19,6 +19,8 @@
 #include <vector>
 #include "merkle.cuh"
 #include "hosthash.hpp"
+#include "keccak.cuh"
+#include "fri_tail.cuh"
 
 namespace zkb {
 
@@ -137,9 +139,52 @@ int zkb_fri_prove_batch(zkb_ctx* c, const zkb_fri_params* p, const void* codewor
     { fe io = h_inv(offset); for (uint64_t r = 0; r < R; r++) { inv_offset[r] = io; io = h_mul(io, io); } }
 
     // ---- commit phase (fri.rs:115-172), all instances in lockstep
+    const bool host_path = getenv("ZKB_HOST_ASSEMBLY") != nullptr;     // the round-1 path: host Fiat-Shamir hop per round, host object framing
     std::vector<uint8_t> roots(batch * 64);
     std::vector<fe> alpha(batch, fe_zero()), kk(batch);
     fe omega_inv_r = omega_inv0;
+    const bool dev_fs = !host_path && R <= ZKB_FS_MAX_ROUNDS;
+    if (dev_fs) {
+        // device Fiat-Shamir: one sponge per instance (FsDev[b]); the tree kernel of round r appends Root, draws alpha and leaves
+        // alpha / offset_r for the fold of round r + 1 - no copy, no synchronisation and no host hashing between the rounds
+        ZKB_TRY(ensure_fs_dev(c, batch));
+        FsDev* fs = (FsDev*)c->fs_dev;
+        const size_t head = offsetof(FsDev, inv_off_m2) + R * sizeof(fe);
+        uint8_t* stage = nullptr;
+        ZKB_TRY(host_scratch_reserve(c, 0, batch * head, &stage));
+        const fe r2 = ZKB_FE_R2;
+        std::vector<fe> inv_m2(R);
+        for (uint64_t r = 0; r < R; r++) inv_m2[r] = fe_montmul(fe_to_mont(inv_offset[r]), r2);
+        parallel_for(batch, c->assembly_threads, [&](size_t b) {
+            FsDev* h = (FsDev*)(stage + b * head);                       // only the first `head` bytes of each FsDev are staged
+            ps_export_sponge(ps[b], &h->sp);
+            h->kk_m = fe_zero(); h->alpha = fe_zero();
+            memcpy(h->inv_off_m2, inv_m2.data(), R * sizeof(fe));
+        });
+        ZKB_CUDA(c, cudaMemcpy2DAsync(fs, sizeof(FsDev), stage, head, head, batch, cudaMemcpyHostToDevice, c->stream));
+        for (uint64_t r = 0; r < R; r++) {
+            BatchArgs ba;
+            ba.batch = (uint32_t)batch; ba.nodes_stride = inst_bytes;
+            FsHook hook;
+            hook.fs = fs; hook.round = (uint32_t)r; hook.want_alpha = r + 1 < R;
+            if (r == 0) {
+                ba.vals_stride = stride;
+                ZKB_TRY(merkle_build_levels_batch(c, (const fe*)codewords, nullptr, len[0], lay[0], A + node_off[0], ba, &hook));
+            } else {
+                FoldArgs f;
+                f.cw = cw_ptr(r - 1); f.next = (fe*)(A + cw_off[r]); f.half = len[r];
+                f.winv = winv_tab; f.exp_mul = 1ull << (r - 1);
+                f.kk_m = fe_zero();
+                f.kk_dev = (const uint8_t*)&fs->kk_m; f.kk_stride = sizeof(FsDev);
+                f.wr_inv_m = fe_to_mont(omega_inv_r);
+                ba.vals_stride = cw_stride(r - 1); ba.next_stride = inst_bytes / sizeof(fe);
+                ZKB_TRY(merkle_build_levels_batch(c, nullptr, &f, len[r], lay[r], A + node_off[r], ba, &hook));
+                omega_inv_r = h_mul(omega_inv_r, omega_inv_r);
+            }
+        }
+        roots.resize(batch * R * 64);
+        ZKB_CUDA(c, cudaMemcpy2DAsync(roots.data(), R * 64, fs->roots, sizeof(FsDev), R * 64, batch, cudaMemcpyDeviceToHost, c->stream));
+    } else {
     for (uint64_t r = 0; r < R; r++) {
         BatchArgs ba;
         ba.batch = (uint32_t)batch; ba.nodes_stride = inst_bytes;
@@ -170,15 +215,18 @@ int zkb_fri_prove_batch(zkb_ctx* c, const zkb_fri_params* p, const void* codewor
             }
         }
     }
+    }
     // ---- last codewords (fri.rs:166), top-level indices (fri.rs:223-228)
     const uint64_t last_len = len[R - 1];
     std::vector<uint8_t> last(batch * last_len * 16);
     ZKB_CUDA(c, cudaMemcpy2DAsync(last.data(), last_len * 16, cw_ptr(R - 1), cw_stride(R - 1) * sizeof(fe), last_len * 16, batch,
                                   cudaMemcpyDeviceToHost, c->stream));
-    ZKB_CUDA(c, cudaStreamSynchronize(c->stream));
+    ZKB_CUDA(c, ctx_stream_sync(c));
     std::vector<uint64_t> idx(batch * ncc);
     int bad = 0;
     for (size_t b = 0; b < batch; b++) {
+        if (dev_fs)
+            for (uint64_t r = 0; r < R; r++) zkb_ps_push_root(ps[b], roots.data() + (b * R + r) * 64, 64);      // fri.rs:136-137, in round order
         zkb_ps_push_codeword(ps[b], last.data() + b * last_len * 16, last_len);
         uint8_t seed[32];
         zkb_ps_fiat_shamir(ps[b], 32, seed);
@@ -186,7 +234,62 @@ int zkb_fri_prove_batch(zkb_ctx* c, const zkb_fri_params* p, const void* codewor
         for (uint64_t s = 0; s < ncc; s++) idx[b * ncc + s] = top_indices_out[b * ncc + s];
     }
     if (bad) return set_err(c, ZKB_ERR_ARG, "sample_indices failed");
-    // ---- query phase (fri.rs:174-208, 234-246): per layer pair one gather + two opening launches for all instances
+    // ---- query phase (fri.rs:174-208, 234-246)
+    bool wire = !host_path;
+    for (uint64_t r = 0; r < R; r++) if (lay[r].log_n < 1 || lay[r].log_n > 17) wire = false;
+    if (wire) {
+        // The device writes the finished objects: per instance ONE contiguous segment [round 0: ncc Leafs, ncc x (Path a, Path b, Path c)]
+        // [round 1: ...] ... in wire format (k_leafs_wire, k_open_wire), one D2H for the whole batch, one append per proof stream.
+        std::vector<uint64_t> base(R, 0);
+        uint64_t seg = 0;
+        for (uint64_t r = 0; r + 1 < R; r++) {
+            base[r] = seg;
+            seg += ncc * 57 + ncc * (2 * (9 + 72ull * lay[r].log_n) + (9 + 72ull * lay[r + 1].log_n));
+        }
+        const uint64_t seg_pad = (seg + 15) & ~15ull;
+        // indices of every round, computed up front (fri.rs:234-237): per round [ab: batch x 2 ncc][c: batch x ncc]
+        const size_t per_round = batch * ncc * 3;
+        std::vector<uint64_t> hidx((R - 1) * per_round + batch);
+        for (uint64_t r = 0; r + 1 < R; r++) {
+            const uint64_t half = len[r] / 2;
+            for (auto& i : idx) i %= half;
+            uint64_t* ab = hidx.data() + r * per_round;
+            uint64_t* cc = ab + 2 * batch * ncc;
+            for (size_t q = 0; q < batch * ncc; q++) { ab[2 * q] = idx[q]; ab[2 * q + 1] = idx[q] + half; cc[q] = idx[q]; }
+        }
+        uint64_t* yoff = hidx.data() + (R - 1) * per_round;
+        for (size_t bi = 0; bi < batch; bi++) yoff[bi] = bi * seg_pad;
+        DevBuf q;
+        const size_t idx_bytes = (hidx.size() * 8 + 255) & ~(size_t)255;
+        ZKB_TRY(q.alloc(c, idx_bytes + batch * seg_pad));
+        uint64_t* d_idx = (uint64_t*)q.p;
+        uint8_t* d_wire = (uint8_t*)q.p + idx_bytes;
+        const uint64_t* d_yoff = d_idx + (R - 1) * per_round;
+        ZKB_CUDA(c, cudaMemcpyAsync(d_idx, hidx.data(), hidx.size() * 8, cudaMemcpyHostToDevice, c->stream));
+        for (uint64_t r = 0; r + 1 < R; r++) {
+            const uint64_t half = len[r] / 2;
+            const uint64_t pc = 9 + 72ull * lay[r].log_n, pn = 9 + 72ull * lay[r + 1].log_n, trip = 2 * pc + pn;
+            const uint64_t* d_ab = d_idx + r * per_round;
+            const uint64_t* d_c = d_ab + 2 * batch * ncc;
+            ZKB_TRY(fri_leafs_wire_batch(c, cw_ptr(r), cw_stride(r), cw_ptr(r + 1), cw_stride(r + 1), half, d_c, ncc, (uint32_t)batch, d_wire, d_yoff, base[r]));
+            ZKB_TRY(merkle_open_wire_batch(c, cw_ptr(r), lay[r], A + node_off[r], d_ab, 2 * ncc, (uint32_t)batch, cw_stride(r), inst_bytes,
+                                           d_wire, d_yoff, 2, base[r] + ncc * 57, trip, pc, false));
+            ZKB_TRY(merkle_open_wire_batch(c, cw_ptr(r + 1), lay[r + 1], A + node_off[r + 1], d_c, ncc, (uint32_t)batch, cw_stride(r + 1), inst_bytes,
+                                           d_wire, d_yoff, 1, base[r] + ncc * 57 + 2 * pc, trip, 0, false));
+        }
+        uint8_t* hw = nullptr;                                               // pinned: the D2H copy runs at PCIe rate
+        ZKB_TRY(host_scratch_reserve(c, 1, batch * seg_pad, &hw));
+        ZKB_CUDA(c, cudaMemcpyAsync(hw, d_wire, batch * seg_pad, cudaMemcpyDeviceToHost, c->stream));
+        ZKB_CUDA(c, ctx_stream_sync(c));
+        parallel_for(batch, c->assembly_threads, [&](size_t bi) {
+            std::vector<uint8_t>& v = ps[bi]->body;
+            v.insert(v.end(), hw + bi * seg_pad, hw + bi * seg_pad + seg);
+            ps[bi]->has_field = true;                                        // Leafs carry field elements (proof_stream_enum.rs:105-112)
+        });
+        return 0;
+    }
+    // (round-1 path, kept for ZKB_HOST_ASSEMBLY=1 and for layer shapes the wire kernels do not take: raw paths to the host,
+    // objects framed by host threads)
     DevBuf q;
     const size_t max_path = (size_t)lay[0].log_n * 64;
     const size_t idx_bytes = (batch * ncc * 8 * 3 + 255) & ~(size_t)255, leaf_bytes = (batch * ncc * 48 + 255) & ~(size_t)255;
@@ -220,7 +323,7 @@ int zkb_fri_prove_batch(zkb_ctx* c, const zkb_fri_params* p, const void* codewor
         ZKB_CUDA(c, cudaMemcpyAsync(leafs, d_leafs, batch * ncc * 48, cudaMemcpyDeviceToHost, c->stream));
         ZKB_CUDA(c, cudaMemcpyAsync(hab, d_pab, 2 * batch * ncc * pb_cur, cudaMemcpyDeviceToHost, c->stream));
         if (pb_nxt) ZKB_CUDA(c, cudaMemcpyAsync(hc, d_pc, batch * ncc * pb_nxt, cudaMemcpyDeviceToHost, c->stream));
-        ZKB_CUDA(c, cudaStreamSynchronize(c->stream));
+        ZKB_CUDA(c, ctx_stream_sync(c));
         parallel_for(batch, c->assembly_threads, [&](size_t b) {
             const uint8_t* lf = leafs + b * ncc * 48;
             for (uint64_t s = 0; s < ncc; s++)                               // fri.rs:189-195
@@ -256,6 +359,44 @@ int zkb_merkle_open_ps_batch(zkb_tree* const* trees, size_t count, const uint64_
     for (size_t i = 0; i < count * k; i++)
         if (idx[i] >= n) return set_err(c, ZKB_ERR_INDEX, "cannot open invalid index %llu", (unsigned long long)idx[i]);
     ZKB_CUDA(c, cudaSetDevice(c->device));
+    if (getenv("ZKB_HOST_ASSEMBLY") == nullptr && trees[0]->layout.log_n >= 1 && trees[0]->layout.log_n <= 17) {
+        // device-side framing: record (Value, Path) s of tree i at its final position inside its proof's segment; trees that share a
+        // proof stream append in increasing tree order (stark.rs:546-560 loops index-major per codeword in the order of the commits)
+        const uint64_t rec = 25 + 9 + 72ull * trees[0]->layout.log_n;
+        std::vector<zkb_ps*> streams;
+        std::vector<uint64_t> members;                                       // trees per stream
+        std::vector<uint64_t> hbuf(count * k + count);
+        uint64_t* yoff = hbuf.data() + count * k;
+        memcpy(hbuf.data(), idx, count * k * 8);
+        std::vector<size_t> group(count);
+        for (size_t i = 0; i < count; i++) {
+            size_t g = std::find(streams.begin(), streams.end(), ps[i]) - streams.begin();
+            if (g == streams.size()) { streams.push_back(ps[i]); members.push_back(0); }
+            group[i] = g;
+            members[g]++;
+        }
+        std::vector<uint64_t> seg_off(streams.size() + 1, 0), fill(streams.size(), 0);
+        for (size_t g = 0; g < streams.size(); g++) seg_off[g + 1] = seg_off[g] + ((members[g] * k * rec + 15) & ~15ull);
+        for (size_t i = 0; i < count; i++) { yoff[i] = seg_off[group[i]] + fill[group[i]] * k * rec; fill[group[i]]++; }
+        DevBuf buf;
+        const size_t hb = (hbuf.size() * 8 + 255) & ~(size_t)255;
+        ZKB_TRY(buf.alloc(c, hb + seg_off.back()));
+        uint64_t* d_idx = (uint64_t*)buf.p;
+        uint8_t* d_wire = (uint8_t*)buf.p + hb;
+        ZKB_CUDA(c, cudaMemcpyAsync(d_idx, hbuf.data(), hbuf.size() * 8, cudaMemcpyHostToDevice, c->stream));
+        ZKB_TRY(merkle_open_wire_batch(c, trees[0]->vals, trees[0]->layout, trees[0]->nodes, d_idx, k, (uint32_t)count, (uint64_t)vstride, (uint64_t)nstride,
+                                       d_wire, d_idx + count * k, 1, 0, rec, 0, true));
+        uint8_t* hw = nullptr;
+        ZKB_TRY(host_scratch_reserve(c, 1, seg_off.back(), &hw));
+        ZKB_CUDA(c, cudaMemcpyAsync(hw, d_wire, seg_off.back(), cudaMemcpyDeviceToHost, c->stream));
+        ZKB_CUDA(c, ctx_stream_sync(c));
+        parallel_for(streams.size(), c->assembly_threads, [&](size_t g) {
+            std::vector<uint8_t>& v = streams[g]->body;
+            v.insert(v.end(), hw + seg_off[g], hw + seg_off[g] + members[g] * k * rec);
+            streams[g]->has_field = true;                                    // Value objects carry field elements
+        });
+        return 0;
+    }
     const size_t depth = trees[0]->layout.log_n, path_bytes = depth * 64;
     const size_t idx_bytes = (count * k * 8 + 255) & ~(size_t)255, val_bytes = (count * k * 16 + 255) & ~(size_t)255;
     DevBuf buf;
@@ -273,7 +414,7 @@ int zkb_merkle_open_ps_batch(zkb_tree* const* trees, size_t count, const uint64_
     uint8_t* host = nullptr;                                                  // pinned
     ZKB_TRY(host_scratch_reserve(c, 1, val_bytes + count * k * path_bytes, &host));
     ZKB_CUDA(c, cudaMemcpyAsync(host, d_vals, val_bytes + count * k * path_bytes, cudaMemcpyDeviceToHost, c->stream));
-    ZKB_CUDA(c, cudaStreamSynchronize(c->stream));
+    ZKB_CUDA(c, ctx_stream_sync(c));
     // trees that share a proof stream append in increasing tree order; one worker per distinct stream
     std::vector<zkb_ps*> streams;
     std::vector<std::vector<size_t>> members;

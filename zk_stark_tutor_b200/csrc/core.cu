@@ -1,8 +1,10 @@
 // core.cu - context lifecycle, scratch arena, power-table cache, host scalar helpers.
 #include <stdarg.h>
+#include <unistd.h>
 #include <stdlib.h>
 #include <string.h>
 #include "ctx.hpp"
+#include "keccak.cuh"
 
 namespace zkb {
 
@@ -123,6 +125,27 @@ int host_scratch_reserve(zkb_ctx* c, int slot, size_t bytes, uint8_t** out) {
     return 0;
 }
 
+cudaError_t ctx_stream_sync(zkb_ctx* c) {
+    if (!c->blocking_sync) return cudaStreamSynchronize(c->stream);
+    // poll + sleep: the thread gives its core away while the GPU works (cudaStreamSynchronize spins)
+    for (;;) {
+        cudaError_t e = cudaStreamQuery(c->stream);
+        if (e != cudaErrorNotReady) return e;
+        usleep(15);
+    }
+}
+
+int ensure_fs_dev(zkb_ctx* c, size_t count) {
+    if (c->fs_dev_count >= count) return 0;
+    ZKB_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (c->fs_dev) cudaFree(c->fs_dev);
+    c->fs_dev = nullptr; c->fs_dev_count = 0;
+    ZKB_CUDA(c, cudaMalloc(&c->fs_dev, count * sizeof(FsDev) + 256));       // + the tail kernel's barrier word
+    ZKB_CUDA(c, cudaMemsetAsync(c->fs_dev, 0, count * sizeof(FsDev) + 256, c->stream));
+    c->fs_dev_count = count;
+    return 0;
+}
+
 fe h_inv(const fe& a) {
     if (fe_is_zero(a)) return fe_zero();
     // a^(p-2), p-2 = 0xCB7FFFFF_FFFFFFFF_FFFFFFFF_FFFFFFFF
@@ -216,6 +239,7 @@ int zkb_ctx_create(int device, void* stream, zkb_ctx** out) {
     if (cudaMallocHost(&c->pinned, c->pinned_bytes) != cudaSuccess) { delete c; return ZKB_ERR_CUDA; }
     memset(c->pinned, 0, c->pinned_bytes);          // the root handshake reads a sequence flag from this buffer
     if (ntt_device_init(c) != 0 || merkle_device_init(c) != 0 || fri_tail_device_init(c) != 0) { zkb_ctx_destroy(c); return ZKB_ERR_CUDA; }
+    if (const char* e = getenv("ZKB_BLOCKING_SYNC")) c->blocking_sync = atoi(e) != 0;
     if (const char* e = getenv("ZKB_TAIL_THREADS")) { int t = atoi(e); if (t == 0 || t == 128 || t == 256 || t == 512) c->tail_threads = (uint32_t)t; }
     *out = c;
     return 0;
@@ -257,6 +281,12 @@ int zkb_ctx_assembly_threads(zkb_ctx* c, int threads) {
 int zkb_ctx_tail_threads(zkb_ctx* c, int threads) {
     if (!c || (threads != 0 && threads != 128 && threads != 256 && threads != 512)) return ZKB_ERR_ARG;
     c->tail_threads = (uint32_t)threads;
+    return 0;
+}
+
+int zkb_ctx_blocking_sync(zkb_ctx* c, int enable) {
+    if (!c) return ZKB_ERR_ARG;
+    c->blocking_sync = enable != 0;
     return 0;
 }
 

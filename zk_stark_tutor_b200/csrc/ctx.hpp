@@ -54,6 +54,7 @@ struct zkb_ctx {
     size_t assembly_threads = 16;    // host threads per batched call for proof-stream assembly (zkb_ctx_assembly_threads)
     bool zero_copy_inputs = true;    // pinned host LDE inputs are read in place by the first NTT pass (zkb_ctx_zero_copy_inputs)
     uint32_t* tree_bars = nullptr;   // k_tree's arrival counter (device; zero between launches)
+    bool blocking_sync = false;      // wait for the stream by polling + sleeping instead of spinning (zkb_ctx_blocking_sync)
     uint32_t tail_threads = 512;     // threads per CTA of the persistent FRI tail kernel (zkb_ctx_tail_threads)
     void* fs_dev = nullptr;          // device Fiat-Shamir contexts (keccak.cuh FsDev x fs_dev_count) + the tail kernel's barrier word
     size_t fs_dev_count = 0;
@@ -105,6 +106,12 @@ int prof_collect(zkb_ctx* c);
 int ntt_device_init(zkb_ctx* c);
 int merkle_device_init(zkb_ctx* c);
 int fri_tail_device_init(zkb_ctx* c);
+// room for `count` device Fiat-Shamir contexts (keccak.cuh FsDev) in c->fs_dev (+ the tail kernel's barrier word behind them)
+int ensure_fs_dev(zkb_ctx* c, size_t count);
+
+// cudaStreamSynchronize(c->stream), or - blocking_sync - cudaStreamQuery + usleep: the calling thread sleeps instead of
+// spinning on a core (callers that keep many contexts in flight on their own threads)
+cudaError_t ctx_stream_sync(zkb_ctx* c);
 
 int scratch_reserve(zkb_ctx* c, size_t bytes, void** out);
 // pinned host buffer `slot` of at least `bytes` (grow-only, owned by the context): D2H copies into pageable memory

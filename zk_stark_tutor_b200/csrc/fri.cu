@@ -253,16 +253,6 @@ static int fri_commit_impl(zkb_ctx* c, const zkb_fri_params* p, const void* code
     return 0;
 }
 
-static int ensure_fs_dev(zkb_ctx* c, size_t count) {
-    if (c->fs_dev_count >= count) return 0;
-    ZKB_CUDA(c, cudaStreamSynchronize(c->stream));
-    if (c->fs_dev) cudaFree(c->fs_dev);
-    c->fs_dev = nullptr; c->fs_dev_count = 0;
-    ZKB_CUDA(c, cudaMalloc(&c->fs_dev, count * sizeof(FsDev) + 256));       // + the tail kernel's barrier word
-    ZKB_CUDA(c, cudaMemsetAsync(c->fs_dev, 0, count * sizeof(FsDev) + 256, c->stream));
-    c->fs_dev_count = count;
-    return 0;
-}
 
 #define ZKB_PINNED_FS_INIT 16384u     // c->pinned: staging of the FsDev head (sponge, kk_m, alpha, inv_off_m2[rounds])
 #define ZKB_PINNED_TAIL_OUT 65536u    // c->pinned: roots + last codeword written by the tail kernel

@@ -279,6 +279,142 @@ __global__ void __launch_bounds__(128) k_open(OpenArgs a) {
     }
 }
 
+// ---- openings in WIRE FORMAT (src/stark/proof_stream_enum.rs:67-127) ------------------------------------------------------
+// The batched provers used to bring raw paths to the host and let host threads wrap every node in its object framing
+// (1.16 MB of proof per RPSSS signature, 14,000 nodes): that assembly, not the GPU, bounded the batch workloads.  Here the kernel
+// that computes an authentication path writes the finished objects - [Value: 04 | u64_be(16) | value_be16] and
+// Path: 02 | u64_be(72 d) | d x (u64_be(64) | node) - at the byte offset the object has inside its proof, so the host appends
+// one contiguous segment per proof.  One warp per opening; the record is built in shared memory at the destination's 16-byte
+// phase and leaves as aligned 128-bit stores (byte stores only for the ragged head and tail).
+struct OpenWireArgs {
+    const fe* vals;
+    const uint8_t* nodes;
+    TreeLayout layout;
+    const uint64_t* idx;             // k indices per blockIdx.y
+    uint32_t k;
+    uint64_t vals_stride, nodes_stride;   // per blockIdx.y
+    uint8_t* out;                    // wire buffer (device)
+    const uint64_t* y_off;           // byte offset of blockIdx.y's segment inside `out`
+    uint32_t qdiv;                   // record q at y_off[y] + base + (q / qdiv) * stride_hi + (q % qdiv) * stride_lo
+    uint64_t base, stride_hi, stride_lo;
+    uint32_t with_value;
+};
+#define ZKB_WIRE_MAX_DEPTH 17
+#define ZKB_WIRE_REC_BYTES (16 + 25 + 9 + ZKB_WIRE_MAX_DEPTH * 72 + 16)
+__device__ __forceinline__ void wire_put_be64(uint8_t* p, uint64_t v, uint32_t lane) {
+    if (lane < 8) p[lane] = (uint8_t)(v >> (56 - 8 * lane));
+}
+__global__ void __launch_bounds__(128) k_open_wire(OpenWireArgs a) {
+    __shared__ uint64_t dig[4][14][8];          // per warp: 8 + 4 + 2 digests
+    __shared__ __align__(16) uint8_t recs[4][(ZKB_WIRE_REC_BYTES + 15) & ~15];
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    a.vals += (uint64_t)blockIdx.y * a.vals_stride;
+    a.nodes += (uint64_t)blockIdx.y * a.nodes_stride;
+    a.idx += (uint64_t)blockIdx.y * a.k;
+    const uint32_t q = blockIdx.x * 4 + warp;
+    if (q >= a.k) return;
+    const uint64_t idx = a.idx[q];
+    const uint32_t log_n = a.layout.log_n;
+    uint8_t* const dest = a.out + a.y_off[blockIdx.y] + a.base + (uint64_t)(q / a.qdiv) * a.stride_hi + (uint64_t)(q % a.qdiv) * a.stride_lo;
+    const uint32_t m = (uint32_t)(reinterpret_cast<uintptr_t>(dest) & 15u);
+    uint8_t* rec = recs[warp] + m;               // record byte p lives at rec[p]: same 16-byte phase as the destination
+    uint32_t pos = 0;
+    if (a.with_value) {                          // stark.rs:550-553: Value(codeword[i])
+        const fe v = fe_ldg(a.vals + idx);
+        if (lane == 0) rec[0] = 4;
+        wire_put_be64(rec + 1, 16, lane);
+        if (lane < 16) rec[9 + lane] = (uint8_t)(v.v[3 - (lane >> 2)] >> (24 - 8 * (lane & 3)));
+        pos = 25;
+    }
+    if (lane == 0) rec[pos] = 2;                 // Path(open(i))
+    wire_put_be64(rec + pos + 1, (uint64_t)log_n * 72, lane);
+    pos += 9;
+    uint64_t (*D)[8] = dig[warp];
+    auto put_node = [&](uint32_t level, const uint8_t* src) {          // 64 bytes from shared or global memory
+        uint8_t* o = rec + pos + level * 72;
+        wire_put_be64(o, 64, lane);
+        const uint16_t w = reinterpret_cast<const uint16_t*>(src)[lane];
+        o[8 + 2 * lane] = (uint8_t)w;
+        o[9 + 2 * lane] = (uint8_t)(w >> 8);
+    };
+    uint32_t l = 0;
+    while (l < log_n) {
+        if (a.layout.stored[l] && (l + 1 > log_n || a.layout.stored[l + 1] || l + 1 == log_n)) {
+            put_node(l, a.nodes + (a.layout.level_off[l] + ((idx >> l) ^ 1)) * 64);
+            l++;
+            continue;
+        }
+        // group with base level l (leaves when l == 0 and not stored, else a stored level): siblings at levels l, l+1, l+2
+        const uint64_t base = (idx >> (l + 3)) << 3;
+        if (lane < 8) {
+            uint64_t h[8];
+            if (a.layout.stored[l]) {
+                g_load_digest(a.nodes + a.layout.level_off[l] * 64, base + lane, h);
+            } else {
+                fe v = fe_ldg(a.vals + base + lane);
+                b2_leaf_call(&v, h);
+            }
+            for (int i = 0; i < 8; i++) D[lane][i] = h[i];
+        }
+        __syncwarp();
+        if (lane < 4) {
+            uint64_t h[8];
+            b2_node_call(D[2 * lane], D[2 * lane + 1], h);
+            for (int i = 0; i < 8; i++) D[8 + lane][i] = h[i];
+        }
+        __syncwarp();
+        if (lane < 2) {
+            uint64_t h[8];
+            b2_node_call(D[8 + 2 * lane], D[8 + 2 * lane + 1], h);
+            for (int i = 0; i < 8; i++) D[12 + lane][i] = h[i];
+        }
+        __syncwarp();
+        const uint32_t p0 = (uint32_t)(idx >> l) & 7u;
+        put_node(l, reinterpret_cast<const uint8_t*>(D[p0 ^ 1]));
+        put_node(l + 1, reinterpret_cast<const uint8_t*>(D[8 + ((p0 >> 1) ^ 1)]));
+        put_node(l + 2, reinterpret_cast<const uint8_t*>(D[12 + ((p0 >> 2) ^ 1)]));
+        __syncwarp();
+        l += 3;
+    }
+    __syncwarp();
+    // ---- the record leaves: bytes [m, m + total) of the 16-byte-aligned buffer recs[warp] -> dest - m + the same offsets
+    const uint32_t total = pos + log_n * 72, end = m + total;
+    const uint8_t* sb = recs[warp];
+    uint8_t* db = dest - m;
+    const uint32_t c0 = (m + 15u) >> 4, c1 = end >> 4;                   // full 16-byte chunks [c0, c1)
+    if (c0 < c1) {
+        for (uint32_t cidx = c0 + lane; cidx < c1; cidx += 32)
+            reinterpret_cast<uint4*>(db)[cidx] = reinterpret_cast<const uint4*>(sb)[cidx];
+        if (lane < 16) {
+            const uint32_t ph = m + lane, pt = (c1 << 4) + lane;
+            if (ph < (c0 << 4)) db[ph] = sb[ph];                         // ragged head
+            if (pt < end) db[pt] = sb[pt];                               // ragged tail
+        }
+    } else {
+        const uint32_t p = m + lane;                                     // shorter than two chunks: byte by byte
+        if (p < end) db[p] = sb[p];
+        if (p + 32 < end) db[p + 32] = sb[p + 32];
+    }
+}
+
+// Leafs objects of one FRI round for every instance (fri.rs:189-195): 03 | u64_be(48) | cur[a], cur[a + half], nxt[a] big-endian
+__global__ void k_leafs_wire(const fe* cur, uint64_t cur_stride, const fe* nxt, uint64_t nxt_stride, uint64_t half,
+                             const uint64_t* idx, uint32_t k, uint8_t* out, const uint64_t* y_off, uint64_t base) {
+    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= k) return;
+    const uint32_t b = blockIdx.y;
+    cur += (uint64_t)b * cur_stride;
+    nxt += (uint64_t)b * nxt_stride;
+    const uint64_t i = idx[(uint64_t)b * k + s];
+    const fe v[3] = {fe_ldg(cur + i), fe_ldg(cur + i + half), fe_ldg(nxt + i)};
+    uint8_t* o = out + y_off[b] + base + (uint64_t)s * 57;
+    o[0] = 3;
+    for (int j = 0; j < 7; j++) o[1 + j] = 0;
+    o[8] = 48;
+    for (int e = 0; e < 3; e++)
+        for (int j = 0; j < 16; j++) o[9 + 16 * e + j] = (uint8_t)(v[e].v[3 - (j >> 2)] >> (24 - 8 * (j & 3)));
+}
+
 // values at k indices -> contiguous (for the Value objects of the Stark query phase)
 __global__ void k_gather_vals(const fe* __restrict__ vals, const uint64_t* __restrict__ idx, uint32_t k, fe* __restrict__ out) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -448,7 +584,7 @@ int merkle_build_levels_batch(zkb_ctx* c, const fe* vals, const FoldArgs* fold, 
 int merkle_batch_roots(zkb_ctx* c, const TreeLayout& L, const uint8_t* nodes, const BatchArgs& b, uint8_t* roots_host) {
     ZKB_CUDA(c, cudaMemcpy2DAsync(roots_host, 64, nodes + L.level_off[L.log_n] * 64, b.nodes_stride ? b.nodes_stride : 64, 64, b.batch,
                                   cudaMemcpyDeviceToHost, c->stream));
-    ZKB_CUDA(c, cudaStreamSynchronize(c->stream));
+    ZKB_CUDA(c, ctx_stream_sync(c));
     return 0;
 }
 
@@ -471,6 +607,29 @@ int merkle_open_device_batch(zkb_ctx* c, const fe* vals, const TreeLayout& layou
     a.vals = vals; a.nodes = nodes; a.layout = layout; a.idx = d_idx; a.k = (uint32_t)k; a.out = d_out;
     a.vals_stride = vals_stride; a.nodes_stride = nodes_stride;
     { LaunchScope ls(c, K_OPEN); k_open<<<dim3((unsigned)((k + 3) / 4), batch), 128, 0, c->stream>>>(a); }
+    ZKB_CUDA(c, cudaGetLastError());
+    return 0;
+}
+
+// One launch: k openings per instance (blockIdx.y) written as wire objects; see OpenWireArgs.
+int merkle_open_wire_batch(zkb_ctx* c, const fe* vals, const TreeLayout& layout, const uint8_t* nodes, const uint64_t* d_idx, size_t k,
+                           uint32_t batch, uint64_t vals_stride, uint64_t nodes_stride, uint8_t* d_out, const uint64_t* d_y_off,
+                           uint32_t qdiv, uint64_t base, uint64_t stride_hi, uint64_t stride_lo, bool with_value) {
+    if (k == 0 || batch == 0) return 0;
+    if (layout.log_n > ZKB_WIRE_MAX_DEPTH || layout.log_n < 1) return set_err(c, ZKB_ERR_ARG, "internal: wire-format openings take trees of 2..2^%d leaves", ZKB_WIRE_MAX_DEPTH);
+    OpenWireArgs a;
+    a.vals = vals; a.nodes = nodes; a.layout = layout; a.idx = d_idx; a.k = (uint32_t)k;
+    a.vals_stride = vals_stride; a.nodes_stride = nodes_stride;
+    a.out = d_out; a.y_off = d_y_off; a.qdiv = qdiv ? qdiv : 1; a.base = base; a.stride_hi = stride_hi; a.stride_lo = stride_lo;
+    a.with_value = with_value;
+    { LaunchScope ls(c, K_OPEN); k_open_wire<<<dim3((unsigned)((k + 3) / 4), batch), 128, 0, c->stream>>>(a); }
+    ZKB_CUDA(c, cudaGetLastError());
+    return 0;
+}
+int fri_leafs_wire_batch(zkb_ctx* c, const fe* cur, uint64_t cur_stride, const fe* nxt, uint64_t nxt_stride, uint64_t half,
+                         const uint64_t* d_idx, size_t k, uint32_t batch, uint8_t* d_out, const uint64_t* d_y_off, uint64_t base) {
+    if (k == 0 || batch == 0) return 0;
+    { LaunchScope ls(c, K_GATHER); k_leafs_wire<<<dim3((unsigned)((k + 63) / 64), batch), 64, 0, c->stream>>>(cur, cur_stride, nxt, nxt_stride, half, d_idx, (uint32_t)k, d_out, d_y_off, base); }
     ZKB_CUDA(c, cudaGetLastError());
     return 0;
 }

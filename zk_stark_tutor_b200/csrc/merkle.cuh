@@ -86,6 +86,15 @@ int merkle_open_device_batch(zkb_ctx* c, const fe* vals, const TreeLayout& layou
                              const uint64_t* d_idx, size_t k, uint8_t* d_out, uint32_t batch,
                              uint64_t vals_stride, uint64_t nodes_stride);
 
+// Openings written by the device as finished proof-stream objects (proof_stream_enum.rs:67-127): opening q of instance y goes to
+// d_out + d_y_off[y] + base + (q / qdiv) * stride_hi + (q % qdiv) * stride_lo as [Value (25 bytes) if with_value] Path (9 + 72 log_n bytes).
+int merkle_open_wire_batch(zkb_ctx* c, const fe* vals, const TreeLayout& layout, const uint8_t* nodes, const uint64_t* d_idx, size_t k,
+                           uint32_t batch, uint64_t vals_stride, uint64_t nodes_stride, uint8_t* d_out, const uint64_t* d_y_off,
+                           uint32_t qdiv, uint64_t base, uint64_t stride_hi, uint64_t stride_lo, bool with_value);
+// Leafs objects (57 bytes each) of one FRI round: object s of instance y at d_out + d_y_off[y] + base + 57 s
+int fri_leafs_wire_batch(zkb_ctx* c, const fe* cur, uint64_t cur_stride, const fe* nxt, uint64_t nxt_stride, uint64_t half,
+                         const uint64_t* d_idx, size_t k, uint32_t batch, uint8_t* d_out, const uint64_t* d_y_off, uint64_t base);
+
 }  // namespace zkb
 
 struct zkb_tree {

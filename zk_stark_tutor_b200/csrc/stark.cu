@@ -94,7 +94,7 @@ static int get_prefix_tables(zkb_ctx* c, const fe& omicron, uint64_t N, uint64_t
     }
     NttOpts o;
     rc = ntt_exec(c, t->root2n, (const fe*)stage.p, 2 * N, 2 * N, t->dev, 2 * N, 2, ilog2_u64(2 * N), o);
-    if (rc == 0 && cudaStreamSynchronize(c->stream) != cudaSuccess) rc = set_err(c, ZKB_ERR_CUDA, "prefix tables: transform failed");
+    if (rc == 0 && ctx_stream_sync(c) != cudaSuccess) rc = set_err(c, ZKB_ERR_CUDA, "prefix tables: transform failed");
     if (rc) { prefix_tables_destroy(t); return rc; }
     c->attachments.push_back({t, prefix_tables_destroy});
     *out = t;
@@ -157,7 +157,7 @@ int zkb_trace_lde_batch(zkb_ctx* c, const uint8_t omicron_b[16], uint64_t omicro
     lde.has_scale = true;
     lde.scale_base = offset;
     ZKB_TRY(ntt_exec(c, omega, C, m ? L : N, m ? L : N, (fe*)out, out_stride, batch, ilog2_u64(n), lde));   // stark.rs:373-378 for the trace itself
-    if (in.p) ZKB_CUDA(c, cudaStreamSynchronize(c->stream));     // the caller's host buffer has been consumed
+    if (in.p) ZKB_CUDA(c, ctx_stream_sync(c));     // the caller's host buffer has been consumed
     return 0;
 }
 
@@ -179,7 +179,7 @@ int zkb_coset_degree_batch(zkb_ctx* c, const uint8_t omega_b[16], const void* co
     ZKB_CUDA(c, cudaGetLastError());
     std::vector<unsigned long long> host(batch);
     ZKB_CUDA(c, cudaMemcpyAsync(host.data(), deg, batch * 8, cudaMemcpyDeviceToHost, c->stream));
-    ZKB_CUDA(c, cudaStreamSynchronize(c->stream));
+    ZKB_CUDA(c, ctx_stream_sync(c));
     for (size_t b = 0; b < batch; b++) degrees_out[b] = (int64_t)host[b] - 1;     // -1: the zero polynomial (Polynomial::degree() == None)
     return 0;
 }

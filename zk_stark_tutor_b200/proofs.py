@@ -156,6 +156,9 @@ class ProofPipeline:
         import zk_stark_tutor_b200 as zk
         self.zk, self.shape = zk, shape
         self.ctxs = [zk.Context(device, stream="own") for _ in range(lanes)]
+        if lanes > 1:
+            for c in self.ctxs:      # more contexts in flight than idle cores: sleep while the GPU works instead of spinning on a core each
+                c.check(c.lib.zkb_ctx_blocking_sync(c.h, 1))
         if assembly_threads:
             for c in self.ctxs:
                 c.check(c.lib.zkb_ctx_assembly_threads(c.h, int(assembly_threads)))
