@@ -43,6 +43,7 @@ extern "C" {
 #define ZKB_ERR_ROUNDS (-10)     /* FRI needs >= 2 rounds (fri.rs:225 unwrap)                 */
 #define ZKB_ERR_DEGREE (-11)     /* divide by polynomial of larger degree (ntt_arithmetics.rs:268) */
 #define ZKB_ERR_CALLBACK (-12)   /* Fiat-Shamir callback returned non-zero                    */
+#define ZKB_ERR_NOMEM (-13)      /* host allocation failed (std::bad_alloc); a proof stream that was being appended to is unusable */
 
 typedef struct zkb_ctx zkb_ctx;
 typedef struct zkb_tree zkb_tree;

@@ -459,6 +459,28 @@ def test_fast_multiply_trailing_zero_quirk(ctx):
             N.fast_coset_divide(w, n, F.GENERATOR, prod + [0] * 9, bb + [0] * 5)
 
 
+def test_fast_multiply_quirk_beyond_one_tile_and_device_operands(ctx):
+    """The same quirk with operands longer than one 4096-value tile (the literal loop then runs as global-memory stages) and
+    with operands / results that live in device memory: no size or residency limit versus the reference's signatures."""
+    n = 1 << 14
+    w = F.primitive_nth_root(n)
+    a, b = rvals(30) + [0] * 5000, rvals(9) + [0] * 6000            # degrees 29 + 8: order shrinks to 64, operands pad to 8192
+    want = N.fast_multiply(w, n, a, b)
+    assert zk.fast_multiply(w, n, a, b, ctx) == want
+    prod = want + [0] * 4500
+    assert zk.fast_coset_divide(w, n, F.GENERATOR, prod, b, ctx) == N.fast_coset_divide(w, n, F.GENERATOR, prod, b)
+    # device-resident operands through the C ABI
+    import ctypes
+    from zk_stark_tutor_b200.context import le16, pack, unpack
+    x, y = rvals(3000), rvals(2500)
+    dx, dy = cuda(pack(x)), cuda(pack(y))
+    import torch
+    dout = torch.empty((len(x) + len(y), 2), dtype=torch.int64, device="cuda")
+    n_out = ctypes.c_size_t(0)
+    ctx.check(ctx.lib.zkb_poly_mul(ctx.h, le16(w), n, dx.data_ptr(), len(x), dy.data_ptr(), len(y), dout.data_ptr(), ctypes.byref(n_out)))
+    assert unpack(host(dout)[:n_out.value]) == zk.fast_multiply(w, n, x, y, ctx)
+
+
 def test_ntt_with_non_primitive_root_matches_reference_loop(ctx):
     """ntt() does not check its root (ntt.rs:7-49); for lengths up to one tile the CUDA path
     is the same radix-2 DIT op for op, so even a wrong-order root gives the reference's result."""

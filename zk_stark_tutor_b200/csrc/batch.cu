@@ -15,6 +15,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <algorithm>
+#include <atomic>
 #include <thread>
 #include <vector>
 #include "merkle.cuh"
@@ -49,13 +50,18 @@ __global__ void k_gather_vals_batch(const fe* vals, uint64_t vals_stride, const 
 // cap = the context's zkb_ctx_assembly_threads setting: a caller that already keeps several batches in flight on its own threads
 // wants few (measured, 8 batches of 32 signatures in flight on a 16-core host: 1 thread 9,724/s, 4: 9,666/s, 16: 8,339/s)
 template <typename F>
-static void parallel_for(size_t n, size_t cap, F fn) {
+static bool parallel_for(size_t n, size_t cap, F fn) {
     size_t threads = std::min<size_t>(std::min<size_t>(n, cap ? cap : 1), std::max(1u, std::thread::hardware_concurrency()));
-    if (threads <= 1) { for (size_t i = 0; i < n; i++) fn(i); return; }
+    std::atomic<bool> ok(true);
+    auto guarded = [&](size_t i) { try { fn(i); } catch (...) { ok = false; } };     // an exception must not leave a worker thread (std::terminate)
+    if (threads <= 1) { for (size_t i = 0; i < n; i++) guarded(i); return ok; }
     std::vector<std::thread> pool;
-    for (size_t t = 0; t < threads; t++)
-        pool.emplace_back([=]() { for (size_t i = t; i < n; i += threads) fn(i); });
+    try {
+        for (size_t t = 0; t < threads; t++)
+            pool.emplace_back([=, &guarded]() { for (size_t i = t; i < n; i += threads) guarded(i); });
+    } catch (...) { ok = false; }                                                      // thread creation failed: the started ones still finish
     for (auto& th : pool) th.join();
+    return ok;
 }
 
 }  // namespace zkb
@@ -64,7 +70,7 @@ using namespace zkb;
 
 extern "C" {
 
-int zkb_merkle_build_batch(zkb_ctx* c, const void* vals, size_t n, size_t stride, size_t batch, zkb_tree** trees_out, zkb_ps* const* ps) {
+static int zkb_merkle_build_batch_impl(zkb_ctx* c, const void* vals, size_t n, size_t stride, size_t batch, zkb_tree** trees_out, zkb_ps* const* ps) {
     if (!c || !vals || !trees_out || batch == 0) return ZKB_ERR_ARG;
     for (size_t b = 0; b < batch; b++) trees_out[b] = nullptr;
     if (n == 0 || (n & (n - 1))) return set_err(c, ZKB_ERR_NOT_POW2, "Leafs len must be power of two (got %zu)", n);
@@ -97,7 +103,12 @@ int zkb_merkle_build_batch(zkb_ctx* c, const void* vals, size_t n, size_t stride
     return 0;
 }
 
-int zkb_fri_prove_batch(zkb_ctx* c, const zkb_fri_params* p, const void* codewords, size_t n, size_t stride, size_t batch,
+int zkb_merkle_build_batch(zkb_ctx* c, const void* vals, size_t n, size_t stride, size_t batch, zkb_tree** trees_out, zkb_ps* const* ps) {
+    if (!c) return ZKB_ERR_ARG;
+    ZKB_ABI_GUARD(c, return zkb_merkle_build_batch_impl(c, vals, n, stride, batch, trees_out, ps);)
+}
+
+static int zkb_fri_prove_batch_impl(zkb_ctx* c, const zkb_fri_params* p, const void* codewords, size_t n, size_t stride, size_t batch,
                         zkb_ps* const* ps, uint64_t* top_indices_out) {
     if (!c || !p || !codewords || !ps || !top_indices_out || batch == 0) return ZKB_ERR_ARG;
     if (p->domain_length != n) return set_err(c, ZKB_ERR_LENGTH, "Length of the domain doesnt match the length of initial codeword");
@@ -281,12 +292,12 @@ int zkb_fri_prove_batch(zkb_ctx* c, const zkb_fri_params* p, const void* codewor
         ZKB_TRY(host_scratch_reserve(c, 1, batch * seg_pad, &hw));
         ZKB_CUDA(c, cudaMemcpyAsync(hw, d_wire, batch * seg_pad, cudaMemcpyDeviceToHost, c->stream));
         ZKB_CUDA(c, ctx_stream_sync(c));
-        parallel_for(batch, c->assembly_threads, [&](size_t bi) {
+        const bool ok = parallel_for(batch, c->assembly_threads, [&](size_t bi) {
             std::vector<uint8_t>& v = ps[bi]->body;
             v.insert(v.end(), hw + bi * seg_pad, hw + bi * seg_pad + seg);
             ps[bi]->has_field = true;                                        // Leafs carry field elements (proof_stream_enum.rs:105-112)
         });
-        return 0;
+        return ok ? 0 : set_err(c, ZKB_ERR_NOMEM, "out of host memory while appending to the proof streams (they are unusable now)");
     }
     // (round-1 path, kept for ZKB_HOST_ASSEMBLY=1 and for layer shapes the wire kernels do not take: raw paths to the host,
     // objects framed by host threads)
@@ -340,7 +351,12 @@ int zkb_fri_prove_batch(zkb_ctx* c, const zkb_fri_params* p, const void* codewor
     return 0;
 }
 
-int zkb_merkle_open_ps_batch(zkb_tree* const* trees, size_t count, const uint64_t* idx, size_t k, zkb_ps* const* ps) {
+int zkb_fri_prove_batch(zkb_ctx* c, const zkb_fri_params* p, const void* codewords, size_t n, size_t stride, size_t batch, zkb_ps* const* ps, uint64_t* top_indices_out) {
+    if (!c) return ZKB_ERR_ARG;
+    ZKB_ABI_GUARD(c, return zkb_fri_prove_batch_impl(c, p, codewords, n, stride, batch, ps, top_indices_out);)
+}
+
+static int zkb_merkle_open_ps_batch_impl(zkb_tree* const* trees, size_t count, const uint64_t* idx, size_t k, zkb_ps* const* ps) {
     if (!trees || !ps || count == 0 || (k && !idx)) return ZKB_ERR_ARG;
     for (size_t i = 0; i < count; i++) if (!trees[i] || !ps[i]) return ZKB_ERR_ARG;
     zkb_ctx* c = trees[0]->ctx;
@@ -390,12 +406,12 @@ int zkb_merkle_open_ps_batch(zkb_tree* const* trees, size_t count, const uint64_
         ZKB_TRY(host_scratch_reserve(c, 1, seg_off.back(), &hw));
         ZKB_CUDA(c, cudaMemcpyAsync(hw, d_wire, seg_off.back(), cudaMemcpyDeviceToHost, c->stream));
         ZKB_CUDA(c, ctx_stream_sync(c));
-        parallel_for(streams.size(), c->assembly_threads, [&](size_t g) {
+        const bool ok = parallel_for(streams.size(), c->assembly_threads, [&](size_t g) {
             std::vector<uint8_t>& v = streams[g]->body;
             v.insert(v.end(), hw + seg_off[g], hw + seg_off[g] + members[g] * k * rec);
             streams[g]->has_field = true;                                    // Value objects carry field elements
         });
-        return 0;
+        return ok ? 0 : set_err(c, ZKB_ERR_NOMEM, "out of host memory while appending to the proof streams (they are unusable now)");
     }
     const size_t depth = trees[0]->layout.log_n, path_bytes = depth * 64;
     const size_t idx_bytes = (count * k * 8 + 255) & ~(size_t)255, val_bytes = (count * k * 16 + 255) & ~(size_t)255;
@@ -431,6 +447,11 @@ int zkb_merkle_open_ps_batch(zkb_tree* const* trees, size_t count, const uint64_
             }
     });
     return 0;
+}
+
+int zkb_merkle_open_ps_batch(zkb_tree* const* trees, size_t count, const uint64_t* idx, size_t k, zkb_ps* const* ps) {
+    if (!trees || count == 0 || !trees[0]) return ZKB_ERR_ARG;
+    ZKB_ABI_GUARD(trees[0]->ctx, return zkb_merkle_open_ps_batch_impl(trees, count, idx, k, ps);)
 }
 
 }  // extern "C"

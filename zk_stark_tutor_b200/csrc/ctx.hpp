@@ -9,6 +9,7 @@
 #include <string>
 #include <vector>
 #include <memory>
+#include <new>
 #include "fe128.cuh"
 #include "../../include/zkb200.h"
 
@@ -83,6 +84,15 @@ int set_err(zkb_ctx* c, int code, const char* fmt, ...);
             return zkb::set_err((ctx), ZKB_ERR_CUDA, "%s failed: %s (%s:%d)", #call,     \
                                 cudaGetErrorString(e__), __FILE__, __LINE__);            \
     } while (0)
+
+// C++ exceptions must not cross the C ABI (undefined behaviour in ctypes / Rust callers): entry points that allocate on the host
+// run their body under this guard and report std::bad_alloc as ZKB_ERR_NOMEM
+#define ZKB_ABI_GUARD(ctx, body)                                                                 \
+    try { body } catch (const std::bad_alloc&) {                                                 \
+        return zkb::set_err((ctx), ZKB_ERR_NOMEM, "out of host memory (std::bad_alloc)");        \
+    } catch (...) {                                                                              \
+        return zkb::set_err((ctx), ZKB_ERR_NOMEM, "unexpected C++ exception inside the library"); \
+    }
 
 #define ZKB_TRY(expr)            \
     do {                         \

@@ -342,13 +342,13 @@ static int fri_commit_device_fs(zkb_ctx* c, zkb_fri_layers* L, const fe& omega_i
     return 0;
 }
 
-int zkb_fri_commit(zkb_ctx* c, const zkb_fri_params* p, const void* codeword, size_t n,
+static int zkb_fri_commit_body(zkb_ctx* c, const zkb_fri_params* p, const void* codeword, size_t n,
                    zkb_fs_callback fs, void* user, zkb_fri_layers** out) {
     if (!c || !p || !codeword || !fs || !out) return ZKB_ERR_ARG;
     return fri_commit_impl(c, p, codeword, nullptr, 0, n, fs, user, out);
 }
 
-int zkb_lde_fri_commit(zkb_ctx* c, const zkb_fri_params* p, const void* coeffs, size_t n_coeffs,
+static int zkb_lde_fri_commit_body(zkb_ctx* c, const zkb_fri_params* p, const void* coeffs, size_t n_coeffs,
                        zkb_fs_callback fs, void* user, zkb_fri_layers** out) {
     if (!c || !p || !fs || !out || (n_coeffs && !coeffs)) return ZKB_ERR_ARG;
     if (n_coeffs > p->domain_length)
@@ -372,7 +372,7 @@ int zkb_fri_layer_codeword(zkb_fri_layers* l, uint64_t r, void* out) {
     return 0;
 }
 
-int zkb_fri_query(zkb_fri_layers* l, uint64_t r, const uint64_t* idx_c, size_t ncc, uint8_t* leafs_out, uint8_t* paths_out) {
+static int zkb_fri_query_body(zkb_fri_layers* l, uint64_t r, const uint64_t* idx_c, size_t ncc, uint8_t* leafs_out, uint8_t* paths_out) {
     if (!l || !idx_c || !leafs_out || !paths_out) return ZKB_ERR_ARG;
     zkb_ctx* c = l->ctx;
     if (r + 1 >= l->rounds) return set_err(c, ZKB_ERR_ARG, "fri_query: no layer after round %llu", (unsigned long long)r);
@@ -436,7 +436,7 @@ static int push_last_codeword(zkb_fri_layers* L, zkb_ps* ps) {
     return 0;
 }
 
-int zkb_fri_commit_ps(zkb_ctx* c, const zkb_fri_params* p, const void* codeword, size_t n, zkb_ps* ps,
+static int zkb_fri_commit_ps_body(zkb_ctx* c, const zkb_fri_params* p, const void* codeword, size_t n, zkb_ps* ps,
                       zkb_fri_layers** out) {
     if (!c || !p || !codeword || !ps || !out) return ZKB_ERR_ARG;
     ZKB_TRY(fri_commit_impl(c, p, codeword, nullptr, 0, n, ps_callback, ps, out, ps));
@@ -445,7 +445,7 @@ int zkb_fri_commit_ps(zkb_ctx* c, const zkb_fri_params* p, const void* codeword,
     return rc;
 }
 
-int zkb_lde_fri_commit_ps(zkb_ctx* c, const zkb_fri_params* p, const void* coeffs, size_t n_coeffs, zkb_ps* ps,
+static int zkb_lde_fri_commit_ps_body(zkb_ctx* c, const zkb_fri_params* p, const void* coeffs, size_t n_coeffs, zkb_ps* ps,
                           zkb_fri_layers** out) {
     if (!c || !p || !ps || !out) return ZKB_ERR_ARG;
     if (n_coeffs && !coeffs) return ZKB_ERR_ARG;
@@ -457,7 +457,7 @@ int zkb_lde_fri_commit_ps(zkb_ctx* c, const zkb_fri_params* p, const void* coeff
     return rc;
 }
 
-int zkb_fri_prove(zkb_ctx* c, const zkb_fri_params* p, const void* codeword, size_t n, zkb_ps* ps,
+static int zkb_fri_prove_body(zkb_ctx* c, const zkb_fri_params* p, const void* codeword, size_t n, zkb_ps* ps,
                   uint64_t* top_indices_out) {
     if (!c || !p || !ps || !top_indices_out) return ZKB_ERR_ARG;
     const uint64_t ncc = p->num_colinearity_tests;
@@ -491,6 +491,36 @@ int zkb_fri_prove(zkb_ctx* c, const zkb_fri_params* p, const void* codeword, siz
         }
     }
     return 0;
+}
+
+int zkb_fri_commit(zkb_ctx* c, const zkb_fri_params* p, const void* codeword, size_t n, zkb_fs_callback fs, void* user, zkb_fri_layers** out) {
+    if (!c) return ZKB_ERR_ARG;
+    ZKB_ABI_GUARD(c, return zkb_fri_commit_body(c, p, codeword, n, fs, user, out);)
+}
+
+int zkb_lde_fri_commit(zkb_ctx* c, const zkb_fri_params* p, const void* coeffs, size_t n_coeffs, zkb_fs_callback fs, void* user, zkb_fri_layers** out) {
+    if (!c) return ZKB_ERR_ARG;
+    ZKB_ABI_GUARD(c, return zkb_lde_fri_commit_body(c, p, coeffs, n_coeffs, fs, user, out);)
+}
+
+int zkb_fri_commit_ps(zkb_ctx* c, const zkb_fri_params* p, const void* codeword, size_t n, zkb_ps* ps, zkb_fri_layers** out) {
+    if (!c) return ZKB_ERR_ARG;
+    ZKB_ABI_GUARD(c, return zkb_fri_commit_ps_body(c, p, codeword, n, ps, out);)
+}
+
+int zkb_lde_fri_commit_ps(zkb_ctx* c, const zkb_fri_params* p, const void* coeffs, size_t n_coeffs, zkb_ps* ps, zkb_fri_layers** out) {
+    if (!c) return ZKB_ERR_ARG;
+    ZKB_ABI_GUARD(c, return zkb_lde_fri_commit_ps_body(c, p, coeffs, n_coeffs, ps, out);)
+}
+
+int zkb_fri_prove(zkb_ctx* c, const zkb_fri_params* p, const void* codeword, size_t n, zkb_ps* ps, uint64_t* top_indices_out) {
+    if (!c) return ZKB_ERR_ARG;
+    ZKB_ABI_GUARD(c, return zkb_fri_prove_body(c, p, codeword, n, ps, top_indices_out);)
+}
+
+int zkb_fri_query(zkb_fri_layers* l, uint64_t r, const uint64_t* idx_c, size_t ncc, uint8_t* leafs_out, uint8_t* paths_out) {
+    if (!l) return ZKB_ERR_ARG;
+    ZKB_ABI_GUARD(l->ctx, return zkb_fri_query_body(l, r, idx_c, ncc, leafs_out, paths_out);)
 }
 
 }  // extern "C"

@@ -210,7 +210,7 @@ static std::mutex g_pool_mu;
 static std::vector<std::vector<uint8_t>> g_body_pool;
 static const size_t kPoolMax = 1024, kPoolKeepBytes = 8u << 20;   // <= 1024 x ~1.2 MB kept: several batches of signature streams in flight
 
-int zkb_ps_create(const uint8_t* document, size_t document_len, int is_signature, zkb_ps** out) {
+static int zkb_ps_create_body(const uint8_t* document, size_t document_len, int is_signature, zkb_ps** out) {
     if (!out) return ZKB_ERR_ARG;
     zkb_ps* ps = new zkb_ps();
     {
@@ -236,12 +236,12 @@ void zkb_ps_free(zkb_ps* ps) {
     delete ps;
 }
 
-int zkb_ps_push_root(zkb_ps* ps, const uint8_t* root, size_t len) {
+static int zkb_ps_push_root_body(zkb_ps* ps, const uint8_t* root, size_t len) {
     if (!ps || (!root && len)) return ZKB_ERR_ARG;
     ps->push(0, root, len);
     return 0;
 }
-int zkb_ps_push_codeword(zkb_ps* ps, const void* vals_host, size_t n) {
+static int zkb_ps_push_codeword_body(zkb_ps* ps, const void* vals_host, size_t n) {
     if (!ps || (!vals_host && n)) return ZKB_ERR_ARG;
     std::vector<uint8_t> p(n * 16);
     for (size_t i = 0; i < n; i++) le16_to_be16((const uint8_t*)vals_host + 16 * i, p.data() + 16 * i);
@@ -249,7 +249,7 @@ int zkb_ps_push_codeword(zkb_ps* ps, const void* vals_host, size_t n) {
     if (n) ps->has_field = true;
     return 0;
 }
-int zkb_ps_push_path(zkb_ps* ps, const uint8_t* nodes, size_t count) {
+static int zkb_ps_push_path_body(zkb_ps* ps, const uint8_t* nodes, size_t count) {
     if (!ps || (!nodes && count)) return ZKB_ERR_ARG;
     // code || len || count x (u64_be(64) || 64 bytes), written in place (a proof holds ~1,350 paths)
     std::vector<uint8_t>& v = ps->body;
@@ -265,7 +265,7 @@ int zkb_ps_push_path(zkb_ps* ps, const uint8_t* nodes, size_t count) {
     }
     return 0;
 }
-int zkb_ps_push_leafs(zkb_ps* ps, const uint8_t a[16], const uint8_t b[16], const uint8_t c[16]) {
+static int zkb_ps_push_leafs_body(zkb_ps* ps, const uint8_t a[16], const uint8_t b[16], const uint8_t c[16]) {
     if (!ps) return ZKB_ERR_ARG;
     uint8_t p[48];
     le16_to_be16(a, p); le16_to_be16(b, p + 16); le16_to_be16(c, p + 32);
@@ -273,7 +273,7 @@ int zkb_ps_push_leafs(zkb_ps* ps, const uint8_t a[16], const uint8_t b[16], cons
     ps->has_field = true;
     return 0;
 }
-int zkb_ps_push_value(zkb_ps* ps, const uint8_t v[16]) {
+static int zkb_ps_push_value_body(zkb_ps* ps, const uint8_t v[16]) {
     if (!ps) return ZKB_ERR_ARG;
     uint8_t p[16];
     le16_to_be16(v, p);
@@ -281,12 +281,40 @@ int zkb_ps_push_value(zkb_ps* ps, const uint8_t v[16]) {
     ps->has_field = true;
     return 0;
 }
-int zkb_ps_push_object(zkb_ps* ps, uint8_t code, const uint8_t* payload, size_t len) {
+static int zkb_ps_push_object_body(zkb_ps* ps, uint8_t code, const uint8_t* payload, size_t len) {
     if (!ps || (!payload && len) || code > 4) return ZKB_ERR_ARG;
     ps->push(code, payload, len);
     if (code == 3 || code == 4 || (code == 1 && len)) ps->has_field = true;   // proof_stream_enum.rs:76-125
     return 0;
 }
+int zkb_ps_create(const uint8_t* document, size_t document_len, int is_signature, zkb_ps** out) {
+    try { return zkb_ps_create_body(document, document_len, is_signature, out); } catch (...) { return ZKB_ERR_NOMEM; }     // std::bad_alloc must not cross the C ABI; the stream is unusable afterwards
+}
+
+int zkb_ps_push_root(zkb_ps* ps, const uint8_t* root, size_t len) {
+    try { return zkb_ps_push_root_body(ps, root, len); } catch (...) { return ZKB_ERR_NOMEM; }     // std::bad_alloc must not cross the C ABI; the stream is unusable afterwards
+}
+
+int zkb_ps_push_codeword(zkb_ps* ps, const void* vals_host, size_t n) {
+    try { return zkb_ps_push_codeword_body(ps, vals_host, n); } catch (...) { return ZKB_ERR_NOMEM; }     // std::bad_alloc must not cross the C ABI; the stream is unusable afterwards
+}
+
+int zkb_ps_push_path(zkb_ps* ps, const uint8_t* nodes, size_t count) {
+    try { return zkb_ps_push_path_body(ps, nodes, count); } catch (...) { return ZKB_ERR_NOMEM; }     // std::bad_alloc must not cross the C ABI; the stream is unusable afterwards
+}
+
+int zkb_ps_push_leafs(zkb_ps* ps, const uint8_t a[16], const uint8_t b[16], const uint8_t c[16]) {
+    try { return zkb_ps_push_leafs_body(ps, a, b, c); } catch (...) { return ZKB_ERR_NOMEM; }     // std::bad_alloc must not cross the C ABI; the stream is unusable afterwards
+}
+
+int zkb_ps_push_value(zkb_ps* ps, const uint8_t v[16]) {
+    try { return zkb_ps_push_value_body(ps, v); } catch (...) { return ZKB_ERR_NOMEM; }     // std::bad_alloc must not cross the C ABI; the stream is unusable afterwards
+}
+
+int zkb_ps_push_object(zkb_ps* ps, uint8_t code, const uint8_t* payload, size_t len) {
+    try { return zkb_ps_push_object_body(ps, code, payload, len); } catch (...) { return ZKB_ERR_NOMEM; }     // std::bad_alloc must not cross the C ABI; the stream is unusable afterwards
+}
+
 size_t zkb_ps_digest(const zkb_ps* ps, uint8_t* out, size_t cap) {
     if (!ps) return 0;
     size_t total = 16 + ps->body.size();

@@ -25,6 +25,7 @@
 // stages whose odd inputs are all zero are replaced by a broadcast (2 of 24 stages for
 // ef = 4).  The coset scaling c_i*offset^i of the LDE is fused into the pass-1 load.
 #include <string.h>
+#include <vector>
 #include "ctx.hpp"
 #include "ntt.cuh"
 
@@ -618,6 +619,40 @@ __global__ void k_pointwise_div(const fe* a, const fe* b, fe* out, uint64_t n, u
     fe_store(out + i, fe_montmul(acc, fe_ldg(a + i)));     // (1/d)*R * a / R
 }
 
+// ---- the reference's radix-2 loop, literally, for ANY length (ntt.rs:26-46: bit-reversed copy, then one stage per launch with
+// explicit e + o*w / e - o*w and twiddles root^(j * n / (2h)) from a power table of `root`).  Only fast_multiply / fast_coset_divide's
+// trailing-zero quirk needs it above one tile: there ntt() runs at the operand's padded length with a root of SMALLER order, for
+// which the loop is not a DFT and no factorisation applies.  Global-memory passes: slow, correct, rare.
+__global__ void k_bitrev_copy(const fe* __restrict__ in, fe* __restrict__ out, uint32_t log_n) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >> log_n) return;
+    const uint64_t r = __brevll(i) >> (64 - log_n);
+    fe_store(out + r, fe_ldg(in + i));
+}
+__global__ void k_dit_stage(fe* data, uint32_t log_n, uint32_t lh, DevPow pw) {
+    const uint64_t pi = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (pi >> (log_n - 1)) return;
+    const uint64_t h = 1ull << lh, j = pi & (h - 1);
+    const uint64_t s0 = ((pi >> lh) << (lh + 1)) | j;
+    const fe w = pow2lvl(pw, j << (log_n - 1 - lh));                  // root^(j * n / (2h)) * R
+    const fe e = fe_load(data + s0), o = fe_montmul(fe_load(data + s0 + h), w);
+    fe_store(data + s0, fe_add(e, o));
+    fe_store(data + s0 + h, fe_sub(e, o));
+}
+// powers root^i * R for i < n with root of any order: the two-level table only needs exponent arithmetic, not root^n == 1
+static int ntt_literal_big(zkb_ctx* c, const fe& root, const fe* d_in, fe* d_out, uint32_t log_n) {
+    DevPow pw;
+    ZKB_TRY(get_pow_table(c, root, log_n, &pw));
+    const uint64_t n = 1ull << log_n;
+    { LaunchScope ls(c, K_ELEMENTWISE); k_bitrev_copy<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(d_in, d_out, log_n); }
+    for (uint32_t lh = 0; lh < log_n; lh++) {
+        LaunchScope ls(c, K_NTT_PASS);
+        k_dit_stage<<<(unsigned)((n / 2 + 255) / 256), 256, 0, c->stream>>>(d_out, log_n, lh, pw);
+    }
+    ZKB_CUDA(c, cudaGetLastError());
+    return 0;
+}
+
 static int poly_degree(const fe* p, size_t n) {   // polynomial.rs:46-63; -1 for the zero polynomial
     int d = -1;
     for (size_t i = 0; i < n; i++) if (!fe_is_zero(p[i])) d = (int)i;
@@ -786,9 +821,14 @@ static int poly_binop(zkb_ctx* c, bool divide, const uint8_t root_b[16], uint64_
                       const uint8_t* offset_b, const void* lhs, size_t n_lhs, const void* rhs,
                       size_t n_rhs, void* out, size_t* n_out) {
     if (!c || !root_b || !n_out || !out) return ZKB_ERR_ARG;
-    if (is_device_ptr(lhs) || is_device_ptr(rhs) || is_device_ptr(out))
-        return set_err(c, ZKB_ERR_ARG, "poly_mul/coset_div take host pointers");
     ZKB_CUDA(c, cudaSetDevice(c->device));
+    // the degrees are taken on the host (polynomial.rs:46-63 scans the coefficients): device operands are brought over first
+    std::vector<fe> hl, hr, hout;
+    void* out_dev = nullptr;
+    if (lhs && n_lhs && is_device_ptr(lhs)) { hl.resize(n_lhs); ZKB_CUDA(c, cudaMemcpyAsync(hl.data(), lhs, n_lhs * sizeof(fe), cudaMemcpyDeviceToHost, c->stream)); lhs = hl.data(); }
+    if (rhs && n_rhs && is_device_ptr(rhs)) { hr.resize(n_rhs); ZKB_CUDA(c, cudaMemcpyAsync(hr.data(), rhs, n_rhs * sizeof(fe), cudaMemcpyDeviceToHost, c->stream)); rhs = hr.data(); }
+    if (!hl.empty() || !hr.empty()) ZKB_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (is_device_ptr(out)) { out_dev = out; hout.resize(n_lhs + n_rhs + 1); out = hout.data(); }
     fe root = h_load(root_b);
     ZKB_TRY(check_root(c, root, root_order));
     const fe* L = (const fe*)lhs; const fe* R = (const fe*)rhs;
@@ -810,11 +850,19 @@ static int poly_binop(zkb_ctx* c, bool divide, const uint8_t root_b[16], uint64_
     // order-`order` root (:43-47); only the first `order` outputs are used.  Reproduced
     // literally (single-tile DIT), which needs the padded operand to fit one tile.
     const uint64_t nL = next_pow2_u64(n_lhs > order ? n_lhs : order), nR = next_pow2_u64(n_rhs > order ? n_rhs : order);
-    if (nL > order || nR > order) {
-        if (nL > (1ull << TILE_LOG) || nR > (1ull << TILE_LOG))
-            return set_err(c, ZKB_ERR_TOO_LONG, "operand with trailing zeros longer than the transform order %llu is only supported up to %u coefficients",
-                           (unsigned long long)order, 1u << TILE_LOG);
-    }
+    // forward transform of an operand: the factorised engine when its length is the transform order (root primitive for it), else
+    // the reference's loop literally - one tile up to 4096 values (ntt_exec's single-pass path), global-memory stages above
+    auto forward = [&](const fe* src, fe* dst, uint64_t n, const NttOpts& o) -> int {
+        if (n == 1) { ZKB_CUDA(c, cudaMemcpyAsync(dst, src, sizeof(fe), cudaMemcpyDeviceToDevice, c->stream)); return 0; }
+        if (n == order || n <= (1ull << TILE_LOG)) return ntt_exec(c, root, src, n, 0, dst, 0, 1, ilog2_u64(n), o);
+        fe* tmp = const_cast<fe*>(src);
+        if (o.has_scale) {                                               // scale(offset) first (ntt_arithmetics.rs:283-284), in place
+            DevPow sc;
+            ZKB_TRY(get_pow_table(c, o.scale_base, ilog2_u64(n), &sc));
+            { LaunchScope ls(c, K_ELEMENTWISE); k_scale<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(src, tmp, n, sc); }
+        }
+        return ntt_literal_big(c, root, tmp, dst, ilog2_u64(n));
+    };
     const uint32_t log_n = ilog2_u64(order);
     DevBuf buf;
     const size_t total = (size_t)(2 * nL + 2 * nR);
@@ -826,10 +874,8 @@ static int poly_binop(zkb_ctx* c, bool divide, const uint8_t root_b[16], uint64_
     ZKB_CUDA(c, cudaMemcpyAsync(dR, R, sizeof(fe) * n_rhs, cudaMemcpyHostToDevice, c->stream));
     NttOpts fwd;
     if (divide) { fwd.has_scale = true; fwd.scale_base = h_load(offset_b); }
-    if (nL == 1) ZKB_CUDA(c, cudaMemcpyAsync(eL, dL, sizeof(fe), cudaMemcpyDeviceToDevice, c->stream));
-    else ZKB_TRY(ntt_exec(c, root, dL, nL, 0, eL, 0, 1, ilog2_u64(nL), fwd));
-    if (nR == 1) ZKB_CUDA(c, cudaMemcpyAsync(eR, dR, sizeof(fe), cudaMemcpyDeviceToDevice, c->stream));
-    else ZKB_TRY(ntt_exec(c, root, dR, nR, 0, eR, 0, 1, ilog2_u64(nR), fwd));
+    ZKB_TRY(forward(dL, eL, nL, fwd));
+    ZKB_TRY(forward(dR, eR, nR, fwd));
     unsigned blocks = (unsigned)((order + 127) / 128);
     {
         LaunchScope ls(c, K_ELEMENTWISE);
@@ -854,6 +900,7 @@ static int poly_binop(zkb_ctx* c, bool divide, const uint8_t root_b[16], uint64_
     ZKB_CUDA(c, cudaMemcpyAsync(&hflag, flag, 4, cudaMemcpyDeviceToHost, c->stream));
     ZKB_CUDA(c, cudaStreamSynchronize(c->stream));
     if (divide && hflag) return set_err(c, ZKB_ERR_DIV_ZERO, "divide by zero");
+    if (out_dev) ZKB_CUDA(c, cudaMemcpy(out_dev, out, sizeof(fe) * keep, cudaMemcpyHostToDevice));
     *n_out = keep;
     return 0;
 }

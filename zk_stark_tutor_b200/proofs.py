@@ -81,6 +81,10 @@ def prove_hot_path(ctx, fri, shape, columns, combination, proof_stream):
         proof_stream.objects = None
         return list(top)
     finally:
+        try:                                   # torch's allocator does not know the context's own stream: drain it before the tensors go
+            ctx.sync()
+        except Exception:                      # noqa: BLE001 - the original error is the one to report
+            pass
         for h in trees:
             lib.zkb_merkle_free(h)
 
@@ -133,6 +137,10 @@ def prove_hot_path_batch(ctx, fri, shape, packed, proof_streams):
             p.objects = None
         return top.tolist()
     finally:
+        try:                                   # torch's allocator does not know the context's own stream: drain it before the tensors go
+            ctx.sync()
+        except Exception:                      # noqa: BLE001 - the original error is the one to report
+            pass
         for i in range(K * B - 1, -1, -1):           # tree 0 owns the shared arena: free it last
             if trees[i]:
                 lib.zkb_merkle_free(trees[i])

@@ -320,6 +320,10 @@ class Stark:
                 t.open_into(quad, proof_stream)
             return proof_stream.digest()
         finally:
+            try:                                   # torch's allocator does not know the context's own stream: drain it before the tensors go
+                ctx.sync()
+            except Exception:                      # noqa: BLE001 - the original error is the one to report
+                pass
             for t in trees:
                 t.close()
 
@@ -418,6 +422,12 @@ class Stark:
                 return [p.digest() for p in proof_streams]
             return [int(lib.zkb_ps_digest(p.h, None, 0)) for p in proof_streams]
         finally:
+            # tcw / cws / tq come from torch's caching allocator, which does not know the context's own stream: nothing queued on that
+            # stream may still touch them when they are released (error paths included)
+            try:
+                ctx.sync()
+            except Exception:      # noqa: BLE001 - the original error is the one to report
+                pass
             for i in range(K * B - 1, -1, -1):          # tree 0 owns the shared arena: free it last
                 if trees[i]:
                     lib.zkb_merkle_free(trees[i])
