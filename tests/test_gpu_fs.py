@@ -195,3 +195,26 @@ def test_batch_device_assembly_equals_host_assembly(ctx, log_n, ncc, B):
         assert top == dev[0][b]
         assert ps.digest() == dev[1][b], b
         tree.close()
+
+
+@pytest.mark.parametrize("log_n", [18, 19, 21, 22])
+def test_fused_ntt_leaf_pass_parity(ctx, log_n):
+    """ZKB_NTT_LEAF_FUSION=1: the LDE's last pass hashes its own output (k_ntt_rr_leaf) - same codeword, same roots, same stream
+    bytes as the two-kernel path (final pass widths 6, 7 and 8)."""
+    import torch
+    n = 1 << log_n
+    w = F.primitive_nth_root(n)
+    coeffs = cuda(C.synth(0xF00D + log_n, n // 4))
+    fri = zk.FRI(F.GENERATOR, w, n, 4, 64, ctx)
+    res = []
+    for fused in (False, True):
+        if fused:
+            os.environ["ZKB_NTT_LEAF_FUSION"] = "1"
+        try:
+            ps = zk.IndependentProofStream()
+            layers = fri.lde_commit(coeffs, ps)
+            res.append((ps.digest(), [layers.root(r) for r in range(len(layers))], hashlib.sha256(layers.codeword(0).tobytes()).hexdigest()))
+            layers.close()
+        finally:
+            os.environ.pop("ZKB_NTT_LEAF_FUSION", None)
+    assert res[0] == res[1]

@@ -311,7 +311,7 @@ int zkb_ctx_zero_copy_inputs(zkb_ctx* c, int enable) {
 }
 const char* zkb_kernel_name(int kernel_id) {
     static const char* names[K_COUNT] = {"k_pow_table", "k_ntt_pass", "k_elementwise", "k_leaf8<false>", "k_leaf8<true>",
-                                         "k_node8", "k_tree", "k_open", "k_fold", "k_gather3", "k_leaf1", "k_fri_tail"};
+                                         "k_node8", "k_tree", "k_open", "k_fold", "k_gather3", "k_leaf1", "k_fri_tail", "k_ntt_rr_leaf"};
     return (kernel_id >= 0 && kernel_id < K_COUNT) ? names[kernel_id] : nullptr;
 }
 

@@ -102,7 +102,7 @@ int set_err(zkb_ctx* c, int code, const char* fmt, ...);
 
 // kernel classes for zkb_ctx_profile_* (keep in sync with zkb_kernel_name)
 enum KernelId { K_POW_TABLE = 0, K_NTT_PASS = 1, K_ELEMENTWISE = 2, K_LEAF_TILE = 3, K_FOLD_LEAF_TILE = 4,
-                K_NODE_TILE = 5, K_MERKLE_SMALL = 6, K_OPEN = 7, K_FOLD = 8, K_GATHER = 9, K_LEAF1 = 10, K_FRI_TAIL = 11, K_COUNT = 12 };
+                K_NODE_TILE = 5, K_MERKLE_SMALL = 6, K_OPEN = 7, K_FOLD = 8, K_GATHER = 9, K_LEAF1 = 10, K_FRI_TAIL = 11, K_NTT_LEAF = 12, K_COUNT = 13 };
 
 // Brackets one launch with events when profiling is on; always counts the launch.
 struct LaunchScope {

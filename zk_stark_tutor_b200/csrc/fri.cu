@@ -126,7 +126,7 @@ void zkb_fri_layers_free(zkb_fri_layers* l) {
 // by the persistent tail kernel (fri_tail.cu); the roots are pushed to `dev_ps` afterwards (same bytes, same order).
 // Otherwise (`fs` callback: any foreign ProofStream) each round hands its root to the host as before.
 static int fri_commit_device_fs(zkb_ctx* c, zkb_fri_layers* L, const fe& omega_inv0, const DevPow& winv_tab,
-                                const std::vector<fe>& inv_offset, zkb_ps* ps);
+                                const std::vector<fe>& inv_offset, zkb_ps* ps, bool leaf3_done);
 
 static int fri_commit_impl(zkb_ctx* c, const zkb_fri_params* p, const void* codeword, const void* coeffs,
                            size_t n_coeffs, size_t n, zkb_fs_callback fs, void* user, zkb_fri_layers** out, zkb_ps* dev_ps = nullptr) {
@@ -160,6 +160,7 @@ static int fri_commit_impl(zkb_ctx* c, const zkb_fri_params* p, const void* code
     ZKB_CUDA(c, dev_alloc(c, &L->arena, arena_bytes));
     auto fail = [&](int rc) { dev_free(c, L->arena); dev_free(c, L->owned_cw0); L->arena = nullptr; L->owned_cw0 = nullptr; return rc; };
     DevBuf staged_coeffs;
+    bool leaf3_done = false;
     if (codeword && is_device_ptr(codeword)) {
         L->cw.push_back((const fe*)codeword);
     } else {
@@ -178,6 +179,11 @@ static int fri_commit_impl(zkb_ctx* c, const zkb_fri_params* p, const void* code
             NttOpts o;
             o.has_scale = true;
             o.scale_base = offset;
+            // opt-in (measured: no gain, see ntt.cu): the LDE's last pass hashes its own output, layer 0's level-3 nodes come out of the transform
+            if (L->layout[0].top >= 3 && ntt_can_fuse_leaves(ilog2_u64(n)) && getenv("ZKB_NTT_LEAF_FUSION") != nullptr) {
+                o.leaf3_out = (uint8_t*)L->arena + node_off[0] + L->layout[0].level_off[3] * 64;
+                leaf3_done = true;
+            }
             rc = ntt_exec(c, omega, (const fe*)d_coeffs, n_coeffs, 0, (fe*)L->owned_cw0, 0, 1, ilog2_u64(n), o);
             if (rc) return fail(rc);
         }
@@ -202,7 +208,7 @@ static int fri_commit_impl(zkb_ctx* c, const zkb_fri_params* p, const void* code
         for (uint64_t r = 0; r < rounds; r++) { inv_offset[r] = io; io = h_mul(io, io); }
     }
     if (dev_ps && rounds <= ZKB_FS_MAX_ROUNDS && getenv("ZKB_HOST_FS") == nullptr) {
-        rc = fri_commit_device_fs(c, L.get(), omega_inv0, winv_tab, inv_offset, dev_ps);
+        rc = fri_commit_device_fs(c, L.get(), omega_inv0, winv_tab, inv_offset, dev_ps, leaf3_done);
         if (rc) return fail(rc);
         *out = L.release();
         return 0;
@@ -218,7 +224,7 @@ static int fri_commit_impl(zkb_ctx* c, const zkb_fri_params* p, const void* code
         sig.seq = ++c->root_seq;
         const bool polled = len > 1;
         if (r == 0) {
-            rc = merkle_build_levels(c, L->cw[0], nullptr, len, tl, L->nodes[0], &sig);
+            rc = merkle_build_levels(c, L->cw[0], nullptr, len, tl, L->nodes[0], &sig, nullptr, leaf3_done);
         } else {
             FoldArgs f;
             f.cw = L->cw[r - 1]; f.next = (fe*)L->cw[r]; f.half = len;
@@ -258,7 +264,7 @@ static int fri_commit_impl(zkb_ctx* c, const zkb_fri_params* p, const void* code
 #define ZKB_PINNED_TAIL_OUT 65536u    // c->pinned: roots + last codeword written by the tail kernel
 
 static int fri_commit_device_fs(zkb_ctx* c, zkb_fri_layers* L, const fe& omega_inv0, const DevPow& winv_tab,
-                                const std::vector<fe>& inv_offset, zkb_ps* ps) {
+                                const std::vector<fe>& inv_offset, zkb_ps* ps, bool leaf3_done) {
     const uint64_t rounds = L->rounds;
     ZKB_TRY(ensure_fs_dev(c, 1));
     FsDev* fs = (FsDev*)c->fs_dev;
@@ -283,7 +289,7 @@ static int fri_commit_device_fs(zkb_ctx* c, zkb_fri_layers* L, const fe& omega_i
         FsHook hook;
         hook.fs = fs; hook.round = (uint32_t)r; hook.want_alpha = r + 1 < rounds;
         if (r == 0) {
-            ZKB_TRY(merkle_build_levels(c, L->cw[0], nullptr, L->len[0], L->layout[0], L->nodes[0], nullptr, &hook));
+            ZKB_TRY(merkle_build_levels(c, L->cw[0], nullptr, L->len[0], L->layout[0], L->nodes[0], nullptr, &hook, leaf3_done));
         } else {
             FoldArgs f;
             f.cw = L->cw[r - 1]; f.next = (fe*)L->cw[r]; f.half = L->len[r];

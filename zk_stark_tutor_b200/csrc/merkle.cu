@@ -490,7 +490,7 @@ int wait_root(zkb_ctx* c, const RootSignal& s, uint8_t root_out[64]) {
 }
 
 int merkle_build_levels(zkb_ctx* c, const fe* vals, const FoldArgs* fold, uint64_t n,
-                        const TreeLayout& L, uint8_t* nodes, const RootSignal* signal, const FsHook* fs) {
+                        const TreeLayout& L, uint8_t* nodes, const RootSignal* signal, const FsHook* fs, bool leaf3_done) {
     const uint32_t log_n = L.log_n;
     TopArgs a;
     memset(&a, 0, sizeof(a));
@@ -523,7 +523,7 @@ int merkle_build_levels(zkb_ctx* c, const fe* vals, const FoldArgs* fold, uint64
     if (cfg < 0) { const char* e = getenv("ZKB_LEAF_CFG"); cfg = e ? atoi(e) : 0; }
     FoldArgs fa;
     if (fold) fa = *fold; else memset(&fa, 0, sizeof(fa));
-    {
+    if (!leaf3_done) {
         LaunchScope ls(c, fold ? K_FOLD_LEAF_TILE : K_LEAF_TILE);
 #define ZKB_LEAF_LAUNCH(T, M)                                                                                   \
         do {                                                                                                    \

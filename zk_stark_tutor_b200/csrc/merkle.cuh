@@ -56,8 +56,10 @@ struct RootSignal {
     volatile uint32_t* host_flag;
     uint32_t seq;
 };
+// leaf3_done: the level-3 nodes are already in place (the LDE's last pass hashed them, ntt.cu k_ntt_rr_leaf): start above them.
 int merkle_build_levels(zkb_ctx* c, const fe* vals, const FoldArgs* fold, uint64_t n,
-                        const TreeLayout& layout, uint8_t* nodes, const RootSignal* signal = nullptr, const FsHook* fs = nullptr);
+                        const TreeLayout& layout, uint8_t* nodes, const RootSignal* signal = nullptr, const FsHook* fs = nullptr,
+                        bool leaf3_done = false);
 
 // Batched small trees (n <= 2^ZKB_TREE_LEAF_LOG, i.e. layout.top == 0): `batch` independent instances with
 // identical layouts, instance b = blockIdx.y working on buffers offset by b * stride.  One leaf launch and one

@@ -24,10 +24,12 @@
 // to N) is never materialised: loads beyond n_in read as zero, and the leading DIT
 // stages whose odd inputs are all zero are replaced by a broadcast (2 of 24 stages for
 // ef = 4).  The coset scaling c_i*offset^i of the LDE is fused into the pass-1 load.
+#include <stdlib.h>
 #include <string.h>
 #include <vector>
 #include "ctx.hpp"
 #include "ntt.cuh"
+#include "merkle_dev.cuh"
 
 namespace zkb {
 
@@ -339,6 +341,87 @@ __global__ void __launch_bounds__(ZKB_NTT_THREADS, 2) k_ntt_rr(const PassParams 
     }
 }
 
+// ---- the LAST pass of an LDE fused with the layer-0 leaf hashing of the Merkle commitment ------------------------------------
+// ntt_arithmetics.rs:161-170 (fast_coset_evaluate) -> merkle_root.rs:21-32 (commit), stark.rs:373-381 / fri.rs:136.  The pass is
+// bound by the FMA-heavy pipe (IMAD.WIDE), the hashing by the ALU pipe; as two kernels they use one pipe at a time.  Here a CTA
+// transforms its tile exactly like k_ntt_rr<.., .., true>, leaves the 4096 outputs in shared memory (and writes them to the codeword
+// as before), and then every thread hashes two groups of 8 CONSECUTIVE outputs (a tile's outputs are runs of B >= 16 consecutive
+// values) down to their level-3 nodes, as k_leaf8 does.  With two CTAs per SM in different phases, the multiplications of one
+// overlap the hashing of the other, and the codeword is not read back from HBM for hashing.
+template <int LR1, int LR2>
+__global__ void __launch_bounds__(ZKB_NTT_THREADS, 2) k_ntt_rr_leaf(const PassParams p, uint8_t* __restrict__ out3) {
+    extern __shared__ uint4 smem_raw[];
+    constexpr uint32_t R1 = 1u << LR1, R2 = 1u << LR2, S = R1 * R2;
+    constexpr uint32_t ITERS = 16 / R2;                     // (R1 * B) / 256 with S * B = 4096
+    fe* sm = reinterpret_cast<fe*>(smem_raw);
+    const uint32_t B = 1u << p.log_b, pitch = B + 1;
+    fe* tws = sm + (size_t)S * pitch;                      // w_S^j * R, j < S
+    const uint32_t tid = threadIdx.x;
+    uint64_t in_base, out_base;
+    uint32_t inner;
+    tile_origin(p, in_base, out_base, inner);
+    const fe* in = p.in;
+    fe* out = p.out + out_base;
+    for (uint32_t j = tid; j < S; j += ZKB_NTT_THREADS) tws[j] = fe_ldg(p.tw_s + j);
+    __syncthreads();
+    // ---- step 1 (as k_ntt_rr, transposed load)
+    for (uint32_t d = tid; d < R2 * B; d += ZKB_NTT_THREADS) {
+        const uint32_t s0 = d & (R2 - 1), b = d >> LR2;
+        fe x[R1];
+#pragma unroll
+        for (uint32_t s1 = 0; s1 < R1; s1++) x[s1] = fe_ldg(in + in_base + (uint64_t)(R2 * s1 + s0) * p.ld_s + (uint64_t)b * p.ld_b);
+        dft_dif<LR1>(x, tws, R2);
+#pragma unroll
+        for (uint32_t i = 0; i < R1; i++) {
+            const uint32_t ka = brev_c<LR1>(i);
+            fe y = x[i];
+            if (ka != 0 && s0 != 0) y = mm(y, tws[s0 * ka]);
+            sm[(size_t)(ka * R2 + s0) * pitch + b] = y;
+        }
+    }
+    __syncthreads();
+    // ---- step 3: all outputs of this thread stay in registers until every thread has read its inputs
+    fe y[ITERS][R2];
+#pragma unroll
+    for (uint32_t it = 0; it < ITERS; it++) {
+        const uint32_t d = tid + it * ZKB_NTT_THREADS;
+        const uint32_t ka = d >> p.log_b, b = d & (B - 1);
+        fe x[R2];
+#pragma unroll
+        for (uint32_t s0 = 0; s0 < R2; s0++) x[s0] = sm[(size_t)(ka * R2 + s0) * pitch + b];
+        dft_dif<LR2>(x, tws, R1);
+#pragma unroll
+        for (uint32_t kb = 0; kb < R2; kb++) {
+            fe v = x[brev_c<LR2>(kb)];
+            if (p.has_post) v = mm(v, p.post);
+            y[it][kb] = v;
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (uint32_t it = 0; it < ITERS; it++) {
+        const uint32_t d = tid + it * ZKB_NTT_THREADS;
+        const uint32_t ka = d >> p.log_b, b = d & (B - 1);
+#pragma unroll
+        for (uint32_t kb = 0; kb < R2; kb++) {
+            const uint32_t k = ka + R1 * kb;
+            fe_store(out + (uint64_t)k * p.st_k + b, y[it][kb]);     // the codeword (st_b == 1)
+            sm[(size_t)k * pitch + b] = y[it][kb];                   // ... and the tile, run k = outputs [k * st_k, k * st_k + B)
+        }
+    }
+    __syncthreads();
+    // ---- leaf hashing: 512 groups of 8 consecutive outputs per tile, two per thread -> level-3 nodes
+    const uint32_t gshift = p.log_b - 3;                             // groups per run = B / 8
+#pragma unroll 1
+    for (uint32_t g = tid; g < 512; g += ZKB_NTT_THREADS) {
+        const uint32_t k = g >> gshift, h8 = (g & ((1u << gshift) - 1)) << 3;
+        const fe* src = sm + (size_t)k * pitch + h8;
+        uint64_t h[8];
+        reduce8([&](int j, uint64_t* o) { fe v = src[j]; b2_leaf_call(&v, o); }, h);
+        g_store_digest(out3, (out_base + (uint64_t)k * p.st_k + h8) >> 3, h);
+    }
+}
+
 template <int LR1, int LR2>
 static int launch_rr_t(zkb_ctx* c, const PassParams& p, uint32_t tiles, uint32_t batch) {
     const size_t S = (size_t)1 << (LR1 + LR2), B = (size_t)1 << p.log_b;
@@ -364,7 +447,31 @@ int ntt_device_init(zkb_ctx* c) {
     ZKB_CUDA(c, (rr_attrs<4, 3>()));
     ZKB_CUDA(c, (rr_attrs<3, 3>()));
     ZKB_CUDA(c, (rr_attrs<3, 2>()));
+    ZKB_CUDA(c, cudaFuncSetAttribute(k_ntt_rr_leaf<4, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    ZKB_CUDA(c, cudaFuncSetAttribute(k_ntt_rr_leaf<4, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    ZKB_CUDA(c, cudaFuncSetAttribute(k_ntt_rr_leaf<3, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     ZKB_CUDA(c, cudaFuncSetAttribute(k_ntt_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    return 0;
+}
+template <int LR1, int LR2>
+static int launch_rr_leaf_t(zkb_ctx* c, const PassParams& p, uint32_t tiles, uint8_t* out3) {
+    const size_t S = (size_t)1 << (LR1 + LR2), B = (size_t)1 << p.log_b;
+    const size_t smem = (S * (B + 1) + S) * sizeof(fe);
+    LaunchScope ls(c, K_NTT_LEAF);
+    k_ntt_rr_leaf<LR1, LR2><<<tiles, ZKB_NTT_THREADS, smem, c->stream>>>(p, out3);
+    return 0;
+}
+// the final pass of a single transform + layer-0 leaf hashing (log_s in 6..8, tile = 4096 values, no exchange / batch)
+static int launch_pass_rr_leaf(zkb_ctx* c, const PassParams& p, uint32_t tiles, uint8_t* out3) {
+    int rc;
+    switch (p.log_s) {
+        case 8: rc = launch_rr_leaf_t<4, 4>(c, p, tiles, out3); break;
+        case 7: rc = launch_rr_leaf_t<4, 3>(c, p, tiles, out3); break;
+        case 6: rc = launch_rr_leaf_t<3, 3>(c, p, tiles, out3); break;
+        default: return set_err(c, ZKB_ERR_ARG, "internal: fused final pass needs 6 <= log_s <= 8");
+    }
+    ZKB_TRY(rc);
+    ZKB_CUDA(c, cudaGetLastError());
     return 0;
 }
 // register-radix pass for log_s in 5..8
@@ -527,9 +634,24 @@ int ntt_exec(zkb_ctx* c, fe root, const fe* d_in, size_t n_in, size_t in_stride,
             for (uint32_t q = 0; q < x.n_peers && q < ZKB_NTT_MAX_PEERS; q++) p.peer[q] = x.peer[q];
         }
         ZKB_TRY(tw_table(wdt[f], &p.tw_s));
-        ZKB_TRY(launch_pass_rr(c, p, (uint32_t)(outer * p.inner_count), (uint32_t)batch));
+        if (o.leaf3_out && batch == 1 && !o.exchange && wdt[f] >= 6 && wdt[f] + p.log_b == TILE_LOG && p.log_b >= 4)
+            ZKB_TRY(launch_pass_rr_leaf(c, p, (uint32_t)(outer * p.inner_count), o.leaf3_out));
+        else if (o.leaf3_out)
+            return set_err(c, ZKB_ERR_ARG, "internal: this transform shape has no fused leaf-hashing pass (ntt_can_fuse_leaves)");
+        else
+            ZKB_TRY(launch_pass_rr(c, p, (uint32_t)(outer * p.inner_count), (uint32_t)batch));
     }
     return 0;
+}
+
+// does ntt_exec's final pass for 2^log_n values come in the fused-with-leaf-hashing variant?
+bool ntt_can_fuse_leaves(uint32_t log_n) {
+    if (log_n <= TILE_LOG + 5) return false;                              // (trees of <= 2^17 leaves are hashed by the latency kernels anyway)
+    const int passes = log_n <= 16 ? 2 : log_n <= 24 ? 3 : 4;
+    uint32_t left = log_n, w0 = 0, wl = 0;
+    for (int i = 0; i < passes; i++) { uint32_t w = (left + (passes - i) - 1) / (passes - i); if (i == 0) w0 = w; wl = w; left -= w; }
+    const uint32_t lb = TILE_LOG - wl;
+    return wl >= 6 && wl <= 8 && lb <= w0 && lb >= 4;
 }
 
 // ---- cross-rank stage of the four-step NTT: `blk` interleaved G-point transforms, element n1 of column i at in[n1 * blk + i],

@@ -21,7 +21,11 @@ struct NttOpts {
     bool inverse = false;     // use root^-1 and multiply by n^-1 (ntt.rs:51-68)
     bool no_post = false;     // inverse without the n^-1 factor (the caller applies it later)
     const NttExchange* exchange = nullptr;   // batch == 1, 2^13 <= n only
+    // batch == 1, ntt_can_fuse_leaves(log_n): the last pass also hashes the output as Merkle leaves (8 leaf hashes + 7 nodes per
+    // group of 8 consecutive values) and writes the level-3 nodes here (n / 8 x 64 bytes) - what k_leaf8<false> would produce
+    uint8_t* leaf3_out = nullptr;
 };
+bool ntt_can_fuse_leaves(uint32_t log_n);
 
 // d_in / d_out are device pointers; 2^log_n is the transform length; n_in <= 2^log_n values
 // are read per column (the rest are zero); `batch` columns at the given element strides.
