@@ -272,7 +272,7 @@ def probe_int_pipes(local):
     out = {}
     try:
         pl = ctypes.CDLL(os.path.join(os.path.dirname(_lib.LIB_PATH), "libzkb200_probe.so"))
-        for kind, name in ((0, "alu"), (1, "imad"), (3, "prmt"), (40, "imad_wide"), (6, "blake2b_Gcompress_per_s")):
+        for kind, name in ((0, "alu"), (1, "imad"), (3, "prmt"), (40, "imad_wide_accumulate"), (43, "imad_wide"), (6, "blake2b_Gcompress_per_s")):
             r, pm = ctypes.c_double(0), ctypes.c_double(0)
             if pl.zkb_probe_int_pipe(local, kind, ctypes.byref(r), ctypes.byref(pm)) == 0:
                 out[name] = r.value / (1e9 if kind == 6 else 1e12)
@@ -958,6 +958,10 @@ def ntt_record(args, env, four, steps, sub=False):
         # the multiplication as built: 16 limb products + 4 reduction products + 1 low product, all 32x32->64 (IMAD.WIDE)
         peak_mul = probe["imad_wide"] * 1e12 / 21
         int_pipe.update({"imad_Tops_measured": probe.get("imad"), "imad_wide_Tops_measured": probe["imad_wide"],
+                         "imad_wide_accumulate_Tops_measured": probe.get("imad_wide_accumulate"),
+                         "probe_note": "imad_wide: a loop of IMAD.WIDE.U32 Rd, Ra, Rb, RZ and nothing else (csrc/probe.cu kind 43, SASS histogram in profiles/); "
+                                       "imad_wide_accumulate (kind 40, round 1's denominator): mad.wide with a 64-bit addend, which ptxas 12.9 splits into "
+                                       "IMAD.WIDE + IADD3 + IADD3.X on sm_100a",
                          "field_mul_per_s_at_imad_wide_peak": peak_mul, "frac_of_imad_wide_roofline": int_pipe["field_mul_per_s"] / peak_mul,
                          "note": "algorithmic multiplications ((N/2) log2 N per transform, + N for the inverse scaling) against the measured "
                                  "IMAD.WIDE issue rate / 21; the pass executes ~1.25x the algorithmic count (inter-pass twiddles)"})

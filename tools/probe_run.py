@@ -10,7 +10,8 @@ NAMES = {0: "alu (VIADD+LOP3)", 1: "imad", 2: "alu+imad", 3: "prmt", 4: "shf", 5
          20: "LOP3 2 regs", 21: "LOP3 3 regs", 22: "IADD3 3 regs", 23: "IADD3 2 regs", 24: "PRMT 2 regs",
          25: "LOP3(2r)+IMAD(3r)", 26: "LOP3 2r + IADD3 2r", 27: "SHF 2 regs", 28: "IMAD 3 regs",
          30: "IMAD.HI 2 regs", 31: "IMAD.WIDE", 32: "IMAD reg*uniform+reg", 33: "IMAD.HI reg*uniform",
-         40: "IMAD.WIDE reg*reg+acc64", 41: "IMAD.WIDE reg*uniform+acc64"}
+         40: "IMAD.WIDE reg*reg+acc64", 41: "IMAD.WIDE reg*uniform+acc64", 42: "IMAD.WIDE other-acc*reg+acc64",
+         43: "IMAD.WIDE products only"}
 
 
 def main():

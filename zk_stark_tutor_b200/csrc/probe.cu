@@ -164,7 +164,8 @@ static int run_r(int device, double* rate, double* ms_out) {
 }
 
 // IMAD.WIDE rate: 8 independent 64-bit accumulators, acc = a * b + acc (kind 40: b register,
-// kind 41: b = kernel-parameter constant 2^8, the shape the rotate-by-multiply trick needs).
+// kind 41: b = kernel-parameter constant 2^8, the shape the rotate-by-multiply trick needs; kind 42: the multiplicand
+// is the low word of another accumulator, so nothing is loop-invariant and nothing aliases the addend).
 template <int KIND>
 __global__ void __launch_bounds__(256) k_probe_wide(unsigned long long* out, uint32_t ub, int iters) {
     unsigned long long acc[CH];
@@ -181,7 +182,10 @@ __global__ void __launch_bounds__(256) k_probe_wide(unsigned long long* out, uin
 #pragma unroll
             for (int i = 0; i < CH; i++) {
                 const int j = (i + 1 + (u & 3)) % CH;
-                if (KIND == 40) asm volatile("{ .reg .u32 lo; cvt.u32.u64 lo, %0; mad.wide.u32 %0, lo, %1, %0; }" : "+l"(acc[i]) : "r"(b[j]));
+                if (KIND == 43) {            // products only: t[i] = lo(t[i]) * hi(t[i+1]); every half of every result is an operand later
+                    asm volatile("{ .reg .u32 l, h, x; mov.b64 {l, x}, %0; mov.b64 {x, h}, %1; mul.wide.u32 %0, l, h; }" : "+l"(acc[i]) : "l"(acc[(i + 1) % CH]));
+                } else if (KIND == 42) asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc[i]) : "r"((uint32_t)acc[j]), "r"(b[j]));   // multiplicand = low word of ANOTHER accumulator
+                else if (KIND == 40) asm volatile("{ .reg .u32 lo; cvt.u32.u64 lo, %0; mad.wide.u32 %0, lo, %1, %0; }" : "+l"(acc[i]) : "r"(b[j]));
                 else asm volatile("{ .reg .u32 lo; cvt.u32.u64 lo, %0; mad.wide.u32 %0, lo, %1, %0; }" : "+l"(acc[i]) : "r"(ub));
             }
         }
@@ -342,6 +346,8 @@ extern "C" int zkb_probe_int_pipe(int device, int kind, double* lane_ops_per_s, 
         case 33: return run_r<33>(device, lane_ops_per_s, ms_out);
         case 40: return run_wide<40>(device, lane_ops_per_s, ms_out);
         case 41: return run_wide<41>(device, lane_ops_per_s, ms_out);
+        case 42: return run_wide<42>(device, lane_ops_per_s, ms_out);     // multiplicand from another accumulator: ptxas still emits IMAD.WIDE(.., RZ) + IADD3 + IADD3.X
+        case 43: return run_wide<43>(device, lane_ops_per_s, ms_out);     // products only: the SASS loop is IMAD.WIDE.U32 and nothing else
         default: break;
     }
     int sms = 0;
