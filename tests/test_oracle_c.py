@@ -100,3 +100,23 @@ def test_fastfri_matches_literal_restatement():
         assert top1 == top2
         assert ps1.digest() == ps2.digest()
         assert fri.verify(ps2, []) is None
+
+
+def test_bench_digest_file_is_what_the_oracle_computes():
+    """tests/golden/bench_digests.json (bench.py's pre-timing parity checks and the full-size GPU tests rely on it) against the oracle run
+    here, at the sizes that take seconds: configs[2] at 2^16 / 2^18 and the configs[4] checksums at 2^20."""
+    import hashlib
+    import json
+    import os
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, os.path.join(root, "tests"))
+    sys.path.insert(0, os.path.join(root, "tools"))
+    import make_bench_digests as M
+    from golden_ntt import check_against_golden_ntt
+    gold = json.load(open(os.path.join(root, "tests", "golden", "bench_digests.json")))
+    for log_n in (16, 18):
+        assert M.commit_digest(log_n, M.SEED) == gold["configs2"][str(log_n)]
+    n = 1 << 20
+    check_against_golden_ntt(C.ntt(F.primitive_nth_root(n), C.synth(M.SEED_NTT, n)), 20)
+    assert M.checksums(C.synth(1, 1000), first_index=5, step=3)["sum_lo"] == int(C.synth(1, 1000)[:, 0].sum(dtype="uint64"))
