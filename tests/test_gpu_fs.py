@@ -103,20 +103,26 @@ def test_device_fs_commit_vs_oracle(ctx, log_n, pre):
 
 @pytest.mark.parametrize("log_n", [12, 16, 18, 20])
 def test_device_fs_equals_host_hop_path(ctx, log_n):
-    """Same call with ZKB_HOST_FS=1 (one host hop per round, the foreign-stream path): identical proof bytes."""
+    """Same call with ZKB_HOST_FS=1 (one host hop per round, the foreign-stream path) and with ZKB_HOST_ASSEMBLY=1 (query-phase objects
+    framed on the host from raw paths instead of by k_open_wire / k_leafs_wire; pruned trees above 2^17 leaves): identical proof bytes,
+    also for the Value + Path openings of zkb_merkle_open_ps."""
     n, w, cw = _codeword(log_n)
     fri = zk.FRI(F.GENERATOR, w, n, 4, 64, ctx)
+    idx = (ctypes.c_uint64 * 9)(0, 1, n - 1, n // 2, n // 2 - 1, 12345 % n, 777 % n, n // 3, 5)
     d = []
-    for host_fs in (False, True):
-        if host_fs:
-            os.environ["ZKB_HOST_FS"] = "1"
+    for env in ({}, {"ZKB_HOST_FS": "1"}, {"ZKB_HOST_FS": "1", "ZKB_HOST_ASSEMBLY": "1"}, {"ZKB_HOST_ASSEMBLY": "1"}):
+        os.environ.update(env)
         try:
             ps = zk.IndependentProofStream()
             top = fri.prove(cuda(cw), ps)
+            tree = zk.MerkleTree(cuda(cw), ctx)
+            ctx.check(ctx.lib.zkb_merkle_open_ps(tree.h, idx, 9, ps.h))
+            tree.close()
             d.append((top, ps.digest()))
         finally:
-            os.environ.pop("ZKB_HOST_FS", None)
-    assert d[0] == d[1]
+            for k in env:
+                os.environ.pop(k, None)
+    assert d[0] == d[1] == d[2] == d[3]
 
 
 @pytest.mark.parametrize("ncc,ef", [(1, 4), (2, 2), (4, 4), (16, 8), (64, 4), (200, 4)])

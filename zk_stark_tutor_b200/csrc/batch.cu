@@ -247,7 +247,7 @@ static int zkb_fri_prove_batch_impl(zkb_ctx* c, const zkb_fri_params* p, const v
     if (bad) return set_err(c, ZKB_ERR_ARG, "sample_indices failed");
     // ---- query phase (fri.rs:174-208, 234-246)
     bool wire = !host_path;
-    for (uint64_t r = 0; r < R; r++) if (lay[r].log_n < 1 || lay[r].log_n > 17) wire = false;
+    for (uint64_t r = 0; r < R; r++) if (lay[r].log_n < 1 || lay[r].log_n > 30) wire = false;
     if (wire) {
         // The device writes the finished objects: per instance ONE contiguous segment [round 0: ncc Leafs, ncc x (Path a, Path b, Path c)]
         // [round 1: ...] ... in wire format (k_leafs_wire, k_open_wire), one D2H for the whole batch, one append per proof stream.
@@ -375,7 +375,7 @@ static int zkb_merkle_open_ps_batch_impl(zkb_tree* const* trees, size_t count, c
     for (size_t i = 0; i < count * k; i++)
         if (idx[i] >= n) return set_err(c, ZKB_ERR_INDEX, "cannot open invalid index %llu", (unsigned long long)idx[i]);
     ZKB_CUDA(c, cudaSetDevice(c->device));
-    if (getenv("ZKB_HOST_ASSEMBLY") == nullptr && trees[0]->layout.log_n >= 1 && trees[0]->layout.log_n <= 17) {
+    if (getenv("ZKB_HOST_ASSEMBLY") == nullptr && trees[0]->layout.log_n >= 1 && trees[0]->layout.log_n <= 30) {
         // device-side framing: record (Value, Path) s of tree i at its final position inside its proof's segment; trees that share a
         // proof stream append in increasing tree order (stark.rs:546-560 loops index-major per codeword in the order of the commits)
         const uint64_t rec = 25 + 9 + 72ull * trees[0]->layout.log_n;

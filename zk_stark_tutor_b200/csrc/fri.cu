@@ -481,6 +481,53 @@ static int zkb_fri_prove_body(zkb_ctx* c, const zkb_fri_params* p, const void* c
     if (zkb_fri_sample_indices(seed, 32, L->len[1], L->len[R - 1], ncc, top_indices_out) != 0)
         return set_err(c, ZKB_ERR_ARG, "sample_indices failed");
     std::vector<uint64_t> idx(top_indices_out, top_indices_out + ncc);
+    bool wire = getenv("ZKB_HOST_ASSEMBLY") == nullptr && ncc > 0;
+    for (uint64_t r = 0; r < R; r++) if (L->layout[r].log_n < 1 || L->layout[r].log_n > 30) wire = false;
+    if (wire) {
+        // The query phase as finished objects (fri.rs:174-208): for every layer pair ncc Leafs, then ncc x (Path a, Path b, Path c), written by
+        // the opening kernels at their offsets in the proof (merkle.cu k_leafs_wire / k_open_wire); all rounds queued back to back,
+        // ONE copy to the host, ONE append to the proof stream.
+        std::vector<uint64_t> base(R, 0);
+        uint64_t seg = 0;
+        for (uint64_t r = 0; r + 1 < R; r++) {
+            base[r] = seg;
+            seg += ncc * 57 + ncc * (2 * (9 + 72ull * L->layout[r].log_n) + (9 + 72ull * L->layout[r + 1].log_n));
+        }
+        const size_t per_round = ncc * 3;
+        std::vector<uint64_t> hidx((R - 1) * per_round + 1);
+        for (uint64_t r = 0; r + 1 < R; r++) {
+            const uint64_t half = L->len[r] / 2;
+            for (auto& i : idx) i %= half;                   // fri.rs:234-237
+            uint64_t* ab = hidx.data() + r * per_round;
+            uint64_t* cc = ab + 2 * ncc;
+            for (size_t q = 0; q < ncc; q++) { ab[2 * q] = idx[q]; ab[2 * q + 1] = idx[q] + half; cc[q] = idx[q]; }
+        }
+        hidx.back() = 0;                                     // y_off of the single instance
+        DevBuf q;
+        const size_t idx_bytes = (hidx.size() * 8 + 255) & ~(size_t)255;
+        ZKB_TRY(q.alloc(c, idx_bytes + seg + 16));
+        uint64_t* d_idx = (uint64_t*)q.p;
+        uint8_t* d_wire = (uint8_t*)q.p + idx_bytes;
+        const uint64_t* d_yoff = d_idx + (R - 1) * per_round;
+        ZKB_CUDA(c, cudaMemcpyAsync(d_idx, hidx.data(), hidx.size() * 8, cudaMemcpyHostToDevice, c->stream));
+        for (uint64_t r = 0; r + 1 < R; r++) {
+            const uint64_t half = L->len[r] / 2;
+            const uint64_t pc = 9 + 72ull * L->layout[r].log_n, pn = 9 + 72ull * L->layout[r + 1].log_n, trip = 2 * pc + pn;
+            const uint64_t* d_ab = d_idx + r * per_round;
+            const uint64_t* d_c = d_ab + 2 * ncc;
+            ZKB_TRY(fri_leafs_wire_batch(c, L->cw[r], 0, L->cw[r + 1], 0, half, d_c, ncc, 1, d_wire, d_yoff, base[r]));
+            ZKB_TRY(merkle_open_wire_batch(c, L->cw[r], L->layout[r], L->nodes[r], d_ab, 2 * ncc, 1, 0, 0, d_wire, d_yoff, 2, base[r] + ncc * 57, trip, pc, false));
+            ZKB_TRY(merkle_open_wire_batch(c, L->cw[r + 1], L->layout[r + 1], L->nodes[r + 1], d_c, ncc, 1, 0, 0, d_wire, d_yoff, 1,
+                                           base[r] + ncc * 57 + 2 * pc, trip, 0, false));
+        }
+        uint8_t* hw = nullptr;
+        ZKB_TRY(host_scratch_reserve(c, 1, seg, &hw));
+        ZKB_CUDA(c, cudaMemcpyAsync(hw, d_wire, seg, cudaMemcpyDeviceToHost, c->stream));
+        ZKB_CUDA(c, cudaStreamSynchronize(c->stream));
+        ps->body.insert(ps->body.end(), hw, hw + seg);
+        ps->has_field = true;                                // Leafs carry field elements
+        return 0;
+    }
     for (uint64_t r = 0; r + 1 < R; r++) {
         const uint64_t half = L->len[r] / 2;
         for (auto& i : idx) i %= half;                       // fri.rs:234-237

@@ -299,7 +299,7 @@ struct OpenWireArgs {
     uint64_t base, stride_hi, stride_lo;
     uint32_t with_value;
 };
-#define ZKB_WIRE_MAX_DEPTH 17
+#define ZKB_WIRE_MAX_DEPTH 30
 #define ZKB_WIRE_REC_BYTES (16 + 25 + 9 + ZKB_WIRE_MAX_DEPTH * 72 + 16)
 __device__ __forceinline__ void wire_put_be64(uint8_t* p, uint64_t v, uint32_t lane) {
     if (lane < 8) p[lane] = (uint8_t)(v >> (56 - 8 * lane));
@@ -727,7 +727,7 @@ int zkb_merkle_open(zkb_tree* t, const uint64_t* idx, size_t k, uint8_t* paths_o
 
 // stark.rs:546-560: for every opened index push Value(codeword[i]) then Path(open(i)); one batched
 // opening + one D2H instead of k tree rebuilds.
-int zkb_merkle_open_ps(zkb_tree* t, const uint64_t* idx, size_t k, zkb_ps* ps) {
+static int zkb_merkle_open_ps_body(zkb_tree* t, const uint64_t* idx, size_t k, zkb_ps* ps) {
     if (!t || !ps || (k && !idx)) return ZKB_ERR_ARG;
     zkb_ctx* c = t->ctx;
     if (t->n < 2) return set_err(c, ZKB_ERR_INDEX, "open on a 1-leaf tree (the reference recurses forever)");
@@ -736,6 +736,26 @@ int zkb_merkle_open_ps(zkb_tree* t, const uint64_t* idx, size_t k, zkb_ps* ps) {
     if (k == 0) return 0;
     ZKB_CUDA(c, cudaSetDevice(c->device));
     const size_t depth = t->layout.log_n, path_bytes = depth * 64;
+    if (getenv("ZKB_HOST_ASSEMBLY") == nullptr && depth >= 1 && depth <= ZKB_WIRE_MAX_DEPTH) {
+        // objects framed by the opening kernel (k_open_wire): one copy, one append
+        const uint64_t rec = 25 + 9 + 72ull * depth;
+        std::vector<uint64_t> hidx(idx, idx + k);
+        hidx.push_back(0);                                                   // y_off of the single tree
+        DevBuf wb;
+        const size_t ib = (hidx.size() * 8 + 255) & ~(size_t)255;
+        ZKB_TRY(wb.alloc(c, ib + k * rec + 16));
+        uint64_t* d_i = (uint64_t*)wb.p;
+        uint8_t* d_wire = (uint8_t*)wb.p + ib;
+        ZKB_CUDA(c, cudaMemcpyAsync(d_i, hidx.data(), hidx.size() * 8, cudaMemcpyHostToDevice, c->stream));
+        ZKB_TRY(merkle_open_wire_batch(c, t->vals, t->layout, t->nodes, d_i, k, 1, 0, 0, d_wire, d_i + k, 1, 0, rec, 0, true));
+        uint8_t* hw = nullptr;
+        ZKB_TRY(host_scratch_reserve(c, 1, k * rec, &hw));
+        ZKB_CUDA(c, cudaMemcpyAsync(hw, d_wire, k * rec, cudaMemcpyDeviceToHost, c->stream));
+        ZKB_CUDA(c, cudaStreamSynchronize(c->stream));
+        ps->body.insert(ps->body.end(), hw, hw + k * rec);
+        ps->has_field = true;
+        return 0;
+    }
     DevBuf buf;
     const size_t idx_bytes = (k * 8 + 63) & ~(size_t)63, val_bytes = (k * 16 + 63) & ~(size_t)63;
     ZKB_TRY(buf.alloc(c, idx_bytes + val_bytes + k * path_bytes));
@@ -754,6 +774,11 @@ int zkb_merkle_open_ps(zkb_tree* t, const uint64_t* idx, size_t k, zkb_ps* ps) {
         zkb_ps_push_path(ps, host.data() + val_bytes + i * path_bytes, depth);
     }
     return 0;
+}
+
+int zkb_merkle_open_ps(zkb_tree* t, const uint64_t* idx, size_t k, zkb_ps* ps) {
+    if (!t) return ZKB_ERR_ARG;
+    ZKB_ABI_GUARD(t->ctx, return zkb_merkle_open_ps_body(t, idx, k, ps);)
 }
 
 }  // extern "C"
