@@ -223,6 +223,8 @@ class ClockSampler:
         try:
             self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
                                       stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            # nvidia-smi needs a few hundred ms to start: wait for its first line so that a short timed region is not over before the first sample
+            self.first = self.p.stdout.readline()
         except OSError:
             pass
 
@@ -232,6 +234,7 @@ class ClockSampler:
         time.sleep(0.15)
         self.p.terminate()
         out, _ = self.p.communicate(timeout=10)
+        out = (getattr(self, "first", "") or "") + out
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for ln in out.splitlines():
@@ -908,6 +911,15 @@ def ntt_record(args, env, four, steps, sub=False):
             parity = {"checked_before_timing": None, "note": "no oracle digest committed for 2^%d" % log_n, "checksums": got}
     for _ in range(max(args.warmup, 3)):
         step()
+    if sub:
+        # a sub-record's step count is ours to choose: make the timed region long enough (>= ~0.4 s) for the 100 ms clock sampler to see it under load
+        t0 = time.perf_counter()
+        step()
+        stream.synchronize()
+        est = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(est, op=dist.ReduceOp.MAX)
+        steps = max(steps, min(400, int(0.4 / max(float(est.item()), 1e-4)) + 1))
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
     sampler = ClockSampler(local) if rank == 0 else None
     env.barrier()

@@ -293,7 +293,7 @@ static int zkb_fri_prove_batch_impl(zkb_ctx* c, const zkb_fri_params* p, const v
         ZKB_CUDA(c, cudaMemcpyAsync(hw, d_wire, batch * seg_pad, cudaMemcpyDeviceToHost, c->stream));
         ZKB_CUDA(c, ctx_stream_sync(c));
         const bool ok = parallel_for(batch, c->assembly_threads, [&](size_t bi) {
-            std::vector<uint8_t>& v = ps[bi]->body;
+            zkb::PsBody& v = ps[bi]->body;
             v.insert(v.end(), hw + bi * seg_pad, hw + bi * seg_pad + seg);
             ps[bi]->has_field = true;                                        // Leafs carry field elements (proof_stream_enum.rs:105-112)
         });
@@ -407,7 +407,7 @@ static int zkb_merkle_open_ps_batch_impl(zkb_tree* const* trees, size_t count, c
         ZKB_CUDA(c, cudaMemcpyAsync(hw, d_wire, seg_off.back(), cudaMemcpyDeviceToHost, c->stream));
         ZKB_CUDA(c, ctx_stream_sync(c));
         const bool ok = parallel_for(streams.size(), c->assembly_threads, [&](size_t g) {
-            std::vector<uint8_t>& v = streams[g]->body;
+            zkb::PsBody& v = streams[g]->body;
             v.insert(v.end(), hw + seg_off[g], hw + seg_off[g] + members[g] * k * rec);
             streams[g]->has_field = true;                                    // Value objects carry field elements
         });

@@ -8,7 +8,9 @@
 //   FRI::sample_index(es) src/fri.rs:60-113
 //   MerkleRoot::verify    src/merkle_root.rs:69-95
 // These stay on the host by design: they are tiny, serial, and sit between FRI rounds.
+#include <stdlib.h>
 #include <string.h>
+#include <cuda_runtime.h>
 #include <algorithm>
 #include <mutex>
 #include "hosthash.hpp"
@@ -139,9 +141,36 @@ void host_shake256(const uint8_t* msg, size_t len, uint8_t* out, size_t out_len)
 
 }  // namespace zkb
 
+namespace zkb {
+// 64-byte header in front of every body block: magic + kind (1 = cudaHostAlloc, 0 = malloc)
+static const uint64_t kBodyMagic = 0x7a6b62505342ull;
+static const size_t kPinFrom = 256u << 10;
+void* ps_body_alloc(size_t bytes) {
+    uint8_t* raw = nullptr;
+    uint64_t kind = 0;
+    if (bytes >= kPinFrom) {
+        void* p = nullptr;
+        if (cudaHostAlloc(&p, bytes + 64, cudaHostAllocPortable) == cudaSuccess) { raw = (uint8_t*)p; kind = 1; }
+        else cudaGetLastError();                                   // no device / out of pinned memory: pageable memory still works
+    }
+    if (!raw) {
+        raw = (uint8_t*)malloc(bytes + 64);
+        if (!raw) throw std::bad_alloc();
+    }
+    ((uint64_t*)raw)[0] = kBodyMagic; ((uint64_t*)raw)[1] = kind;
+    return raw + 64;
+}
+void ps_body_free(void* p) {
+    if (!p) return;
+    uint8_t* raw = (uint8_t*)p - 64;
+    if (((uint64_t*)raw)[1] == 1) cudaFreeHost(raw); else free(raw);
+}
+}  // namespace zkb
+
 using namespace zkb;
 
-static void put_be64(std::vector<uint8_t>& v, uint64_t x) {
+template <typename V>
+static void put_be64(V& v, uint64_t x) {
     for (int i = 7; i >= 0; i--) v.push_back((uint8_t)(x >> (8 * i)));
 }
 static void le16_to_be16(const uint8_t* le, uint8_t* be) {
@@ -207,7 +236,7 @@ void zkb_shake256(const uint8_t* msg, size_t len, uint8_t* out, size_t out_len) 
 // every first touch, munmap on free) - measured 2.7 ms of 2.8 ms per assembled proof.  A small free list of
 // bodies that keep their capacity removes that (0.3 ms per proof).
 static std::mutex g_pool_mu;
-static std::vector<std::vector<uint8_t>> g_body_pool;
+static std::vector<zkb::PsBody> g_body_pool;
 static const size_t kPoolMax = 1024, kPoolKeepBytes = 8u << 20;   // <= 1024 x ~1.2 MB kept: several batches of signature streams in flight
 
 static int zkb_ps_create_body(const uint8_t* document, size_t document_len, int is_signature, zkb_ps** out) {
@@ -252,7 +281,7 @@ static int zkb_ps_push_codeword_body(zkb_ps* ps, const void* vals_host, size_t n
 static int zkb_ps_push_path_body(zkb_ps* ps, const uint8_t* nodes, size_t count) {
     if (!ps || (!nodes && count)) return ZKB_ERR_ARG;
     // code || len || count x (u64_be(64) || 64 bytes), written in place (a proof holds ~1,350 paths)
-    std::vector<uint8_t>& v = ps->body;
+    zkb::PsBody& v = ps->body;
     const size_t payload = count * 72, at = v.size();
     if (v.capacity() < at + 9 + payload) v.reserve(std::max(v.capacity() * 2, at + 9 + payload));
     v.resize(at + 9 + payload);
