@@ -52,7 +52,24 @@ def blakex():
             "" if (rc == 0 and cs.value == ref) else "(BAD rc=%d checksum %x vs %x)" % (rc, cs.value, ref)))
 
 
+def blakey():
+    """BLAKE2b with 64-bit adds as one accumulating IMAD.WIDE (blake2b_compress_y<CFG>): Gcompress/s per CFG."""
+    lib = ctypes.CDLL(os.path.join(ROOT, "zk_stark_tutor_b200", "lib", "libzkb200_probe.so"))
+    ref = None
+    for cfg in (0, 1, 2, 3, 4, 29, 9, 14, 19, 24, 49, 59, 64, 69, 74, 99, 13, 18, 23, 68, 73, 34, 39, 44):
+        r, ms, cs = ctypes.c_double(0), ctypes.c_double(0), ctypes.c_uint64(0)
+        rc = lib.zkb_probe_blakey(0, cfg, ctypes.byref(r), ctypes.byref(ms), ctypes.byref(cs))
+        if ref is None:
+            ref = cs.value
+        print("blakey cfg %2d (c_frac:%d a_frac:%d hi-imad:%d a_mode:%d)  %6.2f Gcompress/s %s" % (
+            cfg, cfg % 5, (cfg // 5) % 5, (cfg // 25) % 2, (cfg // 50) % 2, r.value / 1e9,
+            "" if (rc == 0 and cs.value == ref) else "(BAD rc=%d checksum %x vs %x)" % (rc, cs.value, ref)))
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "blakey":
+        blakey()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "blakex":
         blakex()
         sys.exit(0)

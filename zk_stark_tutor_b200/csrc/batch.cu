@@ -288,16 +288,16 @@ static int zkb_fri_prove_batch_impl(zkb_ctx* c, const zkb_fri_params* p, const v
             ZKB_TRY(merkle_open_wire_batch(c, cw_ptr(r + 1), lay[r + 1], A + node_off[r + 1], d_c, ncc, (uint32_t)batch, cw_stride(r + 1), inst_bytes,
                                            d_wire, d_yoff, 1, base[r] + ncc * 57 + 2 * pc, trip, 0, false));
         }
-        uint8_t* hw = nullptr;                                               // pinned: the D2H copy runs at PCIe rate
-        ZKB_TRY(host_scratch_reserve(c, 1, batch * seg_pad, &hw));
-        ZKB_CUDA(c, cudaMemcpyAsync(hw, d_wire, batch * seg_pad, cudaMemcpyDeviceToHost, c->stream));
+        // every segment is copied straight to its final address: the tail of its proof stream's body, which lives in pinned host
+        // memory (hosthash.hpp PsBody) - one DMA per proof, no staging buffer and no host memcpy of the ~0.4 MB
+        std::vector<uint8_t*> dst(batch, nullptr);
+        const bool ok = parallel_for(batch, c->assembly_threads, [&](size_t bi) { dst[bi] = ps_body_extend(ps[bi], seg); });
+        if (!ok) return set_err(c, ZKB_ERR_NOMEM, "out of host memory while appending to the proof streams (they are unusable now)");
+        for (size_t bi = 0; bi < batch; bi++)
+            ZKB_CUDA(c, cudaMemcpyAsync(dst[bi], d_wire + bi * seg_pad, seg, cudaMemcpyDeviceToHost, c->stream));
         ZKB_CUDA(c, ctx_stream_sync(c));
-        const bool ok = parallel_for(batch, c->assembly_threads, [&](size_t bi) {
-            zkb::PsBody& v = ps[bi]->body;
-            v.insert(v.end(), hw + bi * seg_pad, hw + bi * seg_pad + seg);
-            ps[bi]->has_field = true;                                        // Leafs carry field elements (proof_stream_enum.rs:105-112)
-        });
-        return ok ? 0 : set_err(c, ZKB_ERR_NOMEM, "out of host memory while appending to the proof streams (they are unusable now)");
+        for (size_t bi = 0; bi < batch; bi++) ps[bi]->has_field = true;      // Leafs carry field elements (proof_stream_enum.rs:105-112)
+        return 0;
     }
     // (round-1 path, kept for ZKB_HOST_ASSEMBLY=1 and for layer shapes the wire kernels do not take: raw paths to the host,
     // objects framed by host threads)
@@ -402,16 +402,15 @@ static int zkb_merkle_open_ps_batch_impl(zkb_tree* const* trees, size_t count, c
         ZKB_CUDA(c, cudaMemcpyAsync(d_idx, hbuf.data(), hbuf.size() * 8, cudaMemcpyHostToDevice, c->stream));
         ZKB_TRY(merkle_open_wire_batch(c, trees[0]->vals, trees[0]->layout, trees[0]->nodes, d_idx, k, (uint32_t)count, (uint64_t)vstride, (uint64_t)nstride,
                                        d_wire, d_idx + count * k, 1, 0, rec, 0, true));
-        uint8_t* hw = nullptr;
-        ZKB_TRY(host_scratch_reserve(c, 1, seg_off.back(), &hw));
-        ZKB_CUDA(c, cudaMemcpyAsync(hw, d_wire, seg_off.back(), cudaMemcpyDeviceToHost, c->stream));
+        // as in zkb_fri_prove_batch: each stream's records go straight from device memory to the tail of its (pinned) body
+        std::vector<uint8_t*> dst(streams.size(), nullptr);
+        const bool ok = parallel_for(streams.size(), c->assembly_threads, [&](size_t g) { dst[g] = ps_body_extend(streams[g], members[g] * k * rec); });
+        if (!ok) return set_err(c, ZKB_ERR_NOMEM, "out of host memory while appending to the proof streams (they are unusable now)");
+        for (size_t g = 0; g < streams.size(); g++)
+            ZKB_CUDA(c, cudaMemcpyAsync(dst[g], d_wire + seg_off[g], members[g] * k * rec, cudaMemcpyDeviceToHost, c->stream));
         ZKB_CUDA(c, ctx_stream_sync(c));
-        const bool ok = parallel_for(streams.size(), c->assembly_threads, [&](size_t g) {
-            zkb::PsBody& v = streams[g]->body;
-            v.insert(v.end(), hw + seg_off[g], hw + seg_off[g] + members[g] * k * rec);
-            streams[g]->has_field = true;                                    // Value objects carry field elements
-        });
-        return ok ? 0 : set_err(c, ZKB_ERR_NOMEM, "out of host memory while appending to the proof streams (they are unusable now)");
+        for (size_t g = 0; g < streams.size(); g++) streams[g]->has_field = true;   // Value objects carry field elements
+        return 0;
     }
     const size_t depth = trees[0]->layout.log_n, path_bytes = depth * 64;
     const size_t idx_bytes = (count * k * 8 + 255) & ~(size_t)255, val_bytes = (count * k * 16 + 255) & ~(size_t)255;

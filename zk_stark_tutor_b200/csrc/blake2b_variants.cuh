@@ -277,4 +277,98 @@ __device__ __forceinline__ void blake2b_compress_x(const uint32_t (&ml)[16], con
 }
 #endif
 
+#if defined(__CUDACC__)
+// ---- round 2: 64-bit adds as ONE accumulating IMAD.WIDE (family "y") ---------------------------
+// The x family above wrote c + d as mad.wide.u32 with a 64-bit addend, which ptxas 12.9 SPLITS into IMAD.WIDE + IADD3 + IADD3.X
+// on sm_100a (found later with probe kind 40): it added FMA-pipe work without removing any ALU-pipe work.  The pair
+// mad.lo.cc / madc.hi (as in fe_montmul) IS fused into one `IMAD.WIDE.U32 Rd, Ra, K1, Rc` with the 64-bit accumulate, so
+// c + d = {IMAD.WIDE(d.lo * 1 + c), hi += d.hi}: the low-word IADD3 and the carry-in IADD3.X leave the ALU pipe.
+//   CFG = c_frac + 5 * a_frac + 25 * hi_imad + 50 * a_mode
+//   c_frac / a_frac in 0..4: how many of every four G functions use the IMAD.WIDE form for their c + d / a + b + m adds
+//   hi_imad: the remaining high-word add as IMAD (mad.lo x, 1, y) instead of leaving the choice to ptxas
+//   a_mode 0: a + b through IMAD.WIDE, + m as an ordinary 64-bit add; 1: + m through a second IMAD.WIDE, one 3-input high add
+template <int HI> __device__ __forceinline__ uint32_t b2y_hiadd(uint32_t x, uint32_t y, uint32_t k1) {
+    if (HI) { uint32_t r; asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(x), "r"(k1), "r"(y)); return r; }
+    return x + y;
+}
+// {lo, hi} = x * k1 + {clo, chi}  (one IMAD.WIDE.U32 with accumulate)
+__device__ __forceinline__ void b2y_wide(uint32_t x, uint32_t k1, uint32_t clo, uint32_t chi, uint32_t& lo, uint32_t& hi) {
+    asm("mad.lo.cc.u32 %0, %2, %3, %4;\n\tmadc.hi.u32 %1, %2, %3, %5;" : "=r"(lo), "=r"(hi) : "r"(x), "r"(k1), "r"(clo), "r"(chi));
+}
+template <bool W, int HI> __device__ __forceinline__ void b2y_add(b2w& c, const b2w& d, uint32_t k1) {
+    if (W) {
+        uint32_t lo, hi;
+        b2y_wide(d.lo, k1, c.lo, c.hi, lo, hi);
+        c.lo = lo; c.hi = b2y_hiadd<HI>(d.hi, hi, k1);
+    } else {
+        b2h_add(c, d);
+    }
+}
+template <bool W, int HI, int AMODE> __device__ __forceinline__ void b2y_add3(b2w& a, const b2w& b, uint32_t mlo, uint32_t mhi, uint32_t k1) {
+    if (W) {
+        uint32_t lo, hi;
+        b2y_wide(b.lo, k1, a.lo, a.hi, lo, hi);
+        if (AMODE == 0) {
+            hi = b2y_hiadd<HI>(b.hi, hi, k1);
+            asm("add.cc.u32 %0, %0, %2;\n\taddc.u32 %1, %1, %3;" : "+r"(lo), "+r"(hi) : "r"(mlo), "r"(mhi));
+        } else {
+            uint32_t lo2, hi2;
+            b2y_wide(mlo, k1, lo, hi, lo2, hi2);
+            lo = lo2; hi = hi2 + b.hi + mhi;
+        }
+        a.lo = lo; a.hi = hi;
+    } else {
+        uint64_t r = b2x_pack(a.lo, a.hi) + b2x_pack(b.lo, b.hi) + b2x_pack(mlo, mhi);
+        a.lo = (uint32_t)r; a.hi = (uint32_t)(r >> 32);
+    }
+}
+#define ZKB_B2Y_G(gi, a, b, c, d, x, y)                                                                   \
+    do {                                                                                                  \
+        b2y_add3<((gi) & 3) < AF, HI, AM>(v[a], v[b], ml[x], mh[x], k1); b2h_xr32(v[d], v[a]);            \
+        b2y_add<((gi) & 3) < CF, HI>(v[c], v[d], k1);                    b2h_xr24(v[b], v[c]);            \
+        b2y_add3<((gi) & 3) < AF, HI, AM>(v[a], v[b], ml[y], mh[y], k1); b2h_xr16(v[d], v[a]);            \
+        b2y_add<((gi) & 3) < CF, HI>(v[c], v[d], k1);                    b2h_xr63(v[b], v[c]);            \
+    } while (0)
+#define ZKB_B2Y_ROUND(s0, s1, s2, s3, s4, s5, s6, s7, s8, s9, s10, s11, s12, s13, s14, s15) \
+    do {                                                                                  \
+        ZKB_B2Y_G(0, 0, 4, 8, 12, s0, s1);   ZKB_B2Y_G(1, 1, 5, 9, 13, s2, s3);   \
+        ZKB_B2Y_G(2, 2, 6, 10, 14, s4, s5);  ZKB_B2Y_G(3, 3, 7, 11, 15, s6, s7);  \
+        ZKB_B2Y_G(4, 0, 5, 10, 15, s8, s9);  ZKB_B2Y_G(5, 1, 6, 11, 12, s10, s11); \
+        ZKB_B2Y_G(6, 2, 7, 8, 13, s12, s13); ZKB_B2Y_G(7, 3, 4, 9, 14, s14, s15); \
+    } while (0)
+template <int CFG>
+__device__ __forceinline__ void blake2b_compress_y(const uint32_t (&ml)[16], const uint32_t (&mh)[16], uint32_t t,
+                                                   uint32_t k1, uint32_t (&hl)[8], uint32_t (&hh)[8]) {
+    constexpr int CF = CFG % 5, AF = (CFG / 5) % 5, HI = (CFG / 25) % 2, AM = (CFG / 50) % 2;
+    const uint64_t iv[8] = {ZKB_B2_IV0, ZKB_B2_IV1, ZKB_B2_IV2, ZKB_B2_IV3, ZKB_B2_IV4, ZKB_B2_IV5, ZKB_B2_IV6, ZKB_B2_IV7};
+    b2w v[16];
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        uint64_t h0 = i == 0 ? ZKB_B2_H0 : iv[i];
+        v[i].lo = (uint32_t)h0; v[i].hi = (uint32_t)(h0 >> 32);
+        uint64_t w = i == 6 ? ~iv[6] : iv[i];
+        v[8 + i].lo = (uint32_t)w; v[8 + i].hi = (uint32_t)(w >> 32);
+    }
+    v[12].lo ^= t;
+    ZKB_B2Y_ROUND(0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15);
+    ZKB_B2Y_ROUND(14, 10, 4, 8, 9, 15, 13, 6, 1, 12, 0, 2, 11, 7, 5, 3);
+    ZKB_B2Y_ROUND(11, 8, 12, 0, 5, 2, 15, 13, 10, 14, 3, 6, 7, 1, 9, 4);
+    ZKB_B2Y_ROUND(7, 9, 3, 1, 13, 12, 11, 14, 2, 6, 5, 10, 4, 0, 15, 8);
+    ZKB_B2Y_ROUND(9, 0, 5, 7, 2, 4, 10, 15, 14, 1, 11, 12, 6, 8, 3, 13);
+    ZKB_B2Y_ROUND(2, 12, 6, 10, 0, 11, 8, 3, 4, 13, 7, 5, 15, 14, 1, 9);
+    ZKB_B2Y_ROUND(12, 5, 1, 15, 14, 13, 4, 10, 0, 7, 6, 3, 9, 2, 8, 11);
+    ZKB_B2Y_ROUND(13, 11, 7, 14, 12, 1, 3, 9, 5, 0, 15, 4, 8, 6, 2, 10);
+    ZKB_B2Y_ROUND(6, 15, 14, 9, 11, 3, 0, 8, 12, 2, 13, 7, 1, 4, 10, 5);
+    ZKB_B2Y_ROUND(10, 2, 8, 4, 7, 6, 1, 5, 15, 11, 9, 14, 3, 12, 13, 0);
+    ZKB_B2Y_ROUND(0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15);
+    ZKB_B2Y_ROUND(14, 10, 4, 8, 9, 15, 13, 6, 1, 12, 0, 2, 11, 7, 5, 3);
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        uint64_t h0 = i == 0 ? ZKB_B2_H0 : iv[i];
+        hl[i] = (uint32_t)h0 ^ v[i].lo ^ v[8 + i].lo;
+        hh[i] = (uint32_t)(h0 >> 32) ^ v[i].hi ^ v[8 + i].hi;
+    }
+}
+#endif
+
 }  // namespace zkb

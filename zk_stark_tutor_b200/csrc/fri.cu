@@ -520,11 +520,9 @@ static int zkb_fri_prove_body(zkb_ctx* c, const zkb_fri_params* p, const void* c
             ZKB_TRY(merkle_open_wire_batch(c, L->cw[r + 1], L->layout[r + 1], L->nodes[r + 1], d_c, ncc, 1, 0, 0, d_wire, d_yoff, 1,
                                            base[r] + ncc * 57 + 2 * pc, trip, 0, false));
         }
-        uint8_t* hw = nullptr;
-        ZKB_TRY(host_scratch_reserve(c, 1, seg, &hw));
-        ZKB_CUDA(c, cudaMemcpyAsync(hw, d_wire, seg, cudaMemcpyDeviceToHost, c->stream));
+        uint8_t* dst = ps_body_extend(ps, seg);              // straight into the (pinned) body: no staging copy
+        ZKB_CUDA(c, cudaMemcpyAsync(dst, d_wire, seg, cudaMemcpyDeviceToHost, c->stream));
         ZKB_CUDA(c, cudaStreamSynchronize(c->stream));
-        ps->body.insert(ps->body.end(), hw, hw + seg);
         ps->has_field = true;                                // Leafs carry field elements
         return 0;
     }

@@ -165,6 +165,14 @@ void ps_body_free(void* p) {
     uint8_t* raw = (uint8_t*)p - 64;
     if (((uint64_t*)raw)[1] == 1) cudaFreeHost(raw); else free(raw);
 }
+uint8_t* ps_body_extend(zkb_ps* ps, size_t bytes) {
+    PsBody& v = ps->body;
+    const size_t at = v.size(), need = at + bytes;
+    // a body that reaches pinned size is given room for a whole proof at once (~1.2 MB): one cudaHostAlloc, kept by the pool afterwards
+    if (v.capacity() < need) v.reserve(std::max(std::max(v.capacity() * 2, need), need >= kPinFrom ? (size_t)(1536u << 10) : need));
+    v.resize(need);
+    return v.data() + at;
+}
 }  // namespace zkb
 
 using namespace zkb;

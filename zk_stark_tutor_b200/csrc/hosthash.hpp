@@ -39,6 +39,11 @@ struct PsBodyAlloc {
 typedef std::vector<uint8_t, PsBodyAlloc<uint8_t>> PsBody;
 }  // namespace zkb
 
+struct zkb_ps;
+namespace zkb {
+// grow a proof stream's body by `bytes` uninitialised bytes and return their address (the target of a device-to-host copy)
+uint8_t* ps_body_extend(zkb_ps* ps, size_t bytes);
+}
 struct zkb_ps {
     std::vector<uint8_t> prefix;     // u64_be(64) || BLAKE2b-512(document) for SignatureProofStream
     zkb::PsBody body;

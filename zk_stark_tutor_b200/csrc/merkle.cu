@@ -748,11 +748,9 @@ static int zkb_merkle_open_ps_body(zkb_tree* t, const uint64_t* idx, size_t k, z
         uint8_t* d_wire = (uint8_t*)wb.p + ib;
         ZKB_CUDA(c, cudaMemcpyAsync(d_i, hidx.data(), hidx.size() * 8, cudaMemcpyHostToDevice, c->stream));
         ZKB_TRY(merkle_open_wire_batch(c, t->vals, t->layout, t->nodes, d_i, k, 1, 0, 0, d_wire, d_i + k, 1, 0, rec, 0, true));
-        uint8_t* hw = nullptr;
-        ZKB_TRY(host_scratch_reserve(c, 1, k * rec, &hw));
-        ZKB_CUDA(c, cudaMemcpyAsync(hw, d_wire, k * rec, cudaMemcpyDeviceToHost, c->stream));
+        uint8_t* dst = ps_body_extend(ps, k * rec);                          // straight into the (pinned) body: no staging copy
+        ZKB_CUDA(c, cudaMemcpyAsync(dst, d_wire, k * rec, cudaMemcpyDeviceToHost, c->stream));
         ZKB_CUDA(c, cudaStreamSynchronize(c->stream));
-        ps->body.insert(ps->body.end(), hw, hw + k * rec);
         ps->has_field = true;
         return 0;
     }

@@ -285,6 +285,71 @@ extern "C" int zkb_probe_blakex(int device, int cfg, double* compress_per_s, dou
     }
 }
 
+template <int CFG>
+__global__ void __launch_bounds__(256, 2) k_probe_blakey(uint64_t* out, int iters, KParams kp) {
+    uint32_t ml[16], mh[16], hl[8], hh[8];
+    const uint32_t k1 = kp.k[0];
+#pragma unroll
+    for (int i = 0; i < 16; i++) {
+        uint64_t w = (uint64_t)(threadIdx.x + 1) * 0x9E3779B97F4A7C15ull + i * 0xBF58476D1CE4E5B9ull + blockIdx.x;
+        ml[i] = (uint32_t)w; mh[i] = (uint32_t)(w >> 32);
+    }
+    for (int it = 0; it < iters; it++) {
+        zkb::blake2b_compress_y<CFG>(ml, mh, 128, k1, hl, hh);
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            ml[i] ^= hl[i]; mh[i] ^= hh[i];
+            asm("add.cc.u32 %0, %0, %2;\n\taddc.u32 %1, %1, %3;" : "+r"(ml[8 + i]), "+r"(mh[8 + i]) : "r"(hl[i]), "r"(hh[i]));
+        }
+    }
+    uint64_t acc = 0;
+#pragma unroll
+    for (int i = 0; i < 16; i++) acc ^= ((uint64_t)mh[i] << 32) | ml[i];
+    if (blockIdx.x == 0 && threadIdx.x == 0) out[1] = acc;
+    if (acc == 0x1234567812345678ull) out[0] = acc;
+}
+
+template <int CFG>
+static int run_blakey(int device, double* rate, double* ms_out, uint64_t* checksum) {
+    int sms = 0;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    uint64_t* d = nullptr;
+    if (cudaMalloc(&d, 64) != cudaSuccess) return -1;
+    cudaMemset(d, 0, 64);
+    const int iters = 256, blocks = sms * 16;
+    KParams kp = {{1u, 2u, 256u, 65536u}};
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    float best = 1e30f;
+    for (int rep = 0; rep < 4; rep++) {
+        cudaEventRecord(e0);
+        k_probe_blakey<CFG><<<blocks, 256>>>(d, iters, kp);
+        cudaEventRecord(e1);
+        if (cudaEventSynchronize(e1) != cudaSuccess) { cudaFree(d); return -1; }
+        float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
+        if (rep > 0 && ms < best) best = ms;
+    }
+    uint64_t hsum[2] = {0, 0};
+    cudaMemcpy(hsum, d, 16, cudaMemcpyDeviceToHost);
+    *checksum = hsum[1];
+    *rate = (double)iters * blocks * 256 / (best * 1e-3);
+    if (ms_out) *ms_out = best;
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaFree(d);
+    return 0;
+}
+
+// CFG = c_frac + 5 * a_frac + 25 * hi_imad + 50 * a_mode (blake2b_variants.cuh, family y)
+extern "C" int zkb_probe_blakey(int device, int cfg, double* compress_per_s, double* ms_out, uint64_t* checksum) {
+    if (cudaSetDevice(device) != cudaSuccess) return -1;
+    switch (cfg) {
+#define ZKB_RY(C) case C: return run_blakey<C>(device, compress_per_s, ms_out, checksum);
+        ZKB_RY(0) ZKB_RY(1) ZKB_RY(2) ZKB_RY(3) ZKB_RY(4) ZKB_RY(29) ZKB_RY(9) ZKB_RY(14) ZKB_RY(19) ZKB_RY(24) ZKB_RY(49)
+        ZKB_RY(59) ZKB_RY(64) ZKB_RY(69) ZKB_RY(74) ZKB_RY(99) ZKB_RY(13) ZKB_RY(18) ZKB_RY(23) ZKB_RY(68) ZKB_RY(73) ZKB_RY(34) ZKB_RY(39) ZKB_RY(44)
+        default: return -2;
+    }
+}
+
 template <int V, int MINB>
 static int run_blake(int device, double* rate, double* ms_out, uint64_t* checksum) {
     int sms = 0;
