@@ -146,6 +146,18 @@ def test_scale_kat_and_random(ctx):
     assert zk.scale(xs, f, ctx) == N.scale(xs, f)
 
 
+def test_device_products_at_edge_values(ctx):
+    # the device Montgomery product (fe128.cuh) on operands that stress its carry / borrow paths: scale([0, a], b) = [0, a * b]
+    edge = [0, 1, 2, P - 1, P - 2, (P - 1) // 2, (P + 1) // 2, 1 << 32, (1 << 32) - 1, 1 << 64, (1 << 96) - 1, 1 << 96, (1 << 127) - 1, 1 << 127,
+            0xCB800000 << 96, (0xCB800000 << 96) - 1, 0xFFFFFFFF00000000FFFFFFFF00000000, 0x00000000FFFFFFFF00000000FFFFFFFF % P]
+    for b in edge[1:]:
+        xs = [0] + edge + rvals(13)
+        assert zk.scale(xs, b, ctx) == [x * pow(b, i, P) % P for i, x in enumerate(xs)]
+    for a in edge:
+        for b in edge[1:]:
+            assert zk.scale([0, a], b, ctx) == [0, a * b % P]
+
+
 @pytest.mark.parametrize("log_n,n_coeffs", [(1, 1), (2, 1), (3, 2), (6, 16), (6, 13), (10, 256), (12, 1000), (12, 4096), (13, 2048),
                                             (14, 4096), (16, 1 << 14), (17, 40000), (20, 1 << 18), (21, 1 << 19), (22, 1 << 20), (22, 3)])
 def test_coset_lde_vs_oracle(ctx, log_n, n_coeffs):

@@ -66,7 +66,21 @@ def blakey():
             "" if (rc == 0 and cs.value == ref) else "(BAD rc=%d checksum %x vs %x)" % (rc, cs.value, ref)))
 
 
+def mix():
+    """ALU-pipe xor + IMAD.WIDE / IMAD per step: clk per step per warp per scheduler (do the wide multiplies overlap with the ALU pipe?)."""
+    lib = ctypes.CDLL(os.path.join(ROOT, "zk_stark_tutor_b200", "lib", "libzkb200_probe.so"))
+    forms = {0: "IMAD.WIDE product", 1: "IMAD.WIDE accumulate", 2: "IMAD"}
+    # (form 0 is not listed: ptxas rewrites a product whose high word is unused into a 32-bit IMAD)
+    for a, w, f in ((16, 0, 0), (0, 8, 1), (0, 8, 2), (16, 8, 1), (16, 8, 2), (16, 4, 1), (16, 2, 1), (8, 8, 1), (8, 8, 2), (8, 4, 1), (4, 8, 1), (12, 8, 1)):
+        r = ctypes.c_double(0)
+        rc = lib.zkb_probe_mix(0, a, w, f, ctypes.byref(r))
+        print("mix %2d LOP3 + %d %-20s rc=%d  %6.2f clk/step   (alone: ALU %d, multiplies %d at 2 clk / %d at 4 clk)" % (a, w, forms[f], rc, r.value, 2 * a, 2 * w, 4 * w))
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "mix":
+        mix()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "blakey":
         blakey()
         sys.exit(0)

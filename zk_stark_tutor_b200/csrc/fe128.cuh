@@ -14,8 +14,8 @@
 // conditional correction; no lazy [0,2p) representation fits in four limbs.
 //
 // Montgomery reduction exploits p = 1 + c*2^119: p^-1 = 1 - c*2^119 (mod 2^128), so the
-// multiplier m = -T_lo * p^-1 is a negation plus one 32-bit multiply-add, and m*p costs four
-// products m_i * 0xCB800000; 16 + 4 (+1 low) 32x32 products per field multiplication.
+// quotient digit m' = T_lo * p^-1 is T_lo with one limb adjusted, and m'*p costs four
+// products m'_i * 0xCB800000; 16 + 4 (+1 low) 32x32 products per field multiplication.
 #pragma once
 #include <stdint.h>
 
@@ -140,17 +140,17 @@ ZKB_HD fe fe_half(const fe& a) {
 // ("even" holds a_i*b_j with i+j even at limb i+j, "odd" those with i+j odd) so that every
 // 32x32->64 product lands on a fixed, aligned register pair and maps to one IMAD.WIDE with
 // carry-out, rows chained by carry; the two are merged with one 7-limb add.  The reduction
-// uses the shape of p = 1 + c*2^119: p^-1 mod 2^128 = 1 - c*2^119, so the full Montgomery
-// multiplier m = -T_lo/p is a 128-bit negation plus ONE 32-bit multiply-add on limb 3, and
-// m*p = m + (m*P3 << 96) needs four products m_i*P3 accumulated straight onto T[4..7];
-// one conditional subtraction makes the result canonical.  36 ALU-pipe + 20 IMAD.WIDE.
+// uses the shape of p = 1 + c*2^119 (P3 = c << 23): p^-1 mod 2^128 = 1 - P3*2^96, so the quotient digit
+// m' = T_lo * p^-1 mod 2^128 is T_lo itself with limb 3 replaced by t3 - lo32(t0*P3) - no negation, no carry chain.
+// m'*p = m' + (m'*P3 << 96) agrees with T on the low 128 bits, so (T - m'*p) / 2^128 = T_hi - hi128(m'*p) with no borrow from
+// below, and hi128(m'*p) = (m'*P3 + m'_3) >> 32 is ONE chain of four wide multiply-adds (the first absorbs m'_3 and with it the
+// carry out of limb 3; its low word is t3 again and is dropped).  The difference lies in (-p, p): p is added back under the
+// borrow mask.  24 ALU-pipe instructions + 21 quarter-rate multiplies (round 1/2a form with m = -T_lo/p: 34 + 21).
 __device__ __forceinline__ fe fe_montmul_ptx(const fe& a, const fe& b) {
     fe r;
     asm("{\n\t"
         ".reg .u32 e0,e1,e2,e3,e4,e5,e6,e7,o0,o1,o2,o3,o4,o5,o6;\n\t"
-        ".reg .u32 t1,t2,t3,t4,t5,t6,t7,m0,m1,m2,m3,nz,c3,u3,u4,u5,u6,u7,u8;\n\t"
-        ".reg .u32 q0l,q0h,q1l,q1h,q2l,q2h,q3l,q3h,r0,r1,r2,r3,top,d0,d1,d2,d3,k;\n\t"
-        ".reg .pred keep;\n\t"
+        ".reg .u32 t1,t2,t3,t4,t5,t6,t7,m3,d0,x0,h0,h1,h2,q1,q2,q3,q4,r0,r1,r2,r3,bw,a0,a3;\n\t"
         ".reg .u64 w0,w1,w2,w3;\n\t"
         // ---- even accumulator: row b0
         "mul.wide.u32 w0, %4, %8;\n\t" "mov.b64 {e0,e1}, w0;\n\t"
@@ -182,31 +182,18 @@ __device__ __forceinline__ fe fe_montmul_ptx(const fe& a, const fe& b) {
         "add.cc.u32 t1, e1, o0;\n\t"  "addc.cc.u32 t2, e2, o1;\n\t" "addc.cc.u32 t3, e3, o2;\n\t"
         "addc.cc.u32 t4, e4, o3;\n\t" "addc.cc.u32 t5, e5, o4;\n\t" "addc.cc.u32 t6, e6, o5;\n\t"
         "addc.u32 t7, e7, o6;\n\t"
-        // ---- m = -T_lo * p^-1 mod 2^128.  p = 1 + c*2^119 so p^-1 = 1 - c*2^119 (mod 2^128) and
-        //      m = -T_lo + ((c*T_lo mod 2^9) << 119) = -T_lo + (lo32(P3*t0) << 96): one 128-bit negation
-        //      (nz = borrow = T_lo != 0) and one 32-bit add on limb 3 (carry-out co is discarded mod 2^128)
-        "sub.cc.u32 m0, 0, e0;\n\t" "subc.cc.u32 m1, 0, t1;\n\t" "subc.cc.u32 m2, 0, t2;\n\t"
-        "subc.cc.u32 m3, 0, t3;\n\t" "subc.u32 nz, 0, 0;\n\t"
+        // ---- m' = (t0, t1, t2, m3), m3 = t3 - lo32(t0*P3);  hi128(m'*p) = (m'*P3 + m3) >> 32 = (q1, q2, q3, q4)
         "mul.lo.u32 d0, e0, 0xCB800000;\n\t"
-        "add.cc.u32 m3, m3, d0;\n\t" "addc.u32 c3, 0, 0;\n\t"
-        // T_lo + m = (d0 << 96) + k*2^128 with k = nz - co
-        "and.b32 nz, nz, 1;\n\t" "sub.u32 k, nz, c3;\n\t"
-        // (T + m*p) >> 128 = T[4..7] + k + ((d0 + m0*P3) >> 32) + m1*P3 + (m2*P3 << 32) + (m3*P3 << 64):
-        // limb 3 cancels inside the first wide multiply-add (addend {d0, k}); the other three products
-        // are accumulated straight onto T[4..7] in two carry chains
-        "mov.b64 w1, {d0, k};\n\t" "mad.wide.u32 w0, m0, 0xCB800000, w1;\n\t" "mov.b64 {q0l,q0h}, w0;\n\t"
-        "mad.lo.cc.u32 r0, m1, 0xCB800000, t4;\n\t"  "madc.hi.cc.u32 r1, m1, 0xCB800000, t5;\n\t"
-        "madc.lo.cc.u32 r2, m3, 0xCB800000, t6;\n\t" "madc.hi.cc.u32 r3, m3, 0xCB800000, t7;\n\t"
-        "addc.u32 top, 0, 0;\n\t"
-        "add.cc.u32 r0, r0, q0h;\n\t"
-        "madc.lo.cc.u32 r1, m2, 0xCB800000, r1;\n\t" "madc.hi.cc.u32 r2, m2, 0xCB800000, r2;\n\t"
-        "addc.cc.u32 r3, r3, 0;\n\t" "addc.u32 top, top, 0;\n\t"
-        // ---- conditional subtraction of p = {1, 0, 0, P3}: keep r iff (top:r) < p
-        "sub.cc.u32 d0, r0, 1;\n\t" "subc.cc.u32 d1, r1, 0;\n\t" "subc.cc.u32 d2, r2, 0;\n\t"
-        "subc.cc.u32 d3, r3, 0xCB800000;\n\t" "subc.u32 k, top, 0;\n\t"
-        "setp.ne.u32 keep, k, 0;\n\t"
-        "selp.u32 %0, r0, d0, keep;\n\t" "selp.u32 %1, r1, d1, keep;\n\t"
-        "selp.u32 %2, r2, d2, keep;\n\t" "selp.u32 %3, r3, d3, keep;\n\t"
+        "sub.u32 m3, t3, d0;\n\t"
+        "mad.lo.cc.u32 x0, e0, 0xCB800000, m3;\n\t" "madc.hi.u32 h0, e0, 0xCB800000, 0;\n\t"
+        "mad.lo.cc.u32 q1, t1, 0xCB800000, h0;\n\t" "madc.hi.u32 h1, t1, 0xCB800000, 0;\n\t"
+        "mad.lo.cc.u32 q2, t2, 0xCB800000, h1;\n\t" "madc.hi.u32 h2, t2, 0xCB800000, 0;\n\t"
+        "mad.lo.cc.u32 q3, m3, 0xCB800000, h2;\n\t" "madc.hi.u32 q4, m3, 0xCB800000, 0;\n\t"
+        // ---- r = T_hi - (q1..q4) in (-p, p); + p = {1, 0, 0, P3} under the borrow mask
+        "sub.cc.u32 r0, t4, q1;\n\t" "subc.cc.u32 r1, t5, q2;\n\t" "subc.cc.u32 r2, t6, q3;\n\t" "subc.cc.u32 r3, t7, q4;\n\t"
+        "subc.u32 bw, 0, 0;\n\t"
+        "and.b32 a0, bw, 1;\n\t" "and.b32 a3, bw, 0xCB800000;\n\t"
+        "add.cc.u32 %0, r0, a0;\n\t" "addc.cc.u32 %1, r1, 0;\n\t" "addc.cc.u32 %2, r2, 0;\n\t" "addc.u32 %3, r3, a3;\n\t"
         "}"
         : "=r"(r.v[0]), "=r"(r.v[1]), "=r"(r.v[2]), "=r"(r.v[3])
         : "r"(a.v[0]), "r"(a.v[1]), "r"(a.v[2]), "r"(a.v[3]), "r"(b.v[0]), "r"(b.v[1]), "r"(b.v[2]), "r"(b.v[3]));

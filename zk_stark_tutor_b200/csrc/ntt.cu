@@ -76,10 +76,11 @@ __device__ __forceinline__ uint32_t bitrev(uint32_t x, uint32_t bits) { return _
 #define ZKB_NTT_THREADS 256
 // Which multiplications of the register-radix pass are INLINE (the rest go through the out-of-line mm / mm2): bit 0 the DFT stages,
 // bit 1 the step-1 twiddles, bit 2 the step-3 running products.  An out-of-line call is a scheduling barrier and costs ~12 argument
-// moves per product; everything inline (190 KB of SASS) stalls on instruction fetch.  Measured on B200, 2^24 forward + inverse:
-// 0: 2.598 ms (69 KB per kernel), 1: 2.423 (98 KB), 3: 2.380 (111 KB), 7: 2.432 (136 KB).
+// moves per product; too much inline code stalls on instruction fetch.  Measured on B200, 2^24 forward + inverse:
+//   34-ALU-instruction multiplication (round 2a): 0: 2.598 ms (69 KB per kernel), 1: 2.423 (98 KB), 3: 2.380 (111 KB), 7: 2.432 (136 KB)
+//   24-ALU-instruction multiplication (fe128.cuh now): 1: 2.245, 3: 2.178 (100 KB), 7: 2.154 (118 KB)
 #ifndef ZKB_NTT_INLINE_DFT
-#define ZKB_NTT_INLINE_DFT 3
+#define ZKB_NTT_INLINE_DFT 7
 #endif
 
 // block -> (outer offset in, outer offset out, inner)

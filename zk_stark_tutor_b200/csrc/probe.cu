@@ -220,6 +220,71 @@ static int run_wide(int device, double* rate, double* ms_out) {
     return 0;
 }
 
+// ---- do IMAD.WIDE and ALU-pipe instructions overlap?  A xor (LOP3) + W wide multiply(-add)s per step on independent registers.
+// F = 0: IMAD.WIDE products only, 1: IMAD.WIDE with the 64-bit accumulate (mad.lo.cc / madc.hi, the form ptxas fuses), 2: 32-bit IMAD.
+// Reports clk per step per warp on one SMSP: 2 clk per ALU instruction alone; if the wide multiplies overlapped perfectly the mix
+// would cost max(2 A, 4 W).
+template <int A, int W, int F>
+__global__ void __launch_bounds__(256) k_probe_mix(unsigned long long* out, uint32_t ub, int iters) {
+    uint32_t x[A > 0 ? A : 1], lo[W > 0 ? W : 1], hi[W > 0 ? W : 1], m[W > 0 ? W : 1];
+#pragma unroll
+    for (int i = 0; i < (A > 0 ? A : 1); i++) x[i] = threadIdx.x * 2654435761u + i * 40503u + blockIdx.x;
+#pragma unroll
+    for (int i = 0; i < (W > 0 ? W : 1); i++) { lo[i] = threadIdx.x * 97u + i; hi[i] = blockIdx.x + 3u * i; m[i] = (threadIdx.x + i) | 1u; }
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+#pragma unroll
+            for (int i = 0; i < (A > W ? A : W); i++) {
+                if (i < A) asm volatile("lop3.b32 %0, %0, %1, %2, 0xCA;" : "+r"(x[i]) : "r"(x[(i + 1 + u) % A]), "r"(x[(i + 5 + u) % A]));   // 3-input select: cannot be merged with its neighbours
+                if (i < W) {
+                    if (F == 0) asm volatile("{ .reg .u64 t; mul.wide.u32 t, %0, %2; mov.b64 {%0, %1}, t; }" : "+r"(lo[i]), "+r"(hi[i]) : "r"(m[(i + 1) % W]));
+                    else if (F == 1) asm volatile("mad.lo.cc.u32 %0, %2, %3, %0;\n\tmadc.hi.u32 %1, %2, %3, %1;" : "+r"(lo[i]), "+r"(hi[i]) : "r"(m[i]), "r"(ub));
+                    else asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(lo[i]) : "r"(m[i]), "r"(ub));
+                }
+            }
+        }
+    }
+    unsigned long long acc = 0;
+#pragma unroll
+    for (int i = 0; i < (A > 0 ? A : 1); i++) acc ^= x[i];
+#pragma unroll
+    for (int i = 0; i < (W > 0 ? W : 1); i++) acc ^= ((unsigned long long)hi[i] << 32) | lo[i];
+    if (acc == 0x12345678ull) out[0] = acc;
+}
+template <int A, int W, int F>
+static int run_mix(int device, double* clk_per_step) {
+    int sms = 0, khz = 0;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, device);
+    unsigned long long* d = nullptr;
+    if (cudaMalloc(&d, 64) != cudaSuccess) return -1;
+    const int iters = 2048, blocks = sms * 4;                    // 4 x 256 threads per SM = 8 warps per scheduler
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    float best = 1e30f;
+    for (int rep = 0; rep < 4; rep++) {
+        cudaEventRecord(e0);
+        k_probe_mix<A, W, F><<<blocks, 256>>>(d, 3u, iters);
+        cudaEventRecord(e1);
+        if (cudaEventSynchronize(e1) != cudaSuccess) { cudaFree(d); return -1; }
+        float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
+        if (rep > 0 && ms < best) best = ms;
+    }
+    *clk_per_step = (double)best * 1e-3 * (double)khz * 1e3 / ((double)iters * 4.0) / 8.0;
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaFree(d);
+    return 0;
+}
+extern "C" int zkb_probe_mix(int device, int a, int w, int f, double* clk_per_step) {
+    if (cudaSetDevice(device) != cudaSuccess) return -1;
+#define ZKB_RM(AA, WW, FF) if (a == AA && w == WW && f == FF) return run_mix<AA, WW, FF>(device, clk_per_step);
+    ZKB_RM(16, 0, 0) ZKB_RM(0, 8, 0) ZKB_RM(0, 8, 1) ZKB_RM(0, 8, 2)
+    ZKB_RM(16, 8, 0) ZKB_RM(16, 8, 1) ZKB_RM(16, 8, 2) ZKB_RM(16, 4, 0) ZKB_RM(16, 4, 1) ZKB_RM(16, 2, 1)
+    ZKB_RM(8, 8, 0) ZKB_RM(8, 8, 1) ZKB_RM(8, 8, 2) ZKB_RM(8, 4, 1) ZKB_RM(4, 8, 1) ZKB_RM(12, 8, 1)
+    return -2;
+}
+
 struct KParams { uint32_t k[4]; };
 template <int CFG>
 __global__ void __launch_bounds__(256, 2) k_probe_blakex(uint64_t* out, int iters, KParams kp) {
