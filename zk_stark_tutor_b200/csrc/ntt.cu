@@ -52,7 +52,9 @@ struct PassParams {
     DevPow sc;
     uint32_t has_post;           // multiply stored value by `post` (n^-1 for the iNTT)
     fe post;
-    const fe* tw_s;              // w_S^j * R, j < S/2
+    const fe* tw_s;              // w_S^j * R, j < S
+    const fe* tw_x;              // k_ntt_rr<.., .., false, false, true>: the pass's inter-pass twiddles themselves, tw_x[k * tw_x_cols + col] =
+    uint64_t tw_x_cols;          //   w^(k * col * tw_mul) * R (* n^-1 for an inverse transform) - see tw_exact_table/2
     // two-level outer index (four-pass transforms): outer = oa + outer_a_count * ob
     uint32_t outer_a_count;      // 0: single level
     uint64_t ld_outer2, st_outer2;
@@ -279,7 +281,7 @@ template <int LOGR> __host__ __device__ constexpr int brev_c(int i) {
     return r;
 }
 
-template <int LR1, int LR2, bool TRANSPOSED, bool EXCHANGE = false>
+template <int LR1, int LR2, bool TRANSPOSED, bool EXCHANGE = false, bool TWX = false>
 __global__ void __launch_bounds__(ZKB_NTT_THREADS, 2) k_ntt_rr(const PassParams p) {
     extern __shared__ uint4 smem_raw[];
     constexpr uint32_t R1 = 1u << LR1, R2 = 1u << LR2, S = R1 * R2;
@@ -331,7 +333,9 @@ __global__ void __launch_bounds__(ZKB_NTT_THREADS, 2) k_ntt_rr(const PassParams 
         for (uint32_t s0 = 0; s0 < R2; s0++) x[s0] = sm[(size_t)(ka * R2 + s0) * pitch + b];
         dft_dif<LR2>(x, tws, R1);
         fe t, step;
-        if (p.has_tw) {
+        const fe* txp = nullptr;                               // TWX: this thread's column of the exact twiddle table
+        if (TWX) txp = p.tw_x + (uint64_t)ka * p.tw_x_cols + ((uint64_t)inner * B + b);
+        else if (p.has_tw) {
             const uint64_t col = (uint64_t)inner * B + b;
             t = pow2lvl_c(p.tw, (uint64_t)ka * col * p.tw_mul);
             step = pow2lvl_c(p.tw, (uint64_t)R1 * col * p.tw_mul);
@@ -345,7 +349,10 @@ __global__ void __launch_bounds__(ZKB_NTT_THREADS, 2) k_ntt_rr(const PassParams 
 #pragma unroll
         for (uint32_t kb = 0; kb < R2; kb++) {
             fe y = x[brev_c<LR2>(kb)];
-            if (p.has_tw) {
+            if (TWX) {
+                // one look-up and one product per output instead of the running product's two (and the table carries n^-1)
+                y = fe_montmul(y, fe_ldg(txp + (uint64_t)(R1 * kb) * p.tw_x_cols));
+            } else if (p.has_tw) {
 #if (ZKB_NTT_INLINE_DFT & 4)
                 y = fe_montmul(y, t);
                 if (kb + 1 < R2) t = fe_montmul(t, step);
@@ -459,6 +466,7 @@ static int launch_rr_t(zkb_ctx* c, const PassParams& p, uint32_t tiles, uint32_t
     LaunchScope ls(c, K_NTT_PASS);
     if (p.transposed && (p.has_oscale || p.n_peers)) k_ntt_rr<LR1, LR2, true, true><<<grid, ZKB_NTT_THREADS, smem, c->stream>>>(p);
     else if (p.transposed) k_ntt_rr<LR1, LR2, true><<<grid, ZKB_NTT_THREADS, smem, c->stream>>>(p);
+    else if (p.tw_x) k_ntt_rr<LR1, LR2, false, false, true><<<grid, ZKB_NTT_THREADS, smem, c->stream>>>(p);
     else k_ntt_rr<LR1, LR2, false><<<grid, ZKB_NTT_THREADS, smem, c->stream>>>(p);
     return 0;
 }
@@ -467,6 +475,7 @@ static cudaError_t rr_attrs() {
     cudaError_t e = cudaFuncSetAttribute(k_ntt_rr<LR1, LR2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_ntt_rr<LR1, LR2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_ntt_rr<LR1, LR2, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_ntt_rr<LR1, LR2, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
     return e;
 }
 // The dynamic shared-memory opt-in is a per-DEVICE attribute of a kernel: it is set for the context's device
@@ -542,6 +551,54 @@ static int tw_s_table(zkb_ctx* c, const fe& root, uint32_t log_n, uint32_t log_s
     return 0;
 }
 
+// ---- exact inter-pass twiddle tables ---------------------------------------------------------------------------------------------
+// Pass i multiplies output k of column m by w_N^(k m N_0..N_{i-1}): N_i x M_i = N / (N_0..N_{i-1}) distinct factors.  For every pass but
+// the first that is a small table (2^16 entries for the middle pass of a 2^24 transform, 1 MB, L2-resident): the pass then does ONE
+// look-up and ONE product per output where the running product t *= step does two, and an inverse transform's n^-1 is folded into
+// the table (no scaling pass, no scaling products).  Tables are cached per context (least recently used of 12 is evicted).
+static const uint64_t TWX_MAX_ENTRIES = 1ull << 20;
+struct TwExact { fe root; uint32_t log_n; uint64_t tw_mul, rows, cols; bool has_post; fe* d; uint64_t stamp; };
+struct TwExactCache { std::vector<TwExact> v; uint64_t clock = 0; };
+static void tw_exact_destroy(void* p) {
+    TwExactCache* t = (TwExactCache*)p;
+    for (auto& e : t->v) cudaFree(e.d);
+    delete t;
+}
+__global__ void k_tw_exact(fe* __restrict__ out, uint64_t rows, uint64_t cols, uint64_t tw_mul, DevPow tw, uint32_t has_post, fe post) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows * cols) return;
+    const uint64_t k = i / cols, m = i - k * cols;
+    fe t = pow2lvl(tw, k * m * tw_mul);
+    if (has_post) t = fe_montmul(t, post);                  // post = n^-1 R: (w R)(n^-1 R) / R = w n^-1 R
+    fe_store(out + i, t);
+}
+static int tw_exact_table(zkb_ctx* c, const fe& root, uint32_t log_n, uint64_t tw_mul, uint64_t rows, uint64_t cols, const DevPow& tw,
+                          bool has_post, const fe& post, const fe** out) {
+    TwExactCache* cache = nullptr;
+    for (auto& at : c->attachments) if (at.destroy == tw_exact_destroy) cache = (TwExactCache*)at.p;
+    if (!cache) { cache = new TwExactCache(); c->attachments.push_back({cache, tw_exact_destroy}); }
+    cache->clock++;
+    for (auto& e : cache->v)
+        if (e.log_n == log_n && e.tw_mul == tw_mul && e.rows == rows && e.cols == cols && e.has_post == has_post && fe_eq(e.root, root)) {
+            e.stamp = cache->clock; *out = e.d; return 0;
+        }
+    if (cache->v.size() >= 12) {
+        size_t victim = 0;
+        for (size_t i = 1; i < cache->v.size(); i++) if (cache->v[i].stamp < cache->v[victim].stamp) victim = i;
+        ZKB_CUDA(c, cudaStreamSynchronize(c->stream));
+        cudaFree(cache->v[victim].d);
+        cache->v.erase(cache->v.begin() + victim);
+    }
+    TwExact e{root, log_n, tw_mul, rows, cols, has_post, nullptr, cache->clock};
+    ZKB_CUDA(c, cudaMalloc(&e.d, sizeof(fe) * rows * cols));
+    { LaunchScope ls(c, K_POW_TABLE); k_tw_exact<<<(unsigned)((rows * cols + 255) / 256), 256, 0, c->stream>>>(e.d, rows, cols, tw_mul, tw, has_post ? 1u : 0u, post); }
+    cudaError_t le = cudaGetLastError();
+    if (le != cudaSuccess) { cudaFree(e.d); return set_err(c, ZKB_ERR_CUDA, "k_tw_exact failed: %s", cudaGetErrorString(le)); }
+    cache->v.push_back(e);
+    *out = e.d;
+    return 0;
+}
+
 int ntt_exec(zkb_ctx* c, fe root, const fe* d_in, size_t n_in, size_t in_stride, fe* d_out,
              size_t out_stride, size_t batch, uint32_t log_n, const NttOpts& o) {
     if (batch == 0) return 0;
@@ -608,6 +665,10 @@ int ntt_exec(zkb_ctx* c, fe root, const fe* d_in, size_t n_in, size_t in_stride,
     uint64_t M[4], Nprod[5];
     Nprod[0] = 1;
     for (int i = 0; i < passes; i++) { Nprod[i + 1] = Nprod[i] << wdt[i]; M[i] = N >> (ilog2_u64(Nprod[i + 1])); }
+    // the LAST pass with a small exact twiddle table also applies an inverse transform's n^-1 (folded into the table)
+    int post_pass = -1;
+    if (base.has_post && !getenv("ZKB_NTT_NO_TWX"))
+        for (int i = 0; i + 1 < passes; i++) if ((N >> ilog2_u64(Nprod[i])) <= TWX_MAX_ENTRIES) post_pass = i;
     for (int i = 0; i + 1 < passes; i++) {
         // pass i: N_i-point transforms over digit n_i (stride M_i) for every prefix (k_0 .. k_{i-1}) and column m < M_i,
         // B adjacent columns per tile; then the twiddle w_{M_{i-1}}^(k_i m) = w_N^(k_i m N_0...N_{i-1})
@@ -631,6 +692,10 @@ int ntt_exec(zkb_ctx* c, fe root, const fe* d_in, size_t n_in, size_t in_stride,
             p.has_scale = o.has_scale; p.sc = sc;
         }
         p.has_tw = 1; p.tw = tw; p.tw_mul = Nprod[i];
+        if ((N >> ilog2_u64(Nprod[i])) <= TWX_MAX_ENTRIES && !getenv("ZKB_NTT_NO_TWX")) {
+            p.tw_x_cols = M[i];
+            ZKB_TRY(tw_exact_table(c, root, log_n, Nprod[i], 1ull << wdt[i], M[i], tw, i == post_pass, base.post, &p.tw_x));
+        }
         ZKB_TRY(tw_table(wdt[i], &p.tw_s));
         ZKB_TRY(launch_pass_rr(c, p, (uint32_t)(Nprod[i] * p.inner_count), (uint32_t)batch));
     }
@@ -638,6 +703,7 @@ int ntt_exec(zkb_ctx* c, fe root, const fe* d_in, size_t n_in, size_t in_stride,
         // outer = (k_1 .. k_{P-2}); transposing store X[k_0 + N_0 k_1 + N_0 N_1 k_2 + ...]
         const int f = passes - 1;
         PassParams p = base;
+        if (post_pass >= 0) p.has_post = 0;                      // n^-1 already applied by pass `post_pass`
         p.in = A; p.out = d_out;
         p.log_s = wdt[f];
         uint32_t lb = TILE_LOG - wdt[f];
