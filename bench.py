@@ -64,8 +64,11 @@ def parse():
     ap.add_argument("--proofs", type=int, default=1024)
     ap.add_argument("--proof-batch", type=int, default=64, help="proofs workload: proofs that advance in lockstep per launch (0: one proof per call sequence)")
     ap.add_argument("--columns", type=int, default=64)
+    ap.add_argument("--exact-log-n", action="store_true", help="columns workload: take --log-n literally (by default 24 means the configs[3] size 2^22)")
     ap.add_argument("--asm-threads", type=int, default=0, help="proofs / signatures: host threads per batched call for proof-stream assembly (0: workload default)")
     ap.add_argument("--lanes", type=int, default=4, help="columns in flight per GPU in the columns workload (streams + host threads)")
+    ap.add_argument("--in-flight", type=int, default=4, help="codeword workload: independent codewords in flight per GPU while the K steps are timed "
+                                                              "(1: one after the other, every step host-synchronous - also measured and reported as `single_in_flight`)")
     return ap.parse_args()
 
 
@@ -171,7 +174,7 @@ def reference_arm(args):
     # codeword takes the reference's algorithm ~10 minutes per core.  `config` names the workload the B200 arm ran; the sample and
     # the flagged n log n extrapolation to it are in cpu_baseline.
     columns_mode = args.workload == "columns"
-    log_n = 22 if (columns_mode and args.log_n == 24) else args.log_n
+    log_n = 22 if (columns_mode and args.log_n == 24 and not args.exact_log_n) else args.log_n
     steps, warmup = max(1, args.steps), max(0, args.warmup)
     t0 = time.perf_counter()
     cpu_lde_fri_commit(12, SEED)
@@ -193,7 +196,8 @@ def reference_arm(args):
         "impl": "reference", "metric": METRIC, "value": eps / 1e6, "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": warmup,
         "ms_per_step": ms, "higher_is_better": True, "scaling": "strong" if columns_mode else "weak", "vs_baseline": None,
         "dtype": "u128 (prime field, integer)", "data": "synthetic",
-        "config": codeword_config(args, log_n, rounds, n >> (rounds - 1), columns_mode, args.gpus, args.lanes if (columns_mode and args.lanes > 1) else 0),
+        "config": codeword_config(args, log_n, rounds, n >> (rounds - 1), columns_mode, args.gpus, args.lanes if (columns_mode and args.lanes > 1) else 0,
+                                  0 if columns_mode else max(1, args.in_flight)),
         "cpu_baseline": {"value": eps / 1e6, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
                          "sample_log_n": sample_log,
                          "extrapolated": {"log_n": log_n, "value": ext / 1e6,
@@ -365,7 +369,7 @@ def lde_commit_record(args, env, columns_mode, steps, sub=False):
     torch, zk = env.torch, env.zk
     from zk_stark_tutor_b200 import synth, columns as colmod
     rank, world, local, ctx, stream = env.rank, env.world, env.local, env.ctx, env.stream
-    log_n = 22 if (columns_mode and args.log_n == 24) else args.log_n
+    log_n = 22 if (columns_mode and args.log_n == 24 and not args.exact_log_n) else args.log_n
     my_cols = colmod.partition(args.columns, world, rank) if columns_mode else [rank]
     n, n_coeffs = 1 << log_n, (1 << log_n) // EF
     field = zk.Field()
@@ -405,6 +409,32 @@ def lde_commit_record(args, env, columns_mode, steps, sub=False):
     pipe = None
     if columns_mode and args.lanes > 1:
         pipe = colmod.ColumnPipeline(local, (GENERATOR, omega, n, EF, NCC), lanes=args.lanes)
+    # codeword mode: the metric is a THROUGHPUT, and a single FRI commit is a serial chain whose tree tops and small layers leave most SMs idle
+    # (0.73 ms of 9.7 at 2^24, half of the step at 2^20).  The K timed steps therefore go through `in_flight` lanes (contexts with their own
+    # streams): step k + 1 starts while step k is in its latency-bound phases, and in the e2e arm its H2D copy overlaps step k's kernels.
+    flight = None
+    in_flight = 0 if (columns_mode or sub) else max(1, args.in_flight)
+    ring_dev, ring_host = dev_cols, host_cols
+    if in_flight > 1:
+        flight = colmod.ColumnPipeline(local, (GENERATOR, omega, n, EF, NCC), lanes=in_flight)
+        # overlapping steps cannot be separated by an L2 flush: the inputs cycle through distinct buffers of > 1.5 x L2 in total instead
+        nb = int(min(48, max(in_flight, -(-(192 << 20) // (n_coeffs * 16)))))
+        ring_host = host_cols + [torch.from_numpy(synth.elements(SEED + 7919 * (k + 1) + rank, n_coeffs).view(np.int64)).pin_memory() for k in range(nb - 1)]
+        ring_dev = dev_cols + [h.cuda(non_blocking=True) for h in ring_host[1:]]
+        torch.cuda.synchronize()
+
+    def timed_flight(ring, nsteps):
+        """K steps (one codeword each) through the lanes; device-timed from before the first launch to after the last kernel"""
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        env.barrier()
+        l0 = sum(cx.launches for cx in flight.ctxs)
+        env.flush.fill_(1)
+        a.record(stream)
+        stream.synchronize()
+        flight.run([ring[k % len(ring)] for k in range(nsteps)], zk.IndependentProofStream, keep_roots=False)   # returns when every lane's stream has drained
+        b.record(stream)
+        env.barrier()
+        return env.max_over_ranks(a.elapsed_time(b)), sum(cx.launches for cx in flight.ctxs) - l0
 
     def step(bufs):
         """one step = LDE + FRI commit of every local column (one in codeword mode)"""
@@ -439,9 +469,19 @@ def lde_commit_record(args, env, columns_mode, steps, sub=False):
 
     for _ in range(max(args.warmup, 3)):
         step(dev_cols)
-    sampler = ClockSampler(local) if rank == 0 else None
-    total_ms, launches, _ = timed(dev_cols, steps, False)
-    clocks = sampler.stop() if sampler else None
+    single = None
+    if flight is not None:
+        # one codeword at a time first (round 1's measurement; the per-kernel shares below belong to it), then the K steps in flight
+        s_ms, _, _ = timed(dev_cols, steps, False)
+        flight.run([ring_dev[k % len(ring_dev)] for k in range(max(args.warmup, 3) + in_flight)], zk.IndependentProofStream, keep_roots=False)
+        sampler = ClockSampler(local) if rank == 0 else None
+        total_ms, launches = timed_flight(ring_dev, steps)
+        clocks = sampler.stop() if sampler else None
+        single = {"ms_per_step": s_ms / steps}
+    else:
+        sampler = ClockSampler(local) if rank == 0 else None
+        total_ms, launches, _ = timed(dev_cols, steps, False)
+        clocks = sampler.stop() if sampler else None
     # per-kernel device time (CUDA events around every launch) in a separate pass: the two event records per
     # launch cost ~0.1 ms per step, which does not belong in the headline number
     prof_steps = max(1, min(steps, 5))
@@ -450,9 +490,15 @@ def lde_commit_record(args, env, columns_mode, steps, sub=False):
         step(host_cols)
     e2e_steps = max(3, steps // 2)
     e2e_ms, _, _ = timed(host_cols, e2e_steps, False)
+    if flight is not None:
+        single["e2e_ms_per_step"] = e2e_ms / e2e_steps
+        flight.run([ring_host[k % len(ring_host)] for k in range(in_flight + 1)], zk.IndependentProofStream, keep_roots=False)
+        e2e_steps = steps
+        e2e_ms, _ = timed_flight(ring_host, e2e_steps)
+        flight.close()
     if pipe is not None:
         pipe.close()
-    del dev_cols, host_cols
+    del dev_cols, host_cols, ring_dev, ring_host
     torch.cuda.empty_cache()
     if rank != 0:
         return None
@@ -482,7 +528,7 @@ def lde_commit_record(args, env, columns_mode, steps, sub=False):
                 "achieved": achieved_alu, "peak": alu_peak, "unit": "T lane-ops/s", "frac": (achieved_alu / alu_peak) if alu_peak else None,
                 "traffic": None,
                 "peak_source": "ALU-pipe issue rate measured live on this GPU (csrc/probe.cu: PRMT / LOP3 / IADD3 / SHF all issue at 0.5 warp-instr/clk/SMSP)",
-                "launch_ms": dur * 1e3, "share_of_step": ms_l / prof_steps / ms_per_step,
+                "launch_ms": dur * 1e3, "share_of_step": ms_l / prof_steps / (single["ms_per_step"] if single else ms_per_step),
                 "compressions_per_launch": compressions, "alu_pipe_instr_per_compression": 2014, "canonical_ops_per_compression": 2144,
                 "compressions_per_s": compressions / dur,
                 "frac_of_measured_blake2b_ceiling": (compressions / dur / (probe["blake2b_Gcompress_per_s"] * 1e9)) if probe.get("blake2b_Gcompress_per_s") else None,
@@ -491,26 +537,32 @@ def lde_commit_record(args, env, columns_mode, steps, sub=False):
                         "frac": alg_bytes / dur / 1e9 / peaks["hbm_gbs"] if peaks.get("hbm_gbs") else None, "peak_source": peak_src,
                         "algorithmic_bytes": alg_bytes,
                         "note": "not the binding bound: the kernel moves 24 B per leaf and executes 3,776 ALU-pipe instructions per leaf"},
-                "note": "traffic: not measured in this run (ncu capture: profiles/r01_ncu_full_final_leaf8_ntt_node8.txt, 413 MB DRAM for 403 MB algorithmic at 2^24)"}
+                "note": "traffic: not measured in this run (ncu --set full capture of this kernel, profiles/r02b_ncu_full_leaf.txt: 269 MB read + 149 MB written = 418 MB of DRAM traffic for 403 MB algorithmic at 2^24)"}
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if columns_mode else "weak", "vs_baseline": None,
         "dtype": "u128 (prime field p = 1 + 407*2^119, 4x32-bit limb Montgomery; BLAKE2b-512 on u32 pairs)", "data": "synthetic",
-        "config": codeword_config(args, log_n, rounds, last_len, columns_mode, world, args.lanes if pipe is not None else 0),
+        "config": codeword_config(args, log_n, rounds, last_len, columns_mode, world, args.lanes if pipe is not None else 0, in_flight),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": cols_here * n_coeffs * 16, "d2h_bytes_per_step": cols_here * (rounds * 64 + last_len * 16),
-                "ms_per_step": e2e_ms / e2e_steps, "api": "zkb_lde_fri_commit_ps with pinned host coefficients"},
+                "ms_per_step": e2e_ms / e2e_steps, "api": "zkb_lde_fri_commit_ps with pinned host coefficients"
+                                                          + (" (%d steps, %d codewords in flight: each step's H2D copy overlaps the previous steps' kernels)" % (e2e_steps, in_flight) if flight is not None else "")},
         "gpu_launches": launches, "kernels": kern, "dominant_kernel": dom,
         "kernels_note": "per-kernel times from %d separately profiled step(s) (events around every launch); value / ms_per_step are timed without them" % prof_steps,
         "parity": {"checked_before_timing": "sha256 of the proof-stream bytes (roots + last codeword) == tests/golden/bench_digests.json (CPU oracle)",
                    "columns_checked_on_rank0": checked},
         "roofline": roof, "clocks": clocks,
     }
+    if single is not None:
+        single.update({"value": units / (single["ms_per_step"] * 1e-3) / 1e6, "e2e_value": units / (single["e2e_ms_per_step"] * 1e-3) / 1e6, "unit": UNIT,
+                       "note": "the same K steps one after the other, every step host-synchronous, L2 flushed between steps (rounds 1 / 2a reported this as "
+                               "value / e2e); `kernels` and `roofline.share_of_step` are per step of this mode"})
+        line["single_in_flight"] = single
     if not args.no_cpu_baseline and world == 1 and not sub:
         line["cpu_baseline"] = cpu_baseline_record(args)
     return line
 
 
-def codeword_config(args, log_n, rounds, last_len, columns_mode, world, lanes):
+def codeword_config(args, log_n, rounds, last_len, columns_mode, world, lanes, in_flight=0):
     """the `config` object of the LDE + FRI-commit workloads; the reference arm prints the same one (its bounded sample is
     described in cpu_baseline.sample)"""
     return {"workload": ("configs[3]: %d trace columns x 2^%d dealt round-robin over %d GPU(s); per column: " % (args.columns, log_n, world)
@@ -519,9 +571,12 @@ def codeword_config(args, log_n, rounds, last_len, columns_mode, world, lanes):
                         "(%d roots, %d folds, last codeword %d; ef 4, 64 colinearity tests)%s"
                         % (log_n - 2, log_n, rounds, rounds - 1, last_len, "" if columns_mode else ", one codeword per GPU"),
             "log_n": log_n, "expansion_factor": EF, "num_colinearity_tests": NCC, "rounds": rounds,
-            "l2": "flushed between steps (256 MiB write, untimed); per-step CUDA events summed; working set per step > L2",
+            "l2": ("the K steps overlap (%d codewords in flight), so no flush between them: inputs cycle through distinct buffers of > 1.5 x L2 in total "
+                   "(at most 48), one CUDA-event pair around the K steps; working set per step %s L2" % (in_flight, "<" if log_n < 22 else ">"))
+                  if in_flight > 1 else "flushed between steps (256 MiB write, untimed); per-step CUDA events summed; working set per step > L2",
             "parallelism": "independent codewords / columns per rank, no data-path collective"
-                           + (", %d columns in flight per GPU" % lanes if lanes else "")}
+                           + (", %d columns in flight per GPU" % lanes if lanes else "")
+                           + (", %d codewords in flight per GPU (a step = one codeword; single_in_flight = one at a time)" % in_flight if in_flight > 1 else "")}
 
 
 def cpu_baseline_record(args):
