@@ -67,6 +67,7 @@ def parse():
     ap.add_argument("--exact-log-n", action="store_true", help="columns workload: take --log-n literally (by default 24 means the configs[3] size 2^22)")
     ap.add_argument("--asm-threads", type=int, default=0, help="proofs / signatures: host threads per batched call for proof-stream assembly (0: workload default)")
     ap.add_argument("--lanes", type=int, default=4, help="columns in flight per GPU in the columns workload (streams + host threads)")
+    ap.add_argument("--spin-sync", action="store_true", help="signatures: lanes wait for the GPU by spinning (cudaStreamSynchronize) instead of polling + sleeping")
     ap.add_argument("--in-flight", type=int, default=4, help="codeword workload: independent codewords in flight per GPU while the K steps are timed "
                                                               "(1: one after the other, every step host-synchronous - also measured and reported as `single_in_flight`)")
     return ap.parse_args()
@@ -779,7 +780,7 @@ def signatures_arm(args, ctx, stream, rank, world, local, barrier):
     if lanes > 1:
         for cx in ctxs:      # the lanes already are the host parallelism: few assembly threads per batched call (16: 8,339/s, 4: 9,666/s, 1: 9,724/s)
             cx.check(cx.lib.zkb_ctx_assembly_threads(cx.h, args.asm_threads or 2))
-            cx.check(cx.lib.zkb_ctx_blocking_sync(cx.h, 1))     # 8 lanes on 16 shared cores: sleep while the GPU works (6.4k vs 5.0k signatures/s on a busy host)
+            cx.check(cx.lib.zkb_ctx_blocking_sync(cx.h, 0 if args.spin_sync else 1))     # 8 lanes on 16 shared cores: sleep while the GPU works (6.4k vs 5.0k signatures/s on a busy host)
     starks = [zk.Stark(pr["expansion_factor"], pr["num_collinearity_checks"], pr["security_level"], pr["num_registers"], pr["num_cycles"],
                        pr["transition_constraints_degree"], ctx=cx) for cx in ctxs]
     stark = starks[0]

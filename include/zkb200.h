@@ -372,6 +372,35 @@ int zkb_fri_prove_batch(zkb_ctx* ctx, const zkb_fri_params* p, const void* codew
  * idx[i*k .. i*k+k) and appends to ps[i]; trees that share a proof stream append in increasing tree order. */
 int zkb_merkle_open_ps_batch(zkb_tree* const* trees, size_t count, const uint64_t* idx, size_t k, zkb_ps* const* ps);
 
+/* Stark::prove (stark.rs:276-563) for `batch` instances of one AIR as ONE call: randomized trace -> interpolation + LDE
+ * (zkb_trace_lde_batch) -> boundary quotients (zkb_air_boundary_quotients) -> commits (zkb_merkle_build_batch) -> randomizer
+ * polynomial -> weights from each transcript -> transition quotients + combination (zkb_air_combine, degree check of
+ * stark.rs:451-464) -> FRI::prove (zkb_fri_prove_batch) -> Value / Path openings at the quadrupled indices
+ * (zkb_merkle_open_ps_batch).  The proofs are left in `ps` (read them with zkb_ps_digest); per instance the bytes are those of
+ * the call sequence above, which zk_stark_tutor_b200/stark.py `prove_batch` issues stage by stage. */
+typedef struct zkb_stark_shape {
+    uint8_t omicron[16];                 /* generator of the trace domain (stark.rs:74-77)                               */
+    uint64_t omicron_order;
+    uint64_t trace_length;               /* rows of the original trace                                                   */
+    uint64_t num_randomizers;            /* random rows appended to every register column (stark.rs:286-301)             */
+    uint64_t rnd_poly_len;               /* coefficients of the randomizer polynomial (stark.rs:424-432)                 */
+    uint32_t num_registers;
+    uint32_t num_constraints;
+    const int64_t* tq_degree_bounds;     /* expected degree of every transition quotient; NULL: no degree check          */
+    uint32_t num_boundary;               /* boundary conditions per instance                                             */
+    const uint32_t* boundary_register;   /* register of boundary condition j                                             */
+    const void* lagrange;                /* per register s (m_s conditions, in order): m_s x m_s values, row i = coefficients
+                                            (low first) of the Lagrange basis polynomial of its i-th point; concatenated  */
+    zkb_fri_params fri;                  /* the FRI instance (offset = the coset generator, omega, domain, ef, tests)     */
+    uint64_t proof_bytes;                /* Fiat-Shamir bytes behind the weights (32, stark.rs:447)                       */
+} zkb_stark_shape;
+/* traces: batch x trace_length x num_registers values (host; row r, register s of instance b at (b*trace_length + r)*num_registers + s);
+ * boundary_values: batch x num_boundary values (host); randomness: NULL (OS entropy, getrandom) or batch x
+ * (num_randomizers*num_registers + rnd_poly_len) field elements (host): the randomizer rows (row by row, register by register), then the
+ * randomizer polynomial; proof_len_out: NULL or batch lengths.  A failed degree check returns ZKB_ERR_DEGREE. */
+int zkb_stark_prove_batch(zkb_ctx* ctx, zkb_air* air, const zkb_stark_shape* shape, size_t batch, const void* traces,
+                          const void* boundary_values, const void* randomness, zkb_ps* const* ps, uint64_t* proof_len_out);
+
 #ifdef __cplusplus
 }
 #endif

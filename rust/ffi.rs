@@ -87,6 +87,10 @@ extern "C" {
     pub fn zkb_ntt4_run(plans: *const *mut ZkbNtt4, world: usize, root: *const u8, inverse: c_int, x_local: *const *const c_void,
                         out: *const *mut c_void) -> c_int;
 
+    // ---- Stark::prove for a batch of instances of one AIR as one call (csrc/prover.cu); `air` from zkb_air_create
+    pub fn zkb_stark_prove_batch(ctx: *mut ZkbCtx, air: *mut c_void, shape: *const c_void /* zkb_stark_shape, include/zkb200.h */, batch: usize,
+                                 traces: *const c_void, boundary_values: *const c_void, randomness: *const c_void,
+                                 ps: *const *mut ZkbPs, proof_len_out: *mut u64) -> c_int;
     // ---- per-context knobs
     pub fn zkb_ctx_tail_threads(ctx: *mut ZkbCtx, threads: c_int) -> c_int;
     pub fn zkb_ctx_blocking_sync(ctx: *mut ZkbCtx, enable: c_int) -> c_int;

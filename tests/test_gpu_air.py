@@ -81,6 +81,11 @@ def test_rpsss_signature_through_device_stark(ctx):
                        lockstep=False) == want
     assert cpu.verify(pk, doc, got) is None
     assert cpu.verify(pk, b"another document", got) is not None
+    # the one-call batched prover (zkb_stark_prove_batch) drawing its randomizers from OS entropy: a fresh proof that the restated verifier accepts
+    import os
+    fresh = stark.prove_batch([cpu.rp.trace(sk)], tcs, [cpu.rp.boundary_constraints(pk)], [zk.SignatureProofStream(doc)], [os.urandom])[0]
+    assert len(fresh) == 1156888 and fresh != got
+    assert cpu.verify(pk, doc, fresh) is None
     # a trace that violates the AIR is caught by the degree check (stark.rs:451-464)
     bad = [list(r) for r in cpu.rp.trace(sk)]
     bad[5][1] = (bad[5][1] + 1) % zk.P
@@ -185,4 +190,16 @@ def test_prove_batch_reproduces_committed_signatures(ctx):
     bad[7][0] = (bad[7][0] + 1) % zk.P
     with pytest.raises(ValueError):
         stark.prove_batch([c["trace"], bad], tcs, [c["boundary"]] * 2, [zk.SignatureProofStream(c["doc"]) for _ in range(2)], [drng(b"a"), drng(b"b")])
+    # the stage-by-stage Python call sequence (native=False) and the single C call (zkb_stark_prove_batch, the default) give the same bytes
+    staged = stark.prove_batch([c["trace"] for c in cases], tcs, [c["boundary"] for c in cases], [zk.SignatureProofStream(c["doc"]) for c in cases],
+                               [drng(c["seed"]) for c in cases], native=False)
+    assert staged == sigs
+    with pytest.raises(ValueError):
+        stark.prove_batch([c["trace"], bad], tcs, [c["boundary"]] * 2, [zk.SignatureProofStream(c["doc"]) for _ in range(2)], [drng(b"a"), drng(b"b")],
+                          native=False)
+    # OS entropy (randomness = NULL): a different, valid proof of the same size every time; packed-array traces
+    import os
+    packed = zk.stark.pack([v for row in c["trace"] for v in row]).reshape(len(c["trace"]), pr["num_registers"], 2)
+    a = stark.prove_batch([packed] * 2, tcs, [c["boundary"]] * 2, [zk.SignatureProofStream(c["doc"]) for _ in range(2)], [os.urandom] * 2)
+    assert [len(x) for x in a] == [1156888] * 2 and a[0] != a[1]
     stark.close()

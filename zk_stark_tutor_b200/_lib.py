@@ -41,6 +41,13 @@ class AirShape(ctypes.Structure):
                 ("transition_zerofier", vp), ("transition_zerofier_len", sz), ("shifts", c_u64p)]
 
 
+class StarkShape(ctypes.Structure):
+    _fields_ = [("omicron", ctypes.c_uint8 * 16), ("omicron_order", u64), ("trace_length", u64), ("num_randomizers", u64),
+                ("rnd_poly_len", u64), ("num_registers", ctypes.c_uint32), ("num_constraints", ctypes.c_uint32),
+                ("tq_degree_bounds", ctypes.POINTER(ctypes.c_int64)), ("num_boundary", ctypes.c_uint32),
+                ("boundary_register", ctypes.POINTER(ctypes.c_uint32)), ("lagrange", vp), ("fri", FriParams), ("proof_bytes", u64)]
+
+
 FS_CALLBACK = ctypes.CFUNCTYPE(ctypes.c_int, vp, ctypes.c_uint32, c_u8p, ctypes.c_int, c_u8p)
 
 # name -> (restype, argtypes); mirrors include/zkb200.h one to one
@@ -132,6 +139,7 @@ PROTOTYPES = {
     "zkb_air_combine": (ctypes.c_int, [vp, sz, c_u8p, vp, sz, sz, vp, sz, vp, sz, vp, sz]),
     "zkb_trace_lde_batch": (ctypes.c_int, [vp, c_u8p, u64, u64, c_u8p, u64, c_u8p, vp, sz, sz, vp, sz, vp]),
     "zkb_coset_degree_batch": (ctypes.c_int, [vp, c_u8p, vp, sz, sz, sz, ctypes.POINTER(ctypes.c_int64)]),
+    "zkb_stark_prove_batch": (ctypes.c_int, [vp, vp, ctypes.POINTER(StarkShape), sz, vp, vp, vp, ctypes.POINTER(vp), c_u64p]),
 }
 
 

@@ -328,7 +328,7 @@ class Stark:
                 t.close()
 
     # ---- batches of instances of one AIR in lockstep (csrc/stark.cu, csrc/air.cu, csrc/batch.cu) --------------------------
-    def prove_batch(self, traces, transition_constraints, boundaries, proof_streams, rngs, check_degrees=True, return_bytes=True):
+    def prove_batch(self, traces, transition_constraints, boundaries, proof_streams, rngs, check_degrees=True, return_bytes=True, native=True):
         """Stark::prove for B instances of the same AIR (same constraint list, same boundary POSITIONS; values, traces, documents and
         randomness differ), every launch carrying all of them: trace interpolation + LDE (zkb_trace_lde_batch), boundary quotients in
         evaluation form (zkb_air_boundary_quotients), commits (zkb_merkle_build_batch), the evaluation-form middle (zkb_air_combine),
@@ -342,6 +342,10 @@ class Stark:
         from .context import le16
         ctx, lib, n, nr, B = self.ctx, self.ctx.lib, self.fri_domain_length, self.num_registers, len(traces)
         assert B == len(boundaries) == len(proof_streams) == len(rngs) and B >= 1
+        import os
+        if native and not os.environ.get("ZKB_STAGED_PROVER"):
+            # the whole call sequence below as ONE C call (csrc/prover.cu, zkb_stark_prove_batch): same bytes, no Python between the stages
+            return self._prove_batch_native(traces, transition_constraints, boundaries, proof_streams, rngs, check_degrees, return_bytes)
         dev = torch.device("cuda", ctx.device)
         L = len(traces[0]) + self.num_randomizers
         positions = tuple((c, r) for c, r, _ in boundaries[0])
@@ -431,6 +435,65 @@ class Stark:
             for i in range(K * B - 1, -1, -1):          # tree 0 owns the shared arena: free it last
                 if trees[i]:
                     lib.zkb_merkle_free(trees[i])
+
+    def _prove_batch_native(self, traces, transition_constraints, boundaries, proof_streams, rngs, check_degrees, return_bytes):
+        import ctypes
+        import os
+        from . import _lib
+        from .context import ZkbError
+        ctx, lib, nr, B = self.ctx, self.ctx.lib, self.num_registers, len(traces)
+        t0 = len(traces[0])
+        positions = tuple((c, r) for c, r, _ in boundaries[0])
+        assert all(tuple((c, r) for c, r, _ in b) == positions for b in boundaries), "a batch shares the boundary positions"
+        air, _ = self._air_handle(transition_constraints, positions, t0 + self.num_randomizers)
+        shape = self._stark_shape(transition_constraints, positions, t0, check_degrees)
+        tr = np.empty((B, t0, nr, 2), dtype=np.uint64)
+        for b, t in enumerate(traces):
+            assert len(t) == t0
+            tr[b] = t.reshape(t0, nr, 2) if isinstance(t, np.ndarray) else pack([v for row in t for v in row]).reshape(t0, nr, 2)
+        bv = pack([v for bd in boundaries for _, _, v in bd]) if positions else np.zeros((1, 2), dtype=np.uint64)
+        n_tr, n_rp = self.num_randomizers * nr, shape.rnd_poly_len
+        rnd = None
+        if not all(r is os.urandom for r in rngs):       # reproducible byte sources: the same draws, in the same order, as `prove` (stark.rs:286-301, 424-432)
+            rnd = np.ascontiguousarray(np.stack([np.concatenate([sample_many(r, n_tr), sample_many(r, n_rp)]) for r in rngs]))
+        ps_arr = (ctypes.c_void_p * B)(*[p.h.value for p in proof_streams])
+        lens = (ctypes.c_uint64 * B)()
+        try:
+            ctx.check(lib.zkb_stark_prove_batch(ctx.h, air, ctypes.byref(shape), B, tr.ctypes.data, bv.ctypes.data,
+                                                rnd.ctypes.data if rnd is not None else None, ps_arr, lens))
+        except ZkbError as e:
+            if e.code == -11:                            # ZKB_ERR_DEGREE: the degree check of stark.rs:451-464 (a panic in the reference)
+                raise ValueError(str(e)) from e
+            raise
+        for p in proof_streams:
+            p.objects = None
+        if return_bytes:
+            return [p.digest() for p in proof_streams]
+        return [int(x) for x in lens]
+
+    def _stark_shape(self, transition_constraints, positions, trace_length, check_degrees):
+        """zkb_stark_shape for (constraints, boundary positions, trace length): everything zkb_stark_prove_batch needs beside the AIR handle"""
+        import ctypes
+        from . import _lib
+        key = ("stark_shape", id(transition_constraints), positions, trace_length, bool(check_degrees))
+        if key not in self._cache:
+            nr = self.num_registers
+            tcd, tq_bounds, (counts, _, _) = self._air_shape(transition_constraints)
+            d = _lib.StarkShape()
+            d.omicron[:] = list(int(self.omicron).to_bytes(16, "little"))
+            d.omicron_order, d.trace_length, d.num_randomizers, d.rnd_poly_len = self.omicron_domain_length, trace_length, self.num_randomizers, tcd + 1
+            d.num_registers, d.num_constraints, d.num_boundary = nr, len(counts), len(positions)
+            bounds = np.asarray(tq_bounds, dtype=np.int64)
+            d.tq_degree_bounds = bounds.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)) if check_degrees else None
+            regs = np.asarray([r for _, r in positions] or [0], dtype=np.uint32)
+            d.boundary_register = regs.ctypes.data_as(ctypes.POINTER(ctypes.c_uint32))
+            basis = self._lagrange_basis(positions)
+            lag = pack([c for s in range(nr) for poly in basis[s] for c in poly] or [0])
+            d.lagrange = lag.ctypes.data
+            d.fri = self.fri.params
+            d.proof_bytes = PROOF_BYTES
+            self._cache[key] = (d, bounds, regs, lag, transition_constraints)
+        return self._cache[key][0]
 
     def _lagrange_basis(self, positions):
         """per register the Lagrange basis polynomials of its boundary points (they depend on the positions only)"""
