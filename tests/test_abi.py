@@ -221,3 +221,24 @@ def test_context_calls_fail_without_a_context(L):
     assert L.zkb_trace_lde_batch(None, None, 0, 0, None, 0, None, None, 0, 0, None, 0, None) == -2
     assert L.zkb_coset_degree_batch(None, None, None, 0, 0, 0, None) == -2
     assert L.zkb_air_combination(None, None, None, 0, None, None, None) == -2
+    assert L.zkb_stark_prove_batch(None, None, None, 0, None, None, None, None, None) == -2
+
+
+def test_stark_shape_binding_matches_the_header():
+    """the ctypes mirror of zkb_stark_shape (zkb_stark_prove_batch) has the C struct's layout: sizes and offsets from a compiled probe"""
+    import shutil
+    import subprocess
+    import tempfile
+    from zk_stark_tutor_b200 import _lib
+    if not shutil.which("gcc"):
+        pytest.skip("no gcc")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = ('#include <stddef.h>\n#include <stdio.h>\n#include "zkb200.h"\nint main(void){printf("%zu %zu %zu %zu %zu %zu\\n", sizeof(zkb_stark_shape), '
+           'offsetof(zkb_stark_shape, rnd_poly_len), offsetof(zkb_stark_shape, tq_degree_bounds), offsetof(zkb_stark_shape, lagrange), '
+           'offsetof(zkb_stark_shape, fri), offsetof(zkb_stark_shape, proof_bytes));return 0;}\n')
+    with tempfile.TemporaryDirectory() as d:
+        open(os.path.join(d, "p.c"), "w").write(src)
+        subprocess.check_call(["gcc", "-I", os.path.join(root, "include"), os.path.join(d, "p.c"), "-o", os.path.join(d, "p")])
+        got = [int(x) for x in subprocess.check_output([os.path.join(d, "p")]).split()]
+    S = _lib.StarkShape
+    assert got == [ctypes.sizeof(S), S.rnd_poly_len.offset, S.tq_degree_bounds.offset, S.lagrange.offset, S.fri.offset, S.proof_bytes.offset]
