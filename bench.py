@@ -1039,7 +1039,11 @@ def ntt_record(args, env, four, steps, sub=False):
                                        "IMAD.WIDE + IADD3 + IADD3.X on sm_100a",
                          "field_mul_per_s_at_imad_wide_peak": peak_mul, "frac_of_imad_wide_roofline": int_pipe["field_mul_per_s"] / peak_mul,
                          "note": "algorithmic multiplications ((N/2) log2 N per transform, + N for the inverse scaling) against the measured "
-                                 "IMAD.WIDE issue rate / 21; the pass executes ~1.25x the algorithmic count (inter-pass twiddles)"})
+                                 "IMAD.WIDE issue rate / 21; the passes execute ~1.02x the textbook count (w^0 twiddles skipped, inter-pass twiddles added, "
+                                 "n^-1 folded into a twiddle table)",
+                         "issue_model": "IMAD.WIDE does not overlap with ALU-pipe instructions (tools/probe_run.py mix: 16 LOP3 + 8 IMAD.WIDE = 58.9 clk against "
+                                        "32.5 / 32.4 alone), so a multiplication costs 2 clk x 24 ALU-pipe instructions + 3.3 clk x 21 wide multiplies = 117 clk per warp "
+                                        "and scheduler and a butterfly's add / sub 44 clk: 2^24 forward + inverse cannot take less than ~1.8 ms (DESIGN.md 5)"})
     line = {
         "metric": "NTT throughput, elements/s" + (" (one 2^%d NTT over %d GPUs, four-step, exchange fused into the last local pass)" % (log_n, world) if four
                                                    else " (forward + inverse NTT of 2^%d per GPU)" % log_n),
