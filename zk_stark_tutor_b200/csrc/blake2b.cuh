@@ -169,88 +169,95 @@ ZKB_HD void blake2b_node(const uint64_t (&l)[8], const uint64_t (&r)[8], uint64_
 }
 
 // ---- u128 -> ASCII decimal, packed little-endian into ten 32-bit message words ------
-// x / 10^9 for x < 2^62 (all the long division below needs)
-ZKB_HD uint32_t div1e9(uint64_t x, uint32_t& rem) {
-    uint64_t q = x / 1000000000ull;
-    rem = (uint32_t)(x - q * 1000000000ull);
-    return (uint32_t)q;
+// (round 2b: 23 quarter-rate multiplies and ~200 ALU-pipe instructions per value instead of 75 + 286 - an IMAD.WIDE blocks ALU issue,
+//  DESIGN.md 4, so the long division's and the digit extraction's wide multiplies were ~10 % of the leaf kernels)
+ZKB_HD uint32_t b2_mulhi32(uint32_t a, uint32_t b) {
+#if defined(__CUDA_ARCH__)
+    return __umulhi(a, b);
+#else
+    return (uint32_t)(((uint64_t)a * b) >> 32);
+#endif
 }
-// 9 decimal digits of c (< 10^9), most significant first, one per byte of d[0..8]
-ZKB_HD void digits9(uint32_t c, uint32_t (&d)[9]) {
-#pragma unroll
-    for (int i = 8; i >= 0; i--) {
-        uint32_t q = (uint32_t)(((uint64_t)c * 0xCCCCCCCDull) >> 35);   // c / 10
-        d[i] = c - q * 10u;
-        c = q;
-    }
+// One step of the long division by D = 10^8: x = r * 2^32 + l with r < D; returns floor(x / D), rem = x mod D.
+// M = floor(2^58 / D), so floor(x * M / 2^58) is the quotient or up to 2 below it (x * (2^58 / D - M) / 2^58 < 1.5); the remainder of
+// that estimate is < 3 D < 2^32, i.e. exact in 32-bit arithmetic, and two compares finish the step: one wide multiply, one high
+// multiply and one low multiply instead of the 64-bit division by a constant (a 64 x 64 high product + a 64-bit multiply-subtract).
+ZKB_HD uint32_t div1e8_step(uint32_t r, uint32_t l, uint32_t& rem) {
+    const uint32_t D = 100000000u, M = 2882303761u;
+    const uint64_t t = (uint64_t)r * M + b2_mulhi32(l, M);          // floor(x * M / 2^32) < 2^59
+    const uint32_t q = (uint32_t)(t >> 26);
+    const uint32_t rm = l - q * D;                                   // x - q * D, in [0, 3 D)
+    const uint32_t k = (rm >= D ? 1u : 0u) + (rm >= 2u * D ? 1u : 0u);
+    rem = rm - k * D;
+    return q + k;
+}
+// four decimal digits of x < 10^4 as ASCII bytes, most significant digit in the LOWEST byte (string order), without a wide
+// multiply: x -> two 2-digit lanes (x / 100 low, x % 100 high), both lanes -> tens with ONE multiply (lane * 103 >> 10; 99 * 103 <
+// 2^14, the lanes do not meet), then bytes = tens + (lane - 10 tens) << 8 = (lanes << 8) - 2559 tens, + "0000"
+ZKB_HD uint32_t dec4_ascii(uint32_t x) {
+    const uint32_t q = (x * 5243u) >> 19;                            // x / 100 for x < 10^4
+    const uint32_t v = (x << 16) - q * 6553599u;                     // q | (x - 100 q) << 16
+    const uint32_t t = ((v * 103u) >> 10) & 0x000F000Fu;             // tens of both lanes
+    return (v << 8) + 0x30303030u - t * 2559u;
 }
 
 // Writes the decimal string of `a` (canonical, < 2^128) into w[0..9] (bytes in string
 // order, byte 0 = lowest byte of w[0], zero padded) and returns its length (1..39).
 ZKB_HD uint32_t u128_to_dec_words(const fe& a, uint32_t (&w)[10]) {
-    // long division by 10^9 on 32-bit limbs: value = c4*10^36 + c3*10^27 + c2*10^18 + c1*10^9 + c0
-    uint32_t l0 = a.v[0], l1 = a.v[1], l2 = a.v[2], l3 = a.v[3];
+    // long division by 10^8 on 32-bit limbs: value = c4*10^32 + c3*10^24 + c2*10^16 + c1*10^8 + c0, c4 < 10^7 (the value is < 10^39)
     uint32_t c0, c1, c2, c3, c4, r;
-    // round 1: 4 limbs
-    uint32_t q3 = l3 / 1000000000u; r = l3 - q3 * 1000000000u;
-    uint32_t q2 = div1e9(((uint64_t)r << 32) | l2, r);
-    uint32_t q1 = div1e9(((uint64_t)r << 32) | l1, r);
-    uint32_t q0 = div1e9(((uint64_t)r << 32) | l0, r);
+    // round 1: 4 limbs; the quotient is < 2^101.5, its top limb <= 42
+    const uint32_t q3 = div1e8_step(0u, a.v[3], r);
+    const uint32_t q2 = div1e8_step(r, a.v[2], r);
+    const uint32_t q1 = div1e8_step(r, a.v[1], r);
+    const uint32_t q0 = div1e8_step(r, a.v[0], r);
     c0 = r;
-    // round 2: quotient < 2^98.2, q3 <= 4
+    // round 2: quotient < 2^74.9, top limb < 2^11
     r = q3;
-    uint32_t p2 = div1e9(((uint64_t)r << 32) | q2, r);
-    uint32_t p1 = div1e9(((uint64_t)r << 32) | q1, r);
-    uint32_t p0 = div1e9(((uint64_t)r << 32) | q0, r);
+    const uint32_t p2 = div1e8_step(r, q2, r);
+    const uint32_t p1 = div1e8_step(r, q1, r);
+    const uint32_t p0 = div1e8_step(r, q0, r);
     c1 = r;
-    // round 3: quotient < 2^68.3, p2 <= 19
+    // round 3: quotient < 2^48.4, top limb < 2^17
     r = p2;
-    uint32_t s1 = div1e9(((uint64_t)r << 32) | p1, r);
-    uint32_t s0 = div1e9(((uint64_t)r << 32) | p0, r);
+    const uint32_t s1 = div1e8_step(r, p1, r);
+    const uint32_t s0 = div1e8_step(r, p0, r);
     c2 = r;
-    // round 4: quotient < 2^38.4
-    uint64_t rest = ((uint64_t)s1 << 32) | s0;
-    c4 = div1e9(rest, c3);                                  // c4 <= 340
-    uint32_t d[40];
+    // round 4: quotient < 2^21.8
+    c4 = div1e8_step(s1, s0, c3);
+    // 40 digit positions (the first is always '0'): chunk -> two groups of four digits -> two message words each
+    uint32_t g[10];
     {
-        uint32_t t[9];
-        digits9(c4, t); d[0] = t[6]; d[1] = t[7]; d[2] = t[8];
-        digits9(c3, t);
+        const uint32_t cs[5] = {c4, c3, c2, c1, c0};
 #pragma unroll
-        for (int i = 0; i < 9; i++) d[3 + i] = t[i];
-        digits9(c2, t);
-#pragma unroll
-        for (int i = 0; i < 9; i++) d[12 + i] = t[i];
-        digits9(c1, t);
-#pragma unroll
-        for (int i = 0; i < 9; i++) d[21 + i] = t[i];
-        digits9(c0, t);
-#pragma unroll
-        for (int i = 0; i < 9; i++) d[30 + i] = t[i];
-        d[39] = 0;
+        for (int i = 0; i < 5; i++) {
+            const uint32_t hi = b2_mulhi32(cs[i], 0xD1B71759u) >> 13;    // c / 10^4 (exact for every 32-bit c)
+            g[2 * i] = hi;
+            g[2 * i + 1] = cs[i] - hi * 10000u;
+        }
     }
     uint32_t x[10];
 #pragma unroll
-    for (int k = 0; k < 10; k++)
-        x[k] = d[4 * k] | (d[4 * k + 1] << 8) | (d[4 * k + 2] << 16) | (d[4 * k + 3] << 24);
-    // leading zero digits z (0..38; the value 0 keeps one digit)
-    uint32_t z = 38;
+    for (int k = 0; k < 10; k++) x[k] = dec4_ascii(g[k]);
+    // first non-'0' position z (1..39; the value 0 keeps its last digit): the first word whose group is non-zero, then the lowest
+    // non-'0' byte inside it
+    uint32_t zw = 9u, ws = 0x31303030u;
 #pragma unroll
     for (int k = 9; k >= 0; k--) {
-        uint32_t xk = (k == 9) ? (x[9] & 0x00FF0000u ? x[9] : (x[9] | 0x00010000u)) : x[k];
-        // index of the lowest non-zero byte of xk
-        uint32_t lowbit = xk & (0u - xk);
-        uint32_t byte = lowbit > 0x00FFFFFFu ? 3u : (lowbit > 0x0000FFFFu ? 2u : (lowbit > 0xFFu ? 1u : 0u));
-        z = xk != 0 ? (uint32_t)(4 * k) + byte : z;
+        zw = g[k] != 0u ? (uint32_t)k : zw;
+        ws = g[k] != 0u ? x[k] : ws;
     }
-    // ASCII, then shift the 39-byte string left by z bytes (zero fill)
-#pragma unroll
-    for (int k = 0; k < 9; k++) x[k] += 0x30303030u;
-    x[9] += 0x00303030u;
-    uint32_t zb = z & 3u, zw = z >> 2;
+    const uint32_t raw = ws ^ 0x30303030u;                            // != 0
+#if defined(__CUDA_ARCH__)
+    const uint32_t zb = (uint32_t)(__ffs((int)raw) - 1) >> 3;
+#else
+    const uint32_t zb = (raw & 0xFFu) ? 0u : ((raw & 0xFF00u) ? 1u : ((raw & 0xFF0000u) ? 2u : 3u));
+#endif
+    const uint32_t z = 4u * zw + zb;
+    // shift the 40-byte string left by z bytes (zero fill)
     uint32_t y[11];
 #if defined(__CUDA_ARCH__)
-    uint32_t sel = 0x3210u + 0x1111u * zb;
+    const uint32_t sel = 0x3210u + 0x1111u * zb;
 #pragma unroll
     for (int k = 0; k < 10; k++) y[k] = __byte_perm(x[k], k < 9 ? x[k + 1] : 0u, sel);
 #else
@@ -272,7 +279,7 @@ ZKB_HD uint32_t u128_to_dec_words(const fe& a, uint32_t (&w)[10]) {
     for (int k = 0; k < 10; k++) y[k] = (zw & 8u) ? (k + 8 < 10 ? y[k + 8] : 0u) : y[k];
 #pragma unroll
     for (int k = 0; k < 10; k++) w[k] = y[k];
-    return 39u - z;
+    return 40u - z;
 }
 
 // leaf = H(decimal string of a)
