@@ -72,6 +72,22 @@ int main() {
         CHECK(fromfe(fe_from_mont(x)) == 1, "G^(2^119) != 1");
         CHECK(fe_eq(fe_mont_pow(g, 12345), fe_montmul(fe_mont_pow(g, 12344), g)), "pow");
     }
+    // leaf encoder, piece by piece: the 4-digit groups (all of them), the split of every 8-digit chunk, the division steps (edges + random)
+    for (uint32_t x = 0; x < 10000; x++) {
+        uint32_t wv = dec4_ascii(x); char b4[8]; snprintf(b4, 8, "%04u", x);
+        CHECK(memcmp(&wv, b4, 4) == 0, "dec4_ascii %u", x);
+    }
+    for (uint32_t cch = 0; cch < 100000000u; cch++) {
+        uint32_t hi = b2_mulhi32(cch, 0xD1B71759u) >> 13;
+        if (hi != cch / 10000u) { CHECK(false, "chunk / 10^4 at %u", cch); break; }
+    }
+    for (int it = 0; it < 20000000; it++) {
+        uint32_t r = (uint32_t)(rnd64() % 100000000u), l = (uint32_t)rnd64();
+        if (it < 64) { r = (it & 1) ? 99999999u : 0u; l = (it & 2) ? 0xFFFFFFFFu : ((it & 4) ? 0u : l); if (it & 8) r = (uint32_t)(rnd64() % 100000000u); if (it & 16) l = 0xFFFFFFFFu - (uint32_t)(it >> 5); }
+        u128 x = ((u128)r << 32) | l;
+        uint32_t rem, q = div1e8_step(r, l, rem);
+        if (q != (uint32_t)(x / 100000000u) || rem != (uint32_t)(x % 100000000u)) { CHECK(false, "div1e8_step r=%u l=%u", r, l); break; }
+    }
     // leaf encoder + hashes
     u128 edge[] = {0, 1, 9, 10, 11, 99, 100, 5462, 999999999, 1000000000, 1000000001,
                    (u128)1000000000 * 1000000000, (u128)1000000000 * 1000000000 - 1,
