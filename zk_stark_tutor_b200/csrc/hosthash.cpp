@@ -245,14 +245,17 @@ void zkb_shake256(const uint8_t* msg, size_t len, uint8_t* out, size_t out_len) 
 // bodies that keep their capacity removes that (0.3 ms per proof).
 static std::mutex g_pool_mu;
 static std::vector<zkb::PsBody> g_body_pool;
-static const size_t kPoolMax = 1024, kPoolKeepBytes = 8u << 20;   // <= 1024 x ~1.2 MB kept: several batches of signature streams in flight
+// <= 1024 bodies and <= 2 GB kept: several batches of ~1.2 MB signature streams in flight, or a few 35 MB proofs of 2^24-value codewords (a pinned
+// block of that size costs ~10 ms to allocate - more than the proof's kernels)
+static const size_t kPoolMax = 1024, kPoolKeepBytes = 128u << 20, kPoolTotalBytes = (size_t)2 << 30;
+static size_t g_pool_bytes = 0;
 
 static int zkb_ps_create_body(const uint8_t* document, size_t document_len, int is_signature, zkb_ps** out) {
     if (!out) return ZKB_ERR_ARG;
     zkb_ps* ps = new zkb_ps();
     {
         std::lock_guard<std::mutex> lk(g_pool_mu);
-        if (!g_body_pool.empty()) { ps->body.swap(g_body_pool.back()); g_body_pool.pop_back(); }
+        if (!g_body_pool.empty()) { ps->body.swap(g_body_pool.back()); g_body_pool.pop_back(); g_pool_bytes -= ps->body.capacity(); }
     }
     ps->body.clear();
     if (is_signature) {
@@ -268,7 +271,10 @@ void zkb_ps_free(zkb_ps* ps) {
     if (!ps) return;
     if (ps->body.capacity() >= (64u << 10) && ps->body.capacity() <= kPoolKeepBytes) {
         std::lock_guard<std::mutex> lk(g_pool_mu);
-        if (g_body_pool.size() < kPoolMax) { g_body_pool.emplace_back(); g_body_pool.back().swap(ps->body); }
+        if (g_body_pool.size() < kPoolMax && g_pool_bytes + ps->body.capacity() <= kPoolTotalBytes) {
+            g_pool_bytes += ps->body.capacity();
+            g_body_pool.emplace_back(); g_body_pool.back().swap(ps->body);
+        }
     }
     delete ps;
 }
