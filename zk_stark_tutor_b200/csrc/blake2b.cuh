@@ -179,17 +179,18 @@ ZKB_HD uint32_t b2_mulhi32(uint32_t a, uint32_t b) {
 #endif
 }
 // One step of the long division by D = 10^8: x = r * 2^32 + l with r < D; returns floor(x / D), rem = x mod D.
-// M = floor(2^58 / D), so floor(x * M / 2^58) is the quotient or up to 2 below it (x * (2^58 / D - M) / 2^58 < 1.5); the remainder of
-// that estimate is < 3 D < 2^32, i.e. exact in 32-bit arithmetic, and two compares finish the step: one wide multiply, one high
-// multiply and one low multiply instead of the 64-bit division by a constant (a 64 x 64 high product + a 64-bit multiply-subtract).
+// M = floor(2^58 / D) = 2882303761 leaves 2^58 - M D = 51711744, so x M / 2^58 = x / D - x * 51711744 / (D 2^58) > x / D - 0.771 for every
+// x < D 2^32: floor(x M / 2^58) is the quotient or ONE below it.  The remainder of that estimate is < 2 D < 2^32, i.e. exact in 32-bit
+// arithmetic, and one compare finishes the step: one wide multiply, one high multiply and one low multiply instead of the 64-bit division
+// by a constant (a 64 x 64 high product + a 64-bit multiply-subtract).
 ZKB_HD uint32_t div1e8_step(uint32_t r, uint32_t l, uint32_t& rem) {
     const uint32_t D = 100000000u, M = 2882303761u;
     const uint64_t t = (uint64_t)r * M + b2_mulhi32(l, M);          // floor(x * M / 2^32) < 2^59
     const uint32_t q = (uint32_t)(t >> 26);
-    const uint32_t rm = l - q * D;                                   // x - q * D, in [0, 3 D)
-    const uint32_t k = (rm >= D ? 1u : 0u) + (rm >= 2u * D ? 1u : 0u);
-    rem = rm - k * D;
-    return q + k;
+    const uint32_t rm = l - q * D;                                   // x - q * D, in [0, 2 D)
+    const bool up = rm >= D;
+    rem = up ? rm - D : rm;
+    return up ? q + 1u : q;
 }
 // four decimal digits of x < 10^4 as ASCII bytes, most significant digit in the LOWEST byte (string order), without a wide
 // multiply: x -> two 2-digit lanes (x / 100 low, x % 100 high), both lanes -> tens with ONE multiply (lane * 103 >> 10; 99 * 103 <
@@ -241,12 +242,22 @@ ZKB_HD uint32_t u128_to_dec_words(const fe& a, uint32_t (&w)[10]) {
     for (int k = 0; k < 10; k++) x[k] = dec4_ascii(g[k]);
     // first non-'0' position z (1..39; the value 0 keeps its last digit): the first word whose group is non-zero, then the lowest
     // non-'0' byte inside it
-    uint32_t zw = 9u, ws = 0x31303030u;
+    // (scan the five chunks, then the two groups of the chunk found: 6 compares instead of 10)
+    uint32_t zc = 4u, hs = g[8], ls = g[9], xh = x[8], xl = x[9];
+    {
+        const uint32_t cs[5] = {c4, c3, c2, c1, c0};
 #pragma unroll
-    for (int k = 9; k >= 0; k--) {
-        zw = g[k] != 0u ? (uint32_t)k : zw;
-        ws = g[k] != 0u ? x[k] : ws;
+        for (int i = 3; i >= 0; i--) {
+            const bool nz = cs[i] != 0u;
+            zc = nz ? (uint32_t)i : zc;
+            hs = nz ? g[2 * i] : hs;  ls = nz ? g[2 * i + 1] : ls;
+            xh = nz ? x[2 * i] : xh;  xl = nz ? x[2 * i + 1] : xl;
+        }
     }
+    const bool in_hi = hs != 0u;
+    const uint32_t zw = 2u * zc + (in_hi ? 0u : 1u);
+    uint32_t ws = in_hi ? xh : xl;
+    ws = (hs | ls) != 0u ? ws : 0x31303030u;                          // the value 0: keep the last '0' (the scan ended on chunk 4, word 9)
     const uint32_t raw = ws ^ 0x30303030u;                            // != 0
 #if defined(__CUDA_ARCH__)
     const uint32_t zb = (uint32_t)(__ffs((int)raw) - 1) >> 3;
