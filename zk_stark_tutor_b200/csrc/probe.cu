@@ -344,8 +344,8 @@ extern "C" int zkb_probe_blakex(int device, int cfg, double* compress_per_s, dou
     if (cudaSetDevice(device) != cudaSuccess) return -1;
     switch (cfg) {
 #define ZKB_RX(C) case C: return run_blakex<C>(device, compress_per_s, ms_out, checksum);
-        ZKB_RX(0) ZKB_RX(1) ZKB_RX(2) ZKB_RX(3) ZKB_RX(4) ZKB_RX(5) ZKB_RX(7) ZKB_RX(8) ZKB_RX(16) ZKB_RX(12) ZKB_RX(20) ZKB_RX(28)
-        ZKB_RX(33) ZKB_RX(35) ZKB_RX(39) ZKB_RX(23) ZKB_RX(55) ZKB_RX(19) ZKB_RX(51) ZKB_RX(11) ZKB_RX(43) ZKB_RX(36) ZKB_RX(37) ZKB_RX(21) ZKB_RX(53)
+        // (25 configurations were measured in round 1, profiles/r01_probe.txt; ten stay compiled)
+        ZKB_RX(0) ZKB_RX(1) ZKB_RX(2) ZKB_RX(3) ZKB_RX(4) ZKB_RX(8) ZKB_RX(16) ZKB_RX(28) ZKB_RX(33) ZKB_RX(35)
         default: return -2;
     }
 }
@@ -409,8 +409,8 @@ extern "C" int zkb_probe_blakey(int device, int cfg, double* compress_per_s, dou
     if (cudaSetDevice(device) != cudaSuccess) return -1;
     switch (cfg) {
 #define ZKB_RY(C) case C: return run_blakey<C>(device, compress_per_s, ms_out, checksum);
-        ZKB_RY(0) ZKB_RY(1) ZKB_RY(2) ZKB_RY(3) ZKB_RY(4) ZKB_RY(29) ZKB_RY(9) ZKB_RY(14) ZKB_RY(19) ZKB_RY(24) ZKB_RY(49)
-        ZKB_RY(59) ZKB_RY(64) ZKB_RY(69) ZKB_RY(74) ZKB_RY(99) ZKB_RY(13) ZKB_RY(18) ZKB_RY(23) ZKB_RY(68) ZKB_RY(73) ZKB_RY(34) ZKB_RY(39) ZKB_RY(44)
+        // (24 configurations were measured, profiles/r02_probe_blakey.txt; the eight that span the result stay compiled - each costs ~5 s of build time)
+        ZKB_RY(0) ZKB_RY(2) ZKB_RY(4) ZKB_RY(29) ZKB_RY(24) ZKB_RY(49) ZKB_RY(74) ZKB_RY(99)
         default: return -2;
     }
 }
@@ -454,7 +454,8 @@ extern "C" int zkb_probe_blake(int device, int variant, int minb, double* compre
         if (minb == 2) return run_blake<V, 2>(device, compress_per_s, ms_out, checksum); \
         if (minb == 3) return run_blake<V, 3>(device, compress_per_s, ms_out, checksum); \
         return run_blake<V, 4>(device, compress_per_s, ms_out, checksum); }
-    ZKB_RB(32) ZKB_RB(-1) ZKB_RB(0) ZKB_RB(1) ZKB_RB(2) ZKB_RB(3) ZKB_RB(5) ZKB_RB(7) ZKB_RB(9) ZKB_RB(11) ZKB_RB(15) ZKB_RB(17) ZKB_RB(19) ZKB_RB(4) ZKB_RB(8) ZKB_RB(6)
+    // (16 variants were measured in round 1, profiles/r01_probe.txt; the six tools/probe_run.py still runs stay compiled)
+    ZKB_RB(32) ZKB_RB(-1) ZKB_RB(0) ZKB_RB(1) ZKB_RB(2) ZKB_RB(17)
     return -2;
 }
 
